@@ -1,0 +1,700 @@
+// The C ABI of libtfel_cuda.so (include/tfel_cuda.h): argument checking, host <-> device staging and error
+// translation around the device implementation in mesh.cu / fes.cu / pattern.cu / assemble.cu / solver.cu /
+// spmv.cu / krylov.cu. No entry point computes anything on the host: without a CUDA device every call fails.
+#include "structs.cuh"
+#include "solver.cuh"
+
+#include <exception>
+#include <new>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const tfelcu::Error& e) {
+    g_last_error = e.what();
+    return 1;
+  } catch (const std::bad_alloc&) {
+    g_last_error = "out of host memory";
+    return 2;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return 3;
+  }
+}
+
+using tfelcu::Ctx;
+using tfelcu::DevBuf;
+using tfelcu::fail;
+
+// device view of a caller buffer that may live on the host: copies it when needed
+template <typename T>
+struct Staged {
+  const T* p = nullptr;
+  DevBuf<T> own;
+  Staged(Ctx* ctx, const T* src, size_t n) {
+    if (!n || !src) return;
+    if (tfelcu::is_device_pointer(src)) { p = src; return; }
+    own.alloc(n);
+    ctx->upload(own.p, src, n);
+    p = own.p;
+  }
+};
+
+template <typename T>
+void copy_out(Ctx* ctx, T* dst, const T* d_src, size_t n) {
+  if (!n || !dst) return;
+  TFELCU_CK(cudaMemcpyAsync(dst, d_src, n * sizeof(T), cudaMemcpyDefault, ctx->stream));
+  ctx->sync();
+}
+
+void fill_space(tfelcu::SpaceList& L, int n, tfelcu_fes* const* list, const char* what) {
+  TFELCU_REQUIRE(n >= 1 && n <= tfelcu::kMaxComp, std::string(what) + ": between 1 and 4 component spaces");
+  L.n = n;
+  size_t off = 0;
+  for (int c = 0; c < n; ++c) {
+    TFELCU_REQUIRE(list[c] != nullptr, std::string(what) + ": null space");
+    TFELCU_REQUIRE(list[c]->mesh == list[0]->mesh, std::string(what) + ": component spaces live on different meshes");
+    L.fes[c] = list[c];
+    L.offset[c] = off;
+    off += list[c]->n_dof;
+  }
+  L.offset[n] = off;
+}
+
+void use_device(const Ctx* ctx) { TFELCU_CK(cudaSetDevice(ctx->device)); }
+
+}  // namespace
+
+extern "C" {
+
+const char* tfelcu_last_error(void) { return g_last_error.c_str(); }
+const char* tfelcu_version(void) { return "tfel_b200 0.1 (sm_100a)"; }
+
+// ---- context ---------------------------------------------------------------------------------
+
+static void ctx_init(tfelcu_ctx* c, int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    fail("no CUDA device: libtfel_cuda has no CPU fallback");
+  }
+  TFELCU_REQUIRE(device >= 0 && device < count, "device index out of range");
+  c->device = device;
+  TFELCU_CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  TFELCU_CK(cudaGetDeviceProperties(&prop, device));
+  TFELCU_REQUIRE(prop.major >= 10, "libtfel_cuda is built for sm_100a (Blackwell) only");
+  c->sm_count = prop.multiProcessorCount;
+  TFELCU_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+}
+
+int tfelcu_ctx_create(int device, tfelcu_ctx** ctx) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx != nullptr, "null output pointer");
+    std::unique_ptr<tfelcu_ctx> c(new tfelcu_ctx());
+    ctx_init(c.get(), device);
+    *ctx = c.release();
+  });
+}
+
+int tfelcu_nccl_unique_id(void* out128) {
+  return guarded([&] {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    TFELCU_NCCL(ncclGetUniqueId(&id));
+    std::memcpy(out128, &id, sizeof(id));
+  });
+}
+
+int tfelcu_ctx_create_distributed(int device, int rank, int n_ranks, const void* nccl_unique_id128, tfelcu_ctx** ctx) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx != nullptr && nccl_unique_id128 != nullptr, "null pointer");
+    TFELCU_REQUIRE(n_ranks >= 1 && rank >= 0 && rank < n_ranks, "rank out of range");
+    std::unique_ptr<tfelcu_ctx> c(new tfelcu_ctx());
+    ctx_init(c.get(), device);
+    c->rank = rank; c->n_ranks = n_ranks;
+    ncclUniqueId id;
+    std::memcpy(&id, nccl_unique_id128, sizeof(id));
+    TFELCU_NCCL(ncclCommInitRank(&c->comm, n_ranks, id, rank));
+    *ctx = c.release();
+  });
+}
+
+int tfelcu_ctx_destroy(tfelcu_ctx* ctx) {
+  return guarded([&] {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) ncclCommDestroy(ctx->comm);
+    ctx->table_scratch.release();
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+  });
+}
+
+int tfelcu_ctx_set_stream(tfelcu_ctx* ctx, void* cuda_stream) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx != nullptr, "null context");
+    ctx->sync();
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    ctx->own_stream = false;
+  });
+}
+
+void* tfelcu_ctx_stream(tfelcu_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
+
+int tfelcu_ctx_synchronize(tfelcu_ctx* ctx) {
+  return guarded([&] { TFELCU_REQUIRE(ctx != nullptr, "null context"); use_device(ctx); ctx->sync(); });
+}
+
+int tfelcu_ctx_rank(const tfelcu_ctx* ctx, int* rank, int* n_ranks) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx != nullptr, "null context");
+    if (rank) *rank = ctx->rank;
+    if (n_ranks) *n_ranks = ctx->n_ranks;
+  });
+}
+
+uint64_t tfelcu_ctx_launch_count(const tfelcu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- mesh --------------------------------------------------------------------------------------
+
+int tfelcu_mesh_create(tfelcu_ctx* ctx, int dim, const double* vertices, size_t n_vertices, const uint32_t* cells,
+                       size_t n_cells, tfelcu_mesh** mesh) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx && mesh, "null pointer");
+    TFELCU_REQUIRE(dim == 2 || dim == 3, "meshes of triangles (dim 2) or tetrahedra (dim 3) only");
+    TFELCU_REQUIRE(n_vertices < 0xffffffffull, "too many vertices");
+    TFELCU_REQUIRE((vertices || !n_vertices) && (cells || !n_cells), "null mesh arrays");
+    use_device(ctx);
+    std::unique_ptr<tfelcu_mesh> m(new tfelcu_mesh());
+    m->ctx = ctx; m->dim = dim; m->V = n_vertices; m->K = n_cells;
+    m->vertices.alloc(n_vertices * dim); m->cells.alloc(n_cells * (dim + 1));
+    TFELCU_CK(cudaMemcpyAsync(m->vertices.p, vertices, n_vertices * dim * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    TFELCU_CK(cudaMemcpyAsync(m->cells.p, cells, n_cells * (dim + 1) * sizeof(uint32_t), cudaMemcpyDefault, ctx->stream));
+    ctx->sync();
+    tfelcu::mesh_validate_cells(m.get());
+    *mesh = m.release();
+  });
+}
+
+int tfelcu_mesh_gen_square(tfelcu_ctx* ctx, double x1, double x2, uint32_t n1, uint32_t n2, tfelcu_mesh** mesh) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx && mesh, "null pointer");
+    TFELCU_REQUIRE(n1 >= 1 && n2 >= 1, "gen_square_mesh: at least one cell per direction");
+    use_device(ctx);
+    std::unique_ptr<tfelcu_mesh> m(new tfelcu_mesh());
+    m->ctx = ctx;
+    tfelcu::mesh_generate_square(m.get(), x1, x2, n1, n2);
+    *mesh = m.release();
+  });
+}
+
+int tfelcu_mesh_gen_cube(tfelcu_ctx* ctx, double x1, double x2, double x3, uint32_t n1, uint32_t n2, uint32_t n3,
+                         tfelcu_mesh** mesh) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx && mesh, "null pointer");
+    TFELCU_REQUIRE(n1 >= 1 && n2 >= 1 && n3 >= 1, "gen_cube_mesh: at least one cell per direction");
+    use_device(ctx);
+    std::unique_ptr<tfelcu_mesh> m(new tfelcu_mesh());
+    m->ctx = ctx;
+    tfelcu::mesh_generate_cube(m.get(), x1, x2, x3, n1, n2, n3);
+    *mesh = m.release();
+  });
+}
+
+int tfelcu_mesh_destroy(tfelcu_mesh* mesh) {
+  return guarded([&] { if (mesh) { use_device(mesh->ctx); mesh->ctx->sync(); delete mesh; } });
+}
+
+int tfelcu_mesh_info(const tfelcu_mesh* mesh, int* dim, size_t* n_vertices, size_t* n_cells) {
+  return guarded([&] {
+    TFELCU_REQUIRE(mesh != nullptr, "null mesh");
+    if (dim) *dim = mesh->dim;
+    if (n_vertices) *n_vertices = mesh->V;
+    if (n_cells) *n_cells = mesh->K;
+  });
+}
+
+int tfelcu_mesh_download(const tfelcu_mesh* mesh, double* vertices, uint32_t* cells) {
+  return guarded([&] {
+    TFELCU_REQUIRE(mesh != nullptr, "null mesh");
+    use_device(mesh->ctx);
+    copy_out(mesh->ctx, vertices, mesh->vertices.p, mesh->V * mesh->dim);
+    copy_out(mesh->ctx, cells, mesh->cells.p, mesh->K * (mesh->dim + 1));
+  });
+}
+
+int tfelcu_mesh_geometry(const tfelcu_mesh* mesh, double* vol, double* jmt) {
+  return guarded([&] {
+    TFELCU_REQUIRE(mesh && vol && jmt, "null pointer");
+    use_device(mesh->ctx);
+    tfelcu::mesh_geometry(mesh, vol, jmt);
+  });
+}
+
+int tfelcu_mesh_boundary(tfelcu_mesh* mesh, size_t* n_faces) {
+  return guarded([&] {
+    TFELCU_REQUIRE(mesh != nullptr, "null mesh");
+    use_device(mesh->ctx);
+    tfelcu::mesh_build_boundary(mesh);
+    if (n_faces) *n_faces = mesh->F;
+  });
+}
+
+int tfelcu_mesh_boundary_download(const tfelcu_mesh* mesh, uint32_t* el, uint32_t* parent_cell, uint32_t* parent_subdomain) {
+  return guarded([&] {
+    TFELCU_REQUIRE(mesh && mesh->has_boundary, "call tfelcu_mesh_boundary first");
+    use_device(mesh->ctx);
+    copy_out(mesh->ctx, el, mesh->b_el.p, mesh->F * mesh->dim);
+    copy_out(mesh->ctx, parent_cell, mesh->b_cell.p, mesh->F);
+    copy_out(mesh->ctx, parent_subdomain, mesh->b_sd.p, mesh->F);
+  });
+}
+
+// ---- finite element space -------------------------------------------------------------------------
+
+int tfelcu_fes_create(tfelcu_ctx* ctx, tfelcu_mesh* mesh, int fe, tfelcu_fes** fes) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx && mesh && fes, "null pointer");
+    TFELCU_REQUIRE(mesh->ctx == ctx, "mesh belongs to another context");
+    TFELCU_REQUIRE(fe == TFELCU_FE_P1 || fe == TFELCU_FE_P1_BUBBLE || fe == TFELCU_FE_P2, "unknown finite element id");
+    use_device(ctx);
+    std::unique_ptr<tfelcu_fes> f(new tfelcu_fes());
+    f->ctx = ctx; f->mesh = mesh; f->fe = fe;
+    tfelcu::fes_build(f.get());
+    *fes = f.release();
+  });
+}
+
+int tfelcu_fes_destroy(tfelcu_fes* fes) {
+  return guarded([&] { if (fes) { use_device(fes->ctx); fes->ctx->sync(); delete fes; } });
+}
+
+int tfelcu_fes_info(const tfelcu_fes* fes, int* fe, size_t* n_dof, int* n_dof_per_cell) {
+  return guarded([&] {
+    TFELCU_REQUIRE(fes != nullptr, "null space");
+    if (fe) *fe = fes->fe;
+    if (n_dof) *n_dof = fes->n_dof;
+    if (n_dof_per_cell) *n_dof_per_cell = fes->nd;
+  });
+}
+
+int tfelcu_fes_download_dof_map(const tfelcu_fes* fes, uint32_t* dof_map) {
+  return guarded([&] {
+    TFELCU_REQUIRE(fes && dof_map, "null pointer");
+    use_device(fes->ctx);
+    copy_out(fes->ctx, dof_map, fes->dof_map, fes->mesh->K * (size_t)fes->nd);
+  });
+}
+
+int tfelcu_fes_download_g2l(const tfelcu_fes* fes, uint32_t* g2l) {
+  return guarded([&] {
+    TFELCU_REQUIRE(fes && g2l, "null pointer");
+    use_device(fes->ctx);
+    copy_out(fes->ctx, g2l, fes->g2l.p, fes->n_dof * 2);
+  });
+}
+
+int tfelcu_fes_dof_coordinates(const tfelcu_fes* fes, const uint32_t* dofs, size_t n, double* x) {
+  return guarded([&] {
+    TFELCU_REQUIRE(fes && (x || !n) && (dofs || !n), "null pointer");
+    if (!n) return;
+    use_device(fes->ctx);
+    Ctx* ctx = fes->ctx;
+    Staged<uint32_t> d(ctx, dofs, n);
+    DevBuf<double> out(n * fes->mesh->dim);
+    tfelcu::fes_dof_coordinates(fes, d.p, n, out.p);
+    copy_out(ctx, x, out.p, n * fes->mesh->dim);
+  });
+}
+
+int tfelcu_fes_boundary_dofs(tfelcu_fes* fes, const uint32_t* bcells, size_t n_bcells, int nvb, size_t* n) {
+  return guarded([&] {
+    TFELCU_REQUIRE(fes != nullptr, "null space");
+    use_device(fes->ctx);
+    Ctx* ctx = fes->ctx;
+    if (!bcells) {
+      tfelcu::mesh_build_boundary(fes->mesh);
+      tfelcu::fes_boundary_dofs(fes, fes->mesh->b_el.p, fes->mesh->F, fes->mesh->dim);
+    } else {
+      Staged<uint32_t> b(ctx, bcells, n_bcells * (size_t)nvb);
+      tfelcu::fes_boundary_dofs(fes, b.p, n_bcells, nvb);
+      ctx->sync();
+    }
+    if (n) *n = fes->n_cand;
+  });
+}
+
+int tfelcu_fes_boundary_dofs_get(const tfelcu_fes* fes, uint32_t* dofs, double* x) {
+  return guarded([&] {
+    TFELCU_REQUIRE(fes != nullptr, "null space");
+    use_device(fes->ctx);
+    Ctx* ctx = fes->ctx;
+    copy_out(ctx, dofs, fes->cand.p, fes->n_cand);
+    if (x && fes->n_cand) {
+      DevBuf<double> out(fes->n_cand * fes->mesh->dim);
+      tfelcu::fes_dof_coordinates(fes, fes->cand.p, fes->n_cand, out.p);
+      copy_out(ctx, x, out.p, fes->n_cand * fes->mesh->dim);
+    }
+  });
+}
+
+int tfelcu_fes_add_dirichlet(tfelcu_fes* fes, const uint32_t* dofs, const double* values, size_t n) {
+  return guarded([&] {
+    TFELCU_REQUIRE(fes && (dofs || !n) && (values || !n), "null pointer");
+    if (!n) return;
+    use_device(fes->ctx);
+    Ctx* ctx = fes->ctx;
+    Staged<uint32_t> d(ctx, dofs, n);
+    Staged<double> v(ctx, values, n);
+    tfelcu::fes_add_dirichlet(fes, d.p, v.p, 0.0, n);
+  });
+}
+
+int tfelcu_fes_add_dirichlet_const(tfelcu_fes* fes, double value) {
+  return guarded([&] {
+    TFELCU_REQUIRE(fes != nullptr, "null space");
+    use_device(fes->ctx);
+    tfelcu::fes_add_dirichlet(fes, fes->cand.p, nullptr, value, fes->n_cand);
+  });
+}
+
+int tfelcu_fes_dirichlet_count(const tfelcu_fes* fes, size_t* n) {
+  return guarded([&] { TFELCU_REQUIRE(fes && n, "null pointer"); *n = fes->n_dirichlet; });
+}
+
+int tfelcu_fes_dirichlet_get(const tfelcu_fes* fes, uint32_t* dofs, double* values) {
+  return guarded([&] {
+    TFELCU_REQUIRE(fes != nullptr, "null space");
+    use_device(fes->ctx);
+    tfelcu::fes_dirichlet_get(fes, dofs, values);
+  });
+}
+
+// ---- bilinear form / matrix -----------------------------------------------------------------------
+
+int tfelcu_matrix_create(tfelcu_ctx* ctx, int n_test, tfelcu_fes* const* test, int n_trial, tfelcu_fes* const* trial,
+                         tfelcu_matrix** m) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx && test && trial && m, "null pointer");
+    use_device(ctx);
+    std::unique_ptr<tfelcu_matrix> A(new tfelcu_matrix());
+    A->ctx = ctx;
+    fill_space(A->test, n_test, test, "test space");
+    fill_space(A->trial, n_trial, trial, "trial space");
+    TFELCU_REQUIRE(A->test.fes[0]->mesh == A->trial.fes[0]->mesh, "test and trial spaces live on different meshes");
+    A->mesh = A->test.fes[0]->mesh;
+    A->n_rows = A->test.total(); A->n_cols = A->trial.total();
+    tfelcu::matrix_snapshot_dirichlet(A.get());
+    tfelcu::matrix_build_pattern(A.get());
+    ctx->sync();
+    *m = A.release();
+  });
+}
+
+int tfelcu_matrix_destroy(tfelcu_matrix* m) {
+  return guarded([&] { if (m) { use_device(m->ctx); m->ctx->sync(); delete m; } });
+}
+
+// clear() re-reads the Dirichlet sets of the test spaces (bilinear_form.hpp:159-165). When they changed since the
+// pattern was built the pattern changes with them (identity rows), exactly as a fresh std::map would.
+int tfelcu_matrix_clear(tfelcu_matrix* m) {
+  return guarded([&] {
+    TFELCU_REQUIRE(m != nullptr, "null matrix");
+    use_device(m->ctx);
+    bool changed = false;
+    for (int c = 0; c < m->test.n; ++c) changed = changed || (m->dir_version[c] != m->test.fes[c]->dirichlet_version);
+    if (changed) {
+      tfelcu::matrix_snapshot_dirichlet(m);
+      tfelcu::matrix_build_pattern(m);
+    }
+    m->val_valid = false;
+    m->pristine = true;
+  });
+}
+
+int tfelcu_matrix_info(const tfelcu_matrix* m, size_t* n_rows, size_t* n_cols, size_t* nnz) {
+  return guarded([&] {
+    TFELCU_REQUIRE(m != nullptr, "null matrix");
+    if (n_rows) *n_rows = m->n_rows;
+    if (n_cols) *n_cols = m->n_cols;
+    if (nnz) *nnz = m->nnz;
+  });
+}
+
+int tfelcu_matrix_set_scatter(tfelcu_matrix* m, int scatter) {
+  return guarded([&] {
+    TFELCU_REQUIRE(m != nullptr, "null matrix");
+    TFELCU_REQUIRE(scatter == TFELCU_SCATTER_ROW_GATHER || scatter == TFELCU_SCATTER_COLORED, "unknown scatter strategy");
+    m->scatter = scatter;
+  });
+}
+
+int tfelcu_matrix_assemble(tfelcu_matrix* m, int quad, const tfelcu_factor* factors, int n_factors,
+                           const tfelcu_term* terms, int n_terms) {
+  return guarded([&] {
+    TFELCU_REQUIRE(m && (terms || !n_terms) && (factors || !n_factors), "null pointer");
+    use_device(m->ctx);
+    tfelcu::assemble_bilinear(m, quad, factors, n_factors, terms, n_terms);
+  });
+}
+
+int tfelcu_matrix_download_csr(const tfelcu_matrix* m, int32_t* rowptr, int32_t* colind, double* val) {
+  return guarded([&] {
+    TFELCU_REQUIRE(m != nullptr, "null matrix");
+    use_device(m->ctx);
+    if (val) tfelcu::matrix_ensure_cleared(const_cast<tfelcu_matrix*>(m));
+    copy_out(m->ctx, rowptr, m->rowptr.p, m->n_rows + 1);
+    copy_out(m->ctx, colind, m->colind.p, m->nnz);
+    copy_out(m->ctx, val, m->val.p, m->nnz);
+  });
+}
+
+int tfelcu_matrix_color_count(tfelcu_matrix* m, int* n_colors) {
+  return guarded([&] {
+    TFELCU_REQUIRE(m && n_colors, "null pointer");
+    use_device(m->ctx);
+    tfelcu::matrix_build_colors(m);
+    *n_colors = m->n_colors;
+  });
+}
+
+// ---- linear form / vectors --------------------------------------------------------------------------
+
+int tfelcu_vector_create(tfelcu_ctx* ctx, int n_test, tfelcu_fes* const* test, tfelcu_vector** v) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx && test && v, "null pointer");
+    use_device(ctx);
+    std::unique_ptr<tfelcu_vector> b(new tfelcu_vector());
+    b->ctx = ctx;
+    fill_space(b->space, n_test, test, "test space");
+    b->data.alloc(b->space.total());
+    ctx->zero(b->data.p, b->space.total());
+    *v = b.release();
+  });
+}
+
+int tfelcu_vector_destroy(tfelcu_vector* v) {
+  return guarded([&] { if (v) { use_device(v->ctx); v->ctx->sync(); delete v; } });
+}
+
+int tfelcu_vector_clear(tfelcu_vector* v) {
+  return guarded([&] { TFELCU_REQUIRE(v != nullptr, "null vector"); use_device(v->ctx); v->ctx->zero(v->data.p, v->data.n); });
+}
+
+int tfelcu_vector_size(const tfelcu_vector* v, size_t* n) {
+  return guarded([&] { TFELCU_REQUIRE(v && n, "null pointer"); *n = v->data.n; });
+}
+
+int tfelcu_vector_assemble(tfelcu_vector* v, int quad, const tfelcu_factor* factors, int n_factors,
+                           const tfelcu_term* terms, int n_terms) {
+  return guarded([&] {
+    TFELCU_REQUIRE(v && (terms || !n_terms) && (factors || !n_factors), "null pointer");
+    use_device(v->ctx);
+    tfelcu::assemble_linear(v, quad, factors, n_factors, terms, n_terms);
+  });
+}
+
+int tfelcu_vector_download(const tfelcu_vector* v, double* host) {
+  return guarded([&] {
+    TFELCU_REQUIRE(v && host, "null pointer");
+    use_device(v->ctx);
+    copy_out(v->ctx, host, v->data.p, v->data.n);
+  });
+}
+
+int tfelcu_vector_upload(tfelcu_vector* v, const double* host) {
+  return guarded([&] {
+    TFELCU_REQUIRE(v && host, "null pointer");
+    use_device(v->ctx);
+    TFELCU_CK(cudaMemcpyAsync(v->data.p, host, v->data.n * sizeof(double), cudaMemcpyDefault, v->ctx->stream));
+    v->ctx->sync();
+  });
+}
+
+double* tfelcu_vector_device_ptr(tfelcu_vector* v) { return v ? v->data.p : nullptr; }
+
+int tfelcu_integrate(tfelcu_ctx* ctx, tfelcu_mesh* mesh, int quad, const tfelcu_factor* factors, int n_factors,
+                     const tfelcu_term* terms, int n_terms, double* result) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx && mesh && result && (terms || !n_terms), "null pointer");
+    use_device(ctx);
+    *result = tfelcu::integrate_scalar(ctx, mesh, quad, factors, n_factors, terms, n_terms);
+  });
+}
+
+// ---- solver --------------------------------------------------------------------------------------
+
+int tfelcu_solver_create(tfelcu_ctx* ctx, const tfelcu_solver_params* params, tfelcu_solver** s) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx && params && s, "null pointer");
+    TFELCU_REQUIRE(params->method == TFELCU_METHOD_CG || params->method == TFELCU_METHOD_GMRES, "unknown Krylov method");
+    TFELCU_REQUIRE(params->precond >= TFELCU_PC_NONE && params->precond <= TFELCU_PC_ILU0, "unknown preconditioner");
+    TFELCU_REQUIRE(params->rtol >= 0.0 && params->atol >= 0.0, "negative tolerance");
+    std::unique_ptr<tfelcu_solver> S(new tfelcu_solver());
+    S->ctx = ctx; S->params = *params;
+    *s = S.release();
+  });
+}
+
+int tfelcu_solver_destroy(tfelcu_solver* s) {
+  return guarded([&] { if (s) { use_device(s->ctx); s->ctx->sync(); delete s; } });
+}
+
+int tfelcu_solver_set_operator(tfelcu_solver* s, tfelcu_matrix* m) {
+  return guarded([&] {
+    TFELCU_REQUIRE(s && m, "null pointer");
+    TFELCU_REQUIRE(m->n_rows == m->n_cols, "the operator of a linear solve must be square");
+    use_device(s->ctx);
+    tfelcu::matrix_ensure_cleared(m);
+    s->own_rowptr.release(); s->own_colind.release(); s->own_val.release();
+    s->n = m->n_rows; s->nnz = m->nnz;
+    s->rowptr = m->rowptr.p; s->colind = m->colind.p; s->val = m->val.p;
+    tfelcu::solver_setup(s);
+  });
+}
+
+int tfelcu_solver_set_operator_csr(tfelcu_solver* s, size_t n, const int32_t* rowptr, const int32_t* colind, const double* val) {
+  return guarded([&] {
+    TFELCU_REQUIRE(s && rowptr && (colind || !n) && (val || !n), "null pointer");
+    use_device(s->ctx);
+    Ctx* ctx = s->ctx;
+    int32_t nnz = 0;
+    TFELCU_CK(cudaMemcpyAsync(&nnz, rowptr + n, sizeof(int32_t), cudaMemcpyDefault, ctx->stream));
+    ctx->sync();
+    TFELCU_REQUIRE(nnz >= 0, "corrupt row pointer array");
+    s->own_rowptr.alloc(n + 1); s->own_colind.alloc((size_t)nnz); s->own_val.alloc((size_t)nnz);
+    TFELCU_CK(cudaMemcpyAsync(s->own_rowptr.p, rowptr, (n + 1) * sizeof(int32_t), cudaMemcpyDefault, ctx->stream));
+    if (nnz) {
+      TFELCU_CK(cudaMemcpyAsync(s->own_colind.p, colind, (size_t)nnz * sizeof(int32_t), cudaMemcpyDefault, ctx->stream));
+      TFELCU_CK(cudaMemcpyAsync(s->own_val.p, val, (size_t)nnz * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    }
+    ctx->sync();
+    s->n = n; s->nnz = (size_t)nnz;
+    s->rowptr = s->own_rowptr.p; s->colind = s->own_colind.p; s->val = s->own_val.p;
+    tfelcu::solver_setup(s);
+  });
+}
+
+int tfelcu_solver_solve(tfelcu_solver* s, const double* rhs, double* x, tfelcu_solver_report* report) {
+  return guarded([&] {
+    TFELCU_REQUIRE(s && rhs && x, "null pointer");
+    use_device(s->ctx);
+    Ctx* ctx = s->ctx;
+    tfelcu_solver_report local;
+    tfelcu_solver_report* rep = report ? report : &local;
+    Staged<double> b(ctx, rhs, s->n);
+    if (tfelcu::is_device_pointer(x)) {
+      tfelcu::solver_solve(s, b.p, x, rep);
+    } else {
+      DevBuf<double> dx(s->n);
+      tfelcu::solver_solve(s, b.p, dx.p, rep);
+      copy_out(ctx, x, dx.p, s->n);
+    }
+  });
+}
+
+// rhs of bilinear_form::solve: b with the Dirichlet rows replaced by their values (bilinear_form.hpp:126-137)
+namespace {
+__global__ void k_make_rhs(const double* __restrict__ b, const uint8_t* __restrict__ dir_row,
+                           const double* __restrict__ dir_value, size_t n, double* __restrict__ rhs) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) rhs[i] = dir_row[i] ? dir_value[i] : b[i];
+}
+
+void make_rhs(const tfelcu_matrix* m, const tfelcu_vector* b, double* d_rhs) {
+  TFELCU_REQUIRE(b->data.n == m->n_rows, "linear form and bilinear form have different test spaces");
+  Ctx* ctx = m->ctx;
+  k_make_rhs<<<tfelcu::grid_for(m->n_rows, 256), 256, 0, ctx->stream>>>(b->data.p, m->dir_row.p, m->dir_value.p, m->n_rows, d_rhs);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+}
+}  // namespace
+
+int tfelcu_matrix_make_rhs(const tfelcu_matrix* m, const tfelcu_vector* b, double* rhs) {
+  return guarded([&] {
+    TFELCU_REQUIRE(m && b && rhs, "null pointer");
+    use_device(m->ctx);
+    DevBuf<double> d(m->n_rows);
+    make_rhs(m, b, d.p);
+    copy_out(m->ctx, rhs, d.p, m->n_rows);
+  });
+}
+
+int tfelcu_matrix_solve(tfelcu_matrix* m, const tfelcu_vector* b, tfelcu_solver* s, double* x, tfelcu_solver_report* report) {
+  return guarded([&] {
+    TFELCU_REQUIRE(m && b && s && x, "null pointer");
+    TFELCU_REQUIRE(m->n_rows == m->n_cols, "the operator of a linear solve must be square");
+    use_device(m->ctx);
+    Ctx* ctx = m->ctx;
+    // s.set_operator(a) on every solve, like bilinear_form.hpp:139
+    tfelcu::matrix_ensure_cleared(m);
+    s->own_rowptr.release(); s->own_colind.release(); s->own_val.release();
+    s->n = m->n_rows; s->nnz = m->nnz;
+    s->rowptr = m->rowptr.p; s->colind = m->colind.p; s->val = m->val.p;
+    tfelcu::solver_setup(s);
+    tfelcu_solver_report local;
+    tfelcu_solver_report* rep = report ? report : &local;
+    DevBuf<double> rhs(m->n_rows);
+    make_rhs(m, b, rhs.p);
+    if (tfelcu::is_device_pointer(x)) {
+      tfelcu::solver_solve(s, rhs.p, x, rep);
+    } else {
+      DevBuf<double> dx(m->n_rows);
+      tfelcu::solver_solve(s, rhs.p, dx.p, rep);
+      copy_out(ctx, x, dx.p, m->n_rows);
+    }
+  });
+}
+
+int tfelcu_solver_spmv(tfelcu_solver* s, const double* x, double* y) {
+  return guarded([&] {
+    TFELCU_REQUIRE(s && x && y, "null pointer");
+    TFELCU_REQUIRE(s->rowptr != nullptr, "solver has no operator: call set_operator first");
+    use_device(s->ctx);
+    Ctx* ctx = s->ctx;
+    Staged<double> dx(ctx, x, s->n);
+    if (tfelcu::is_device_pointer(y)) {
+      tfelcu::solver_spmv(s, dx.p, y);
+      ctx->sync();
+    } else {
+      DevBuf<double> dy(s->n);
+      tfelcu::solver_spmv(s, dx.p, dy.p);
+      copy_out(ctx, y, dy.p, s->n);
+    }
+  });
+}
+
+int tfelcu_solver_spmv_bench(tfelcu_solver* s, int reps, double* avg_ms, double* algorithmic_bytes) {
+  return guarded([&] {
+    TFELCU_REQUIRE(s && avg_ms, "null pointer");
+    TFELCU_REQUIRE(s->rowptr != nullptr, "solver has no operator: call set_operator first");
+    TFELCU_REQUIRE(reps >= 1, "at least one repetition");
+    use_device(s->ctx);
+    Ctx* ctx = s->ctx;
+    // x = the solver's p work vector filled with ones through the initial-guess path is not needed: any data
+    ctx->zero(s->p.p, s->n);
+    cudaEvent_t e0, e1;
+    TFELCU_CK(cudaEventCreate(&e0)); TFELCU_CK(cudaEventCreate(&e1));
+    tfelcu::solver_spmv(s, s->p.p, s->q.p);   // warm-up
+    TFELCU_CK(cudaEventRecord(e0, ctx->stream));
+    for (int r = 0; r < reps; ++r) tfelcu::solver_spmv(s, s->p.p, s->q.p);
+    TFELCU_CK(cudaEventRecord(e1, ctx->stream));
+    TFELCU_CK(cudaEventSynchronize(e1));
+    float ms = 0.f; TFELCU_CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *avg_ms = (double)ms / reps;
+    if (algorithmic_bytes) *algorithmic_bytes = 12.0 * (double)s->nnz + 4.0 * (double)(s->n + 1) + 16.0 * (double)s->n;
+  });
+}
+
+}  // extern "C"

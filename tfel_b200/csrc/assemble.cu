@@ -1,0 +1,744 @@
+// Element assembly on device: bilinear_form::operator+= (src/core/bilinear_form.hpp:23-110, composite:
+// composite_bilinear_form.hpp:68-184), linear_form::operator+= (linear_form.hpp:20-142, composite:
+// composite_linear_form.hpp:38-143) and the rank-0 integrate (form.hpp:87-125).
+//
+// The integrand arrives in sum-of-products form (include/tfel_cuda.h: tfelcu_term). Two scatter strategies,
+// both free of atomics and bitwise reproducible:
+//   * owner-computes rows (default): one thread per matrix row walks the cells incident to its dof in
+//     ascending cell order -- the order in which the reference's cell loop adds into its std::map -- and
+//     recomputes its row of each element matrix; every stored value is written exactly once per +=.
+//   * colour-by-colour scatter: cells of one colour share no test dof; one launch per colour, one thread
+//     per cell, read-modify-write into the CSR values.
+// Reference-element tables (quadrature weights, basis values / gradients, and for constant-coefficient
+// forms the pre-integrated reference tensor) are staged in shared memory; per-cell Jacobians are recomputed
+// from the vertex coordinates (no J^{-T} array is materialised, cf. mesh.hpp:581-586).
+#include "structs.cuh"
+#include "geometry.cuh"
+
+namespace tfelcu {
+
+constexpr int kMaxTerms = 16;
+constexpr int kMaxFactors = 8;
+constexpr int kMaxProgOps = 48;
+
+struct DevFactor {
+  int kind, d;
+  int nd;                    // FIELD: dofs per cell of the field's element
+  int tab_off;               // FIELD: offset (doubles) of hat[nq][nd][DIM+1] in the tables buffer
+  const uint32_t* dof_map;   // FIELD
+  const double* data;        // FIELD: coefficients; TABLE: [K][nq]
+  int prog_off, prog_len;    // PROGRAM
+};
+
+struct DevTerm {
+  int test_d, trial_d, n_factors;
+  int factor[5];
+  double c;
+};
+
+struct FormDev {
+  int nq, n_terms, n_factors, pad;
+  int off_w, off_xhat, off_hat_te, off_hat_tr, off_ref, n_stage;
+  const double* tables;
+  DevTerm terms[kMaxTerms];
+  DevFactor factors[kMaxFactors];
+  tfelcu_op prog[kMaxProgOps];
+};
+
+// ------------------------------------------------------------------------------------------
+// device pieces
+// ------------------------------------------------------------------------------------------
+
+template <int DIM>
+__device__ __forceinline__ double run_program(const FormDev& F, int off, int len, const double* x) {
+  double st[8];
+  int sp = 0;
+  for (int p = 0; p < len; ++p) {
+    const tfelcu_op o = F.prog[off + p];
+    switch (o.op) {
+      case TFELCU_OP_CONST: st[sp++] = o.imm; break;
+      case TFELCU_OP_COORD: st[sp++] = x[(int)o.imm < DIM ? (int)o.imm : 0]; break;
+      case TFELCU_OP_ADD: --sp; st[sp - 1] = st[sp - 1] + st[sp]; break;
+      case TFELCU_OP_SUB: --sp; st[sp - 1] = st[sp - 1] - st[sp]; break;
+      case TFELCU_OP_MUL: --sp; st[sp - 1] = st[sp - 1] * st[sp]; break;
+      case TFELCU_OP_DIV: --sp; st[sp - 1] = st[sp - 1] / st[sp]; break;
+      case TFELCU_OP_NEG: st[sp - 1] = -st[sp - 1]; break;
+      case TFELCU_OP_SQRT: st[sp - 1] = sqrt(st[sp - 1]); break;
+      case TFELCU_OP_EXP: st[sp - 1] = exp(st[sp - 1]); break;
+      case TFELCU_OP_SIN: st[sp - 1] = sin(st[sp - 1]); break;
+      case TFELCU_OP_COS: st[sp - 1] = cos(st[sp - 1]); break;
+      case TFELCU_OP_POW: --sp; st[sp - 1] = pow(st[sp - 1], st[sp]); break;
+      case TFELCU_OP_LT: --sp; st[sp - 1] = st[sp - 1] < st[sp] ? 1.0 : 0.0; break;
+      case TFELCU_OP_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
+      default: break;
+    }
+  }
+  return st[0];
+}
+
+// values of all coefficient factors at quadrature point q of cell k
+template <int DIM>
+__device__ __forceinline__ void eval_factors(const FormDev& F, const double* sm, size_t k, int q,
+                                             const CellGeom<DIM>& g, double* fv) {
+  constexpr int W = DIM + 1;
+  for (int f = 0; f < F.n_factors; ++f) {
+    const DevFactor& fa = F.factors[f];
+    double v = 1.0;
+    if (fa.kind == TFELCU_FACTOR_TABLE) {
+      v = __ldg(fa.data + k * F.nq + q);
+    } else if (fa.kind == TFELCU_FACTOR_FIELD) {
+      // finite_element_function::prepare (expression.hpp:114-128): sum_i coef[dof(k, i)] * phi_i[d](x_q)
+      const double* hat = F.tables + fa.tab_off + (size_t)q * fa.nd * W;
+      v = 0.0;
+      for (int i = 0; i < fa.nd; ++i) {
+        const double c = __ldg(fa.data + fa.dof_map[k * fa.nd + i]);
+        double b;
+        if (fa.d == 0) b = __ldg(hat + i * W);
+        else {
+          b = 0.0;
+#pragma unroll
+          for (int t = 0; t < DIM; ++t) b += g.jmt[(fa.d - 1) < DIM ? (fa.d - 1) : 0][t] * __ldg(hat + i * W + 1 + t);
+        }
+        v += c * b;
+      }
+    } else if (fa.kind == TFELCU_FACTOR_PROGRAM) {
+      // x_q = v0 + J xhat_q (cell.hpp:456-468)
+      const double* xh = sm + F.off_xhat + q * DIM;
+      double x[DIM];
+#pragma unroll
+      for (int r = 0; r < DIM; ++r) {
+        double acc = g.v0[r];
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) acc += xh[c] * g.J[r][c];
+        x[r] = acc;
+      }
+      v = run_program<DIM>(F, fa.prog_off, fa.prog_len, x);
+    }
+    fv[f] = v;
+  }
+}
+
+__device__ __forceinline__ double term_coefficient(const DevTerm& t, const double* fv) {
+  double c = t.c;
+  for (int f = 0; f < t.n_factors; ++f) c *= fv[t.factor[f]];
+  return c;
+}
+
+// reference-gradient weights of "derivative d of a basis function": D^d phi = sum_a T[a] hat[a]
+template <int DIM>
+__device__ __forceinline__ void pullback(int d, const CellGeom<DIM>& g, double (&T)[DIM + 1]) {
+  T[0] = d == 0 ? 1.0 : 0.0;
+#pragma unroll
+  for (int s = 0; s < DIM; ++s) {
+    double v = 0.0;
+#pragma unroll
+    for (int dd = 0; dd < DIM; ++dd) v = (d == dd + 1) ? g.jmt[dd][s] : v;
+    T[1 + s] = v;
+  }
+}
+
+// row i of the element matrix of cell k (without the |K| factor): acc[j], j = 0..ND_TR-1
+template <int DIM, int ND_TE, int ND_TR, bool CONST_COEF>
+__device__ __forceinline__ void element_row(const FormDev& F, const double* sm, size_t k, int i,
+                                            const CellGeom<DIM>& g, double (&acc)[ND_TR]) {
+  constexpr int W = DIM + 1;
+#pragma unroll
+  for (int j = 0; j < ND_TR; ++j) acc[j] = 0.0;
+  if constexpr (CONST_COEF) {
+    // sum_t c_t (T_t (x) R_t) : Mhat, Mhat[a][b][i][j] = sum_q w_q hat_te[q][i][a] hat_tr[q][j][b]
+    double G[W][W];
+#pragma unroll
+    for (int a = 0; a < W; ++a)
+#pragma unroll
+      for (int b = 0; b < W; ++b) G[a][b] = 0.0;
+    for (int t = 0; t < F.n_terms; ++t) {
+      double T[W], R[W];
+      pullback<DIM>(F.terms[t].test_d, g, T);
+      pullback<DIM>(F.terms[t].trial_d, g, R);
+      const double c = F.terms[t].c;
+#pragma unroll
+      for (int a = 0; a < W; ++a)
+#pragma unroll
+        for (int b = 0; b < W; ++b) G[a][b] += c * T[a] * R[b];
+    }
+    const double* ref = sm + F.off_ref;
+#pragma unroll
+    for (int a = 0; a < W; ++a)
+#pragma unroll
+      for (int b = 0; b < W; ++b) {
+        const double gab = G[a][b];
+        const double* mrow = ref + ((a * W + b) * ND_TE + i) * ND_TR;
+#pragma unroll
+        for (int j = 0; j < ND_TR; ++j) acc[j] += gab * mrow[j];
+      }
+  } else {
+    const double* wq = sm + F.off_w;
+    const double* hat_te = sm + F.off_hat_te;
+    const double* hat_tr = sm + F.off_hat_tr;
+    for (int q = 0; q < F.nq; ++q) {
+      // fe_value_manager::prepare (fe_value_manager.hpp:103-127) for the one test function of this row
+      const double* ht = hat_te + (q * ND_TE + i) * W;
+      double psi[W];
+      psi[0] = ht[0];
+#pragma unroll
+      for (int s = 0; s < DIM; ++s) {
+        double v = 0.0;
+#pragma unroll
+        for (int t = 0; t < DIM; ++t) v += g.jmt[s][t] * ht[1 + t];
+        psi[1 + s] = v;
+      }
+      double fv[kMaxFactors];
+      eval_factors<DIM>(F, sm, k, q, g, fv);
+      double Wv[W];
+#pragma unroll
+      for (int b = 0; b < W; ++b) Wv[b] = 0.0;
+      for (int t = 0; t < F.n_terms; ++t) {
+        const DevTerm& tm = F.terms[t];
+        double p = psi[0];
+#pragma unroll
+        for (int a = 1; a < W; ++a) p = (tm.test_d == a) ? psi[a] : p;
+        const double tw = wq[q] * term_coefficient(tm, fv) * p;
+#pragma unroll
+        for (int b = 0; b < W; ++b) Wv[b] += (tm.trial_d == b) ? tw : 0.0;
+      }
+      // D^b phi_j = sum_s jmt[b-1][s] hat_j[1+s]  =>  weights on the reference gradient
+      double Wh[W];
+      Wh[0] = Wv[0];
+#pragma unroll
+      for (int s = 0; s < DIM; ++s) {
+        double v = 0.0;
+#pragma unroll
+        for (int b = 0; b < DIM; ++b) v += g.jmt[b][s] * Wv[1 + b];
+        Wh[1 + s] = v;
+      }
+#pragma unroll
+      for (int j = 0; j < ND_TR; ++j) {
+        const double* hr = hat_tr + (q * ND_TR + j) * W;
+        double v = acc[j];
+#pragma unroll
+        for (int a = 0; a < W; ++a) v += Wh[a] * hr[a];
+        acc[j] = v;
+      }
+    }
+  }
+}
+
+// entry i of the element vector of cell k (without |K|)
+template <int DIM, int ND_TE, bool CONST_COEF>
+__device__ __forceinline__ double element_entry(const FormDev& F, const double* sm, size_t k, int i,
+                                                const CellGeom<DIM>& g) {
+  constexpr int W = DIM + 1;
+  double out = 0.0;
+  if constexpr (CONST_COEF) {
+    const double* ref = sm + F.off_ref;   // mhat[a][i] = sum_q w_q hat_te[q][i][a]
+    for (int t = 0; t < F.n_terms; ++t) {
+      double T[W];
+      pullback<DIM>(F.terms[t].test_d, g, T);
+      double v = 0.0;
+#pragma unroll
+      for (int a = 0; a < W; ++a) v += T[a] * ref[a * ND_TE + i];
+      out += F.terms[t].c * v;
+    }
+  } else {
+    const double* wq = sm + F.off_w;
+    const double* hat_te = sm + F.off_hat_te;
+    for (int q = 0; q < F.nq; ++q) {
+      const double* ht = hat_te + (q * ND_TE + i) * W;
+      double psi[W];
+      psi[0] = ht[0];
+#pragma unroll
+      for (int s = 0; s < DIM; ++s) {
+        double v = 0.0;
+#pragma unroll
+        for (int t = 0; t < DIM; ++t) v += g.jmt[s][t] * ht[1 + t];
+        psi[1 + s] = v;
+      }
+      double fv[kMaxFactors];
+      eval_factors<DIM>(F, sm, k, q, g, fv);
+      double f = 0.0;
+      for (int t = 0; t < F.n_terms; ++t) {
+        const DevTerm& tm = F.terms[t];
+        double p = psi[0];
+#pragma unroll
+        for (int a = 1; a < W; ++a) p = (tm.test_d == a) ? psi[a] : p;
+        f += term_coefficient(tm, fv) * p;
+      }
+      out += wq[q] * f;
+    }
+  }
+  return out;
+}
+
+__device__ __forceinline__ int find_in_row(const int32_t* __restrict__ colind, int rs, int re, int32_t col) {
+  int lo = rs, hi = re;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(colind + mid) < col) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+struct RowBlock {
+  const double* vertices; const uint32_t* cells;
+  const uint32_t* map_tr; uint32_t off_te, off_tr; size_t n_rows_comp;
+  const uint32_t* adj_ptr; const uint32_t* adj;
+  const uint8_t* dir_row; const int32_t* rowptr; const int32_t* colind; double* val;
+  int init_mode;   // STAGED only: 1 = values are uninitialised (pending clear()): write them fresh
+};
+
+template <int DIM, int ND_TE, int ND_TR, bool CONST_COEF, bool STAGED>
+__global__ void __launch_bounds__(kRowsPerCta) k_assemble_rows(const __grid_constant__ FormDev F, const RowBlock B) {
+  extern __shared__ double sm[];
+  for (int idx = threadIdx.x; idx < F.n_stage; idx += blockDim.x) sm[idx] = __ldg(F.tables + idx);
+  double* stage = sm + F.n_stage;
+  const size_t r0 = (size_t)blockIdx.x * kRowsPerCta;
+  size_t r1 = r0 + kRowsPerCta; if (r1 > B.n_rows_comp) r1 = B.n_rows_comp;
+  int seg0 = 0, seg_len = 0;
+  if constexpr (STAGED) {
+    seg0 = B.rowptr[B.off_te + r0];
+    seg_len = B.rowptr[B.off_te + r1] - seg0;
+    for (int e = threadIdx.x; e < seg_len; e += blockDim.x) stage[e] = 0.0;
+  }
+  __syncthreads();
+  const size_t r = r0 + threadIdx.x;
+  if (r < r1) {
+    const size_t grow = B.off_te + r;
+    const int rs = B.rowptr[grow], re = B.rowptr[grow + 1];
+    if (!B.dir_row[grow]) {
+      // bilinear_form.hpp:64-109 restricted to the cells that touch this row, in ascending cell order
+      for (uint32_t a = B.adj_ptr[r]; a < B.adj_ptr[r + 1]; ++a) {
+        const uint32_t code = B.adj[a];
+        const size_t k = code / ND_TE; const int i = (int)(code - k * ND_TE);
+        CellGeom<DIM> g;
+        load_cell_geometry<DIM>(B.vertices, B.cells + k * (DIM + 1), g);
+        double acc[ND_TR];
+        element_row<DIM, ND_TE, ND_TR, CONST_COEF>(F, sm, k, i, g, acc);
+#pragma unroll
+        for (int j = 0; j < ND_TR; ++j) {
+          const int32_t col = (int32_t)(B.off_tr + B.map_tr[k * ND_TR + j]);
+          const int pos = find_in_row(B.colind, rs, re, col);
+          if constexpr (STAGED) stage[pos - seg0] += acc[j] * g.vol;
+          else B.val[pos] += acc[j] * g.vol;
+        }
+      }
+    } else if (STAGED && B.init_mode) {
+      stage[find_in_row(B.colind, rs, re, (int32_t)grow) - seg0] = 1.0;   // clear(): bilinear_form.hpp:159-165
+    }
+  }
+  if constexpr (STAGED) {
+    __syncthreads();
+    if (B.init_mode) for (int e = threadIdx.x; e < seg_len; e += blockDim.x) B.val[seg0 + e] = stage[e];
+    else for (int e = threadIdx.x; e < seg_len; e += blockDim.x) B.val[seg0 + e] += stage[e];
+  }
+}
+
+struct ColorBlock {
+  const double* vertices; const uint32_t* cells;
+  const uint32_t* map_te; const uint32_t* map_tr; uint32_t off_te, off_tr;
+  const uint32_t* color_cells; size_t n_cells;
+  const uint8_t* dir_row; const int32_t* rowptr; const int32_t* colind; double* val;
+};
+
+template <int DIM, int ND_TE, int ND_TR, bool CONST_COEF>
+__global__ void __launch_bounds__(128) k_assemble_colored(const __grid_constant__ FormDev F, const ColorBlock B) {
+  extern __shared__ double sm[];
+  for (int idx = threadIdx.x; idx < F.n_stage; idx += blockDim.x) sm[idx] = __ldg(F.tables + idx);
+  __syncthreads();
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B.n_cells) return;
+  const size_t k = B.color_cells[t];
+  CellGeom<DIM> g;
+  load_cell_geometry<DIM>(B.vertices, B.cells + k * (DIM + 1), g);
+  for (int i = 0; i < ND_TE; ++i) {
+    const size_t grow = B.off_te + B.map_te[k * ND_TE + i];
+    if (B.dir_row[grow]) continue;   // bilinear_form.hpp:183-186
+    const int rs = B.rowptr[grow], re = B.rowptr[grow + 1];
+    double acc[ND_TR];
+    element_row<DIM, ND_TE, ND_TR, CONST_COEF>(F, sm, k, i, g, acc);
+#pragma unroll
+    for (int j = 0; j < ND_TR; ++j) {
+      const int32_t col = (int32_t)(B.off_tr + B.map_tr[k * ND_TR + j]);
+      B.val[find_in_row(B.colind, rs, re, col)] += acc[j] * g.vol;
+    }
+  }
+}
+
+struct VecBlock {
+  const double* vertices; const uint32_t* cells;
+  uint32_t off_te; size_t n_rows_comp;
+  const uint32_t* adj_ptr; const uint32_t* adj;
+  double* b;
+};
+
+template <int DIM, int ND_TE, bool CONST_COEF>
+__global__ void __launch_bounds__(128) k_assemble_vector_rows(const __grid_constant__ FormDev F, const VecBlock B) {
+  extern __shared__ double sm[];
+  for (int idx = threadIdx.x; idx < F.n_stage; idx += blockDim.x) sm[idx] = __ldg(F.tables + idx);
+  __syncthreads();
+  const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B.n_rows_comp) return;
+  double sum = 0.0;
+  // linear_form.hpp:55-63: ordered scatter == ascending cell order per dof
+  for (uint32_t a = B.adj_ptr[r]; a < B.adj_ptr[r + 1]; ++a) {
+    const uint32_t code = B.adj[a];
+    const size_t k = code / ND_TE; const int i = (int)(code - k * ND_TE);
+    CellGeom<DIM> g;
+    load_cell_geometry<DIM>(B.vertices, B.cells + k * (DIM + 1), g);
+    sum += element_entry<DIM, ND_TE, CONST_COEF>(F, sm, k, i, g) * g.vol;
+  }
+  B.b[B.off_te + r] += sum;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_integrate(const __grid_constant__ FormDev F, const double* __restrict__ vertices,
+                                                   const uint32_t* __restrict__ cells, size_t K,
+                                                   double* __restrict__ partial) {
+  extern __shared__ double sm[];
+  for (int idx = threadIdx.x; idx < F.n_stage; idx += blockDim.x) sm[idx] = __ldg(F.tables + idx);
+  __shared__ double red[256];
+  __syncthreads();
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double el = 0.0;
+  if (k < K) {
+    CellGeom<DIM> g;
+    load_cell_geometry<DIM>(vertices, cells + k * (DIM + 1), g);
+    const double* wq = sm + F.off_w;
+    for (int q = 0; q < F.nq; ++q) {   // form.hpp:113-121
+      double fv[kMaxFactors];
+      eval_factors<DIM>(F, sm, k, q, g, fv);
+      double f = 0.0;
+      for (int t = 0; t < F.n_terms; ++t) f += term_coefficient(F.terms[t], fv);
+      el += wq[q] * f;
+    }
+    el *= g.vol;
+  }
+  red[threadIdx.x] = el;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {   // fixed tree: reproducible
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ partial, size_t n, double* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (size_t i = threadIdx.x; i < n; i += 256) s += partial[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = red[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: lowering of the C-ABI description to FormDev
+// ------------------------------------------------------------------------------------------
+
+struct FormBuild {
+  FormDev F;
+  std::vector<double> tables;
+  std::vector<DevBuf<double>> keep;   // device copies of host-resident factor data
+  bool const_coef = true;
+};
+
+static void tabulate(int dim, int fe, const Quadrature& Q, std::vector<double>& out) {
+  const int nd = fe_ndof(dim, fe), w = dim + 1;
+  const size_t at = out.size();
+  out.resize(at + (size_t)Q.nq * nd * w);
+  for (int q = 0; q < Q.nq; ++q) fe_eval_hat(dim, fe, &Q.x[(size_t)q * dim], &out[at + (size_t)q * nd * w]);
+}
+
+// terms of block (test component a, trial component b); trial_comp < 0 selects linear-form terms
+static void build_form(Ctx* ctx, tfelcu_mesh* mesh, int quad, const tfelcu_factor* factors, int n_factors,
+                       const tfelcu_term* terms, int n_terms, int comp_te, int fe_te, int comp_tr, int fe_tr,
+                       FormBuild& out) {
+  const int dim = mesh->dim, w = dim + 1;
+  const Quadrature Q = make_quadrature(quad);
+  TFELCU_REQUIRE(Q.dim == dim, "quadrature formula and mesh have different dimensions");
+  TFELCU_REQUIRE(n_factors <= kMaxFactors, "too many coefficient factors in one integrand");
+  FormDev& F = out.F;
+  std::memset(&F, 0, sizeof(F));
+  F.nq = Q.nq;
+  // terms of this block
+  bool used[kMaxFactors] = {false};
+  for (int t = 0; t < n_terms; ++t) {
+    const tfelcu_term& s = terms[t];
+    if (comp_te >= 0 && s.test_comp != comp_te) continue;
+    if (comp_tr >= 0 && s.trial_comp != comp_tr) continue;
+    TFELCU_REQUIRE(F.n_terms < kMaxTerms, "too many terms in one block of the integrand");
+    TFELCU_REQUIRE(s.test_d >= 0 && s.test_d <= dim && s.trial_d >= 0 && s.trial_d <= dim, "derivative index out of range");
+    TFELCU_REQUIRE(s.n_factors >= 0 && s.n_factors <= 5, "too many factors in one term");
+    DevTerm& d = F.terms[F.n_terms++];
+    d.test_d = s.test_d; d.trial_d = s.trial_d; d.c = s.c; d.n_factors = s.n_factors;
+    for (int f = 0; f < s.n_factors; ++f) {
+      TFELCU_REQUIRE(s.factor[f] >= 0 && s.factor[f] < n_factors, "factor index out of range");
+      d.factor[f] = s.factor[f]; used[s.factor[f]] = true;
+      out.const_coef = false;
+    }
+  }
+  // tables staged in shared memory
+  std::vector<double>& T = out.tables;
+  F.off_w = (int)T.size(); T.insert(T.end(), Q.w.begin(), Q.w.end());
+  F.off_xhat = (int)T.size(); T.insert(T.end(), Q.x.begin(), Q.x.end());
+  if (fe_te > 0) { F.off_hat_te = (int)T.size(); tabulate(dim, fe_te, Q, T); }
+  if (fe_tr > 0) { F.off_hat_tr = (int)T.size(); tabulate(dim, fe_tr, Q, T); }
+  if (out.const_coef && fe_te > 0) {
+    const int nd_te = fe_ndof(dim, fe_te);
+    const double* hte = &T[F.off_hat_te];
+    F.off_ref = (int)T.size();
+    if (fe_tr > 0) {
+      const int nd_tr = fe_ndof(dim, fe_tr);
+      const double* htr = &T[F.off_hat_tr];
+      std::vector<double> ref((size_t)w * w * nd_te * nd_tr, 0.0);
+      for (int a = 0; a < w; ++a) for (int b = 0; b < w; ++b)
+        for (int i = 0; i < nd_te; ++i) for (int j = 0; j < nd_tr; ++j) {
+          double s = 0.0;
+          for (int q = 0; q < Q.nq; ++q) s += Q.w[q] * hte[((size_t)q * nd_te + i) * w + a] * htr[((size_t)q * nd_tr + j) * w + b];
+          ref[(((size_t)a * w + b) * nd_te + i) * nd_tr + j] = s;
+        }
+      T.insert(T.end(), ref.begin(), ref.end());
+    } else {
+      std::vector<double> ref((size_t)w * nd_te, 0.0);
+      for (int a = 0; a < w; ++a) for (int i = 0; i < nd_te; ++i) {
+        double s = 0.0;
+        for (int q = 0; q < Q.nq; ++q) s += Q.w[q] * hte[((size_t)q * nd_te + i) * w + a];
+        ref[(size_t)a * nd_te + i] = s;
+      }
+      T.insert(T.end(), ref.begin(), ref.end());
+    }
+  }
+  F.n_stage = (int)T.size();
+  // coefficient factors
+  F.n_factors = n_factors;
+  int prog_at = 0;
+  for (int f = 0; f < n_factors; ++f) {
+    DevFactor& d = F.factors[f];
+    d.kind = 0;
+    if (!used[f]) continue;
+    const tfelcu_factor& s = factors[f];
+    d.kind = s.kind; d.d = s.d;
+    if (s.kind == TFELCU_FACTOR_FIELD) {
+      TFELCU_REQUIRE(s.fes && s.fes->mesh == mesh, "field factor lives on another mesh");
+      TFELCU_REQUIRE(s.d >= 0 && s.d <= dim, "field derivative index out of range");
+      d.nd = s.fes->nd; d.dof_map = s.fes->dof_map;
+      d.tab_off = (int)T.size(); tabulate(dim, s.fes->fe, Q, T);
+      if (is_device_pointer(s.data)) d.data = s.data;
+      else {
+        out.keep.emplace_back(s.fes->n_dof);
+        ctx->upload(out.keep.back().p, s.data, s.fes->n_dof);
+        d.data = out.keep.back().p;
+      }
+    } else if (s.kind == TFELCU_FACTOR_TABLE) {
+      const size_t n = mesh->K * (size_t)Q.nq;
+      if (is_device_pointer(s.data)) d.data = s.data;
+      else {
+        out.keep.emplace_back(n);
+        ctx->upload(out.keep.back().p, s.data, n);
+        d.data = out.keep.back().p;
+      }
+    } else if (s.kind == TFELCU_FACTOR_PROGRAM) {
+      TFELCU_REQUIRE(prog_at + s.n_ops <= kMaxProgOps, "coefficient programs too long");
+      d.prog_off = prog_at; d.prog_len = s.n_ops;
+      int depth = 0;
+      for (int p = 0; p < s.n_ops; ++p) {
+        const int op = s.ops[p].op;
+        if (op == TFELCU_OP_CONST || op == TFELCU_OP_COORD) ++depth;
+        else if (op == TFELCU_OP_ADD || op == TFELCU_OP_SUB || op == TFELCU_OP_MUL || op == TFELCU_OP_DIV ||
+                 op == TFELCU_OP_POW || op == TFELCU_OP_LT) { TFELCU_REQUIRE(depth >= 2, "malformed coefficient program"); --depth; }
+        else TFELCU_REQUIRE(depth >= 1, "malformed coefficient program");
+        TFELCU_REQUIRE(depth <= 8, "coefficient program needs a deeper stack than 8");
+        F.prog[prog_at + p] = s.ops[p];
+      }
+      TFELCU_REQUIRE(depth == 1, "malformed coefficient program");
+      prog_at += s.n_ops;
+    } else {
+      fail("unknown coefficient factor kind");
+    }
+  }
+}
+
+// grow-only device scratch for the tables of the form being assembled (stream ordered reuse)
+static const double* upload_tables(Ctx* ctx, const std::vector<double>& T, DevBuf<double>& scratch) {
+  if (scratch.n < T.size()) { ctx->sync(); scratch.alloc(T.size() * 2); }
+  TFELCU_CK(cudaMemcpyAsync(scratch.p, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return scratch.p;
+}
+
+static DevBuf<double>& table_scratch(Ctx* ctx) { return ctx->table_scratch; }
+
+template <typename Kern>
+static void ensure_smem(Kern kern, size_t bytes) {
+  if (bytes > 48 * 1024) TFELCU_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+template <int DIM, int ND_TE, int ND_TR>
+static void launch_rows(Ctx* ctx, const FormBuild& fb, const RowBlock& B, bool staged, size_t stage_doubles) {
+  const unsigned grid = grid_for(B.n_rows_comp, kRowsPerCta);
+  const size_t smem = ((size_t)fb.F.n_stage + (staged ? stage_doubles : 0)) * sizeof(double);
+#define TFELCU_ROWS(CC, ST)                                                                      \
+  do {                                                                                           \
+    auto kern = k_assemble_rows<DIM, ND_TE, ND_TR, CC, ST>;                                      \
+    ensure_smem(kern, smem);                                                                     \
+    kern<<<grid, kRowsPerCta, smem, ctx->stream>>>(fb.F, B);                                     \
+  } while (0)
+  if (fb.const_coef) { if (staged) TFELCU_ROWS(true, true); else TFELCU_ROWS(true, false); }
+  else { if (staged) TFELCU_ROWS(false, true); else TFELCU_ROWS(false, false); }
+#undef TFELCU_ROWS
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+}
+
+template <int DIM, int ND_TE, int ND_TR>
+static void launch_colored(Ctx* ctx, const FormBuild& fb, const ColorBlock& B) {
+  const unsigned grid = grid_for(B.n_cells, 128);
+  const size_t smem = (size_t)fb.F.n_stage * sizeof(double);
+  if (fb.const_coef) {
+    auto kern = k_assemble_colored<DIM, ND_TE, ND_TR, true>;
+    ensure_smem(kern, smem);
+    kern<<<grid, 128, smem, ctx->stream>>>(fb.F, B);
+  } else {
+    auto kern = k_assemble_colored<DIM, ND_TE, ND_TR, false>;
+    ensure_smem(kern, smem);
+    kern<<<grid, 128, smem, ctx->stream>>>(fb.F, B);
+  }
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+}
+
+template <int DIM, int ND_TE>
+static void launch_vector(Ctx* ctx, const FormBuild& fb, const VecBlock& B) {
+  const unsigned grid = grid_for(B.n_rows_comp, 128);
+  const size_t smem = (size_t)fb.F.n_stage * sizeof(double);
+  if (fb.const_coef) {
+    auto kern = k_assemble_vector_rows<DIM, ND_TE, true>;
+    ensure_smem(kern, smem);
+    kern<<<grid, 128, smem, ctx->stream>>>(fb.F, B);
+  } else {
+    auto kern = k_assemble_vector_rows<DIM, ND_TE, false>;
+    ensure_smem(kern, smem);
+    kern<<<grid, 128, smem, ctx->stream>>>(fb.F, B);
+  }
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+}
+
+// dispatch on (dim, dofs per cell of the test element, of the trial element)
+#define TFELCU_DISPATCH_ND(DIMV, nd, NDV, ...)                                                   \
+  if constexpr (DIMV == 2) {                                                                             \
+    if (nd == 3) { constexpr int NDV = 3; __VA_ARGS__ } else if (nd == 4) { constexpr int NDV = 4; __VA_ARGS__ }   \
+    else if (nd == 6) { constexpr int NDV = 6; __VA_ARGS__ } else fail("unsupported element");   \
+  } else {                                                                                       \
+    if (nd == 4) { constexpr int NDV = 4; __VA_ARGS__ } else if (nd == 5) { constexpr int NDV = 5; __VA_ARGS__ }   \
+    else if (nd == 10) { constexpr int NDV = 10; __VA_ARGS__ } else fail("unsupported element"); \
+  }
+
+template <int DIM>
+static void assemble_bilinear_dim(tfelcu_matrix* m, int quad, const tfelcu_factor* factors, int n_factors,
+                                  const tfelcu_term* terms, int n_terms) {
+  Ctx* ctx = m->ctx;
+  tfelcu_mesh* mesh = m->mesh;
+  const bool single_block = (m->test.n == 1 && m->trial.n == 1);
+  const bool colored = (m->scatter == TFELCU_SCATTER_COLORED);
+  if (colored) matrix_build_colors(m);
+  for (int a = 0; a < m->test.n; ++a)
+    for (int b = 0; b < m->trial.n; ++b) {
+      tfelcu_fes* te = m->test.fes[a]; tfelcu_fes* tr = m->trial.fes[b];
+      FormBuild fb;
+      build_form(ctx, mesh, quad, factors, n_factors, terms, n_terms, a, te->fe, b, tr->fe, fb);
+      if (fb.F.n_terms == 0) continue;   // the block only contributes (already stored) zeros
+      fb.F.tables = upload_tables(ctx, fb.tables, table_scratch(ctx));
+      const size_t stage_bytes = ((size_t)fb.F.n_stage + m->max_block_nnz) * sizeof(double);
+      const bool staged = single_block && !colored && te->nd == tr->nd && stage_bytes <= 160 * 1024;
+      if (!staged) matrix_ensure_cleared(m);
+      if (!colored) {
+        fes_transpose(te);
+        RowBlock B;
+        B.vertices = mesh->vertices.p; B.cells = mesh->cells.p; B.map_tr = tr->dof_map;
+        B.off_te = (uint32_t)m->test.offset[a]; B.off_tr = (uint32_t)m->trial.offset[b]; B.n_rows_comp = te->n_dof;
+        B.adj_ptr = te->adj_ptr.p; B.adj = te->adj.p; B.dir_row = m->dir_row.p;
+        B.rowptr = m->rowptr.p; B.colind = m->colind.p; B.val = m->val.p;
+        B.init_mode = m->val_valid ? 0 : 1;
+        const int nd_te = te->nd, nd_tr = tr->nd;
+        TFELCU_DISPATCH_ND(DIM, nd_te, NTE,
+          TFELCU_DISPATCH_ND(DIM, nd_tr, NTR,
+            if (staged) { if constexpr (NTE == NTR) launch_rows<DIM, NTE, NTR>(ctx, fb, B, true, m->max_block_nnz); }
+            else launch_rows<DIM, NTE, NTR>(ctx, fb, B, false, 0);))
+        if (staged) m->val_valid = true;
+      } else {
+        ColorBlock B;
+        B.vertices = mesh->vertices.p; B.cells = mesh->cells.p; B.map_te = te->dof_map; B.map_tr = tr->dof_map;
+        B.off_te = (uint32_t)m->test.offset[a]; B.off_tr = (uint32_t)m->trial.offset[b];
+        B.dir_row = m->dir_row.p; B.rowptr = m->rowptr.p; B.colind = m->colind.p; B.val = m->val.p;
+        const int nd_te = te->nd, nd_tr = tr->nd;
+        for (int c = 0; c < m->n_colors; ++c) {
+          B.color_cells = m->color_cells.p + m->color_start[c];
+          B.n_cells = m->color_start[c + 1] - m->color_start[c];
+          if (!B.n_cells) continue;
+          TFELCU_DISPATCH_ND(DIM, nd_te, NTE,
+            TFELCU_DISPATCH_ND(DIM, nd_tr, NTR, launch_colored<DIM, NTE, NTR>(ctx, fb, B);))
+        }
+      }
+      if (!fb.keep.empty()) ctx->sync();   // device copies of host coefficient data die with fb
+    }
+  matrix_ensure_cleared(m);
+  m->pristine = false;
+}
+
+void assemble_bilinear(tfelcu_matrix* m, int quad, const tfelcu_factor* factors, int n_factors,
+                       const tfelcu_term* terms, int n_terms) {
+  for (int t = 0; t < n_terms; ++t) {
+    TFELCU_REQUIRE(terms[t].test_comp >= 0 && terms[t].test_comp < m->test.n, "test component out of range");
+    TFELCU_REQUIRE(terms[t].trial_comp >= 0 && terms[t].trial_comp < m->trial.n, "trial component out of range");
+  }
+  if (m->mesh->dim == 2) assemble_bilinear_dim<2>(m, quad, factors, n_factors, terms, n_terms);
+  else assemble_bilinear_dim<3>(m, quad, factors, n_factors, terms, n_terms);
+}
+
+template <int DIM>
+static void assemble_linear_dim(tfelcu_vector* v, int quad, const tfelcu_factor* factors, int n_factors,
+                                const tfelcu_term* terms, int n_terms) {
+  Ctx* ctx = v->ctx;
+  for (int a = 0; a < v->space.n; ++a) {
+    tfelcu_fes* te = v->space.fes[a];
+    FormBuild fb;
+    build_form(ctx, te->mesh, quad, factors, n_factors, terms, n_terms, a, te->fe, -1, 0, fb);
+    if (fb.F.n_terms == 0) continue;
+    fb.F.tables = upload_tables(ctx, fb.tables, table_scratch(ctx));
+    fes_transpose(te);
+    VecBlock B;
+    B.vertices = te->mesh->vertices.p; B.cells = te->mesh->cells.p;
+    B.off_te = (uint32_t)v->space.offset[a]; B.n_rows_comp = te->n_dof;
+    B.adj_ptr = te->adj_ptr.p; B.adj = te->adj.p; B.b = v->data.p;
+    const int nd_te = te->nd;
+    TFELCU_DISPATCH_ND(DIM, nd_te, NTE, launch_vector<DIM, NTE>(ctx, fb, B);)
+    if (!fb.keep.empty()) ctx->sync();
+  }
+}
+
+void assemble_linear(tfelcu_vector* v, int quad, const tfelcu_factor* factors, int n_factors,
+                     const tfelcu_term* terms, int n_terms) {
+  for (int t = 0; t < n_terms; ++t)
+    TFELCU_REQUIRE(terms[t].test_comp >= 0 && terms[t].test_comp < v->space.n, "test component out of range");
+  if (v->space.fes[0]->mesh->dim == 2) assemble_linear_dim<2>(v, quad, factors, n_factors, terms, n_terms);
+  else assemble_linear_dim<3>(v, quad, factors, n_factors, terms, n_terms);
+}
+
+double integrate_scalar(Ctx* ctx, tfelcu_mesh* mesh, int quad, const tfelcu_factor* factors, int n_factors,
+                        const tfelcu_term* terms, int n_terms) {
+  FormBuild fb;
+  build_form(ctx, mesh, quad, factors, n_factors, terms, n_terms, -1, 0, -1, 0, fb);
+  fb.F.tables = upload_tables(ctx, fb.tables, table_scratch(ctx));
+  const unsigned grid = grid_for(mesh->K, 256);
+  DevBuf<double> partial(grid), out(1);
+  const size_t smem = (size_t)fb.F.n_stage * sizeof(double);
+  if (mesh->dim == 2) k_integrate<2><<<grid, 256, smem, ctx->stream>>>(fb.F, mesh->vertices.p, mesh->cells.p, mesh->K, partial.p);
+  else k_integrate<3><<<grid, 256, smem, ctx->stream>>>(fb.F, mesh->vertices.p, mesh->cells.p, mesh->K, partial.p);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  k_sum_partials<<<1, 256, 0, ctx->stream>>>(partial.p, grid, out.p);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  double h = 0.0; ctx->download(&h, out.p, 1);
+  return h;
+}
+
+}  // namespace tfelcu

@@ -1,0 +1,122 @@
+// Shared plumbing of libtfel_cuda: error handling, device buffers, the context.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <memory>
+
+#include "../../include/tfel_cuda.h"
+
+namespace tfelcu {
+
+struct Error : std::runtime_error {
+  explicit Error(const std::string& m) : std::runtime_error(m) {}
+};
+
+[[noreturn]] inline void fail(const std::string& m) { throw Error(m); }
+
+#define TFELCU_CK(call)                                                                         \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      ::tfelcu::fail(std::string(#call) + " failed: " + cudaGetErrorString(e_) + " at " +       \
+                     __FILE__ + ":" + std::to_string(__LINE__));                                \
+  } while (0)
+
+#define TFELCU_NCCL(call)                                                                       \
+  do {                                                                                          \
+    ncclResult_t r_ = (call);                                                                   \
+    if (r_ != ncclSuccess)                                                                      \
+      ::tfelcu::fail(std::string(#call) + " failed: " + ncclGetErrorString(r_) + " at " +       \
+                     __FILE__ + ":" + std::to_string(__LINE__));                                \
+  } while (0)
+
+#define TFELCU_REQUIRE(cond, msg)                                                               \
+  do { if (!(cond)) ::tfelcu::fail(std::string(msg)); } while (0)
+
+// Device array with value semantics disabled (move only).
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t count) { alloc(count); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    // +4 elements of slack: bulk copies in the SpMV kernel read whole 16-byte chunks
+    if (count) TFELCU_CK(cudaMalloc(&p, (count + 4) * sizeof(T)));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+inline bool is_device_pointer(const void* p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  int rank = 0, n_ranks = 1;
+  ncclComm_t comm = nullptr;
+  int sm_count = 148;
+  uint64_t launches = 0;
+  DevBuf<double> table_scratch;   // reference-element tables of the form being assembled (stream ordered reuse)
+
+  void count(uint64_t n = 1) { launches += n; }
+  void sync() { TFELCU_CK(cudaStreamSynchronize(stream)); }
+
+  // host <-> device copies on the context stream
+  template <typename T>
+  void upload(T* dst, const T* src, size_t n) {
+    if (!n) return;
+    TFELCU_CK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDefault, stream));
+  }
+  template <typename T>
+  void download(T* dst, const T* src, size_t n) {
+    if (!n) return;
+    TFELCU_CK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDefault, stream));
+    sync();
+  }
+  template <typename T>
+  void zero(T* dst, size_t n) {
+    if (n) TFELCU_CK(cudaMemsetAsync(dst, 0, n * sizeof(T), stream));
+  }
+};
+
+inline unsigned grid_for(size_t n, unsigned block) {
+  size_t g = (n + block - 1) / block;
+  if (g == 0) g = 1;
+  if (g > 0x7fffffffu) fail("grid too large");
+  return static_cast<unsigned>(g);
+}
+
+#define TFELCU_LAUNCH_CHECK() TFELCU_CK(cudaGetLastError())
+
+}  // namespace tfelcu
+
+// Opaque handle types of the C ABI are the implementation structs below.
+struct tfelcu_ctx : tfelcu::Ctx {};

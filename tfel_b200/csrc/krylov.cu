@@ -1,0 +1,564 @@
+// solver::cuda::gmres_* -- restarted GMRES and the level-scheduled ILU(0) preconditioner.
+// Replaces what PETSc does for the reference behind solver::petsc::gmres_ilu (src/core/solver.hpp:139-163:
+// KSPGMRES with modified Gram-Schmidt, left preconditioning, PCILU in natural ordering, x0 = 0, convergence
+// on the preconditioned residual:  ||M^-1 r|| <= max(rtol ||M^-1 b||, atol), divergence at dtol ||M^-1 b||).
+//
+// ILU(0): the factors live on the pattern of A (the reference's CSR, columns ascending). Rows are grouped in
+// dependency levels (level(i) = 1 + max level of the rows i needs); the numeric factorisation and the two
+// triangular solves walk the levels, one thread per row, each row summed in ascending column order -- the same
+// operation order as the sequential IKJ algorithm, so the factors are bitwise those of a scalar loop.
+#include "solver.cuh"
+#include "sortutil.cuh"
+
+namespace tfelcu {
+
+constexpr int kVecT = 256;
+
+static int vgrid(tfelcu_solver* s) {
+  size_t want = (s->n + kVecT - 1) / kVecT;
+  const size_t cap = (size_t)s->ctx->sm_count * 4;
+  if (want > cap) want = cap;
+  return want < 1 ? 1 : (int)want;
+}
+
+// ------------------------------------------------------------------------------------------
+// ILU(0): symbolic (diagonal positions, levels)
+// ------------------------------------------------------------------------------------------
+
+__global__ void k_diag_pos(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind, size_t n,
+                           int32_t* __restrict__ diag, int* __restrict__ missing) {
+  const size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int lo = rowptr[r], hi = rowptr[r + 1];
+  const int end = hi;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (colind[mid] < (int32_t)r) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= end || colind[lo] != (int32_t)r) { atomicExch(missing, 1); diag[r] = -1; }
+  else diag[r] = lo;
+}
+
+// level of every row in one pass: CTAs take tickets so that rows start in ascending (LOWER) or descending order;
+// a row spins until the rows it depends on -- all of which started earlier -- have published their level.
+template <bool LOWER>
+__global__ void __launch_bounds__(128)
+k_levels(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind, const int32_t* __restrict__ diag,
+         size_t n, unsigned int* __restrict__ ticket, volatile int* __restrict__ level) {
+  __shared__ unsigned int blk;
+  if (threadIdx.x == 0) blk = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const size_t t = (size_t)blk * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const size_t r = LOWER ? t : n - 1 - t;
+  const int e0 = LOWER ? rowptr[r] : diag[r] + 1;
+  const int e1 = LOWER ? diag[r] : rowptr[r + 1];
+  int lv = 0;
+  for (int e = e0; e < e1; ++e) {
+    const int c = colind[e];
+    int l;
+    while ((l = level[c]) < 0) { __nanosleep(20); }
+    lv = l + 1 > lv ? l + 1 : lv;
+  }
+  __threadfence();
+  level[r] = lv;
+}
+
+__global__ void k_max_int(const int* __restrict__ a, size_t n, int* __restrict__ out) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) atomicMax(out, a[i]);
+}
+
+__global__ void k_lower_bounds_i32(const uint32_t* __restrict__ sorted, size_t n, int n_targets, int32_t* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n_targets) return;
+  size_t lo = 0, hi = n;
+  while (lo < hi) {
+    const size_t mid = lo + (hi - lo) / 2;
+    if (sorted[mid] < (uint32_t)t) lo = mid + 1; else hi = mid;
+  }
+  out[t] = (int32_t)lo;
+}
+
+// rows grouped by level (ascending row id inside a level) + start of every level
+static void schedule(Ctx* ctx, const int* d_level, size_t n, DevBuf<int32_t>& order, std::vector<int32_t>& level_ptr) {
+  DevBuf<int> mx(1);
+  ctx->zero(mx.p, 1);
+  k_max_int<<<grid_for(n, 256), 256, 0, ctx->stream>>>(d_level, n, mx.p);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  int n_levels = 0; ctx->download(&n_levels, mx.p, 1);
+  n_levels += 1;
+  DevBuf<uint32_t> ids(n), keys_sorted(n);
+  iota_u32(ctx, ids.p, n);
+  order.alloc(n);
+  sort_pairs<uint32_t, uint32_t>(ctx, reinterpret_cast<const uint32_t*>(d_level), keys_sorted.p, ids.p,
+                                 reinterpret_cast<uint32_t*>(order.p), n, 0, bits_for((size_t)n_levels + 1));
+  DevBuf<int32_t> ptr((size_t)n_levels + 1);
+  k_lower_bounds_i32<<<grid_for((size_t)n_levels + 1, 256), 256, 0, ctx->stream>>>(keys_sorted.p, n, n_levels, ptr.p);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  level_ptr.resize((size_t)n_levels + 1);
+  ctx->download(level_ptr.data(), ptr.p, (size_t)n_levels + 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// ILU(0): numeric factorisation and triangular solves, one launch per group of levels
+// ------------------------------------------------------------------------------------------
+
+// IKJ elimination of one row (the scalar algorithm of a sequential ILU(0)): for k < i in the pattern of row i,
+// l = a_ik / u_kk, then a_ij -= l u_kj for the j > k present in BOTH rows.
+__device__ __forceinline__ void ilu0_row(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                                         const int32_t* __restrict__ diag, double* __restrict__ lu, int i) {
+  const int rs = rowptr[i], re = rowptr[i + 1], di = diag[i];
+  for (int e = rs; e < di; ++e) {
+    const int k = colind[e];
+    const double l = lu[e] / __ldcg(lu + diag[k]);
+    lu[e] = l;
+    if (l == 0.0) continue;
+    int ei = e + 1;
+    const int ke = rowptr[k + 1];
+    for (int ek = diag[k] + 1; ek < ke; ++ek) {
+      const int c = colind[ek];
+      while (ei < re && colind[ei] < c) ++ei;
+      if (ei < re && colind[ei] == c) lu[ei] -= l * __ldcg(lu + ek);
+    }
+  }
+}
+
+__global__ void k_ilu0_level(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                             const int32_t* __restrict__ diag, const int32_t* __restrict__ order, int begin, int end,
+                             double* __restrict__ lu) {
+  const int t = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < end) ilu0_row(rowptr, colind, diag, lu, order[t]);
+}
+
+// several consecutive small levels in one CTA (levels separated by a CTA barrier)
+__global__ void __launch_bounds__(1024)
+k_ilu0_levels_cta(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind, const int32_t* __restrict__ diag,
+                  const int32_t* __restrict__ order, const int32_t* __restrict__ level_ptr, int l0, int l1,
+                  double* __restrict__ lu) {
+  for (int l = l0; l < l1; ++l) {
+    const int t = level_ptr[l] + threadIdx.x;
+    if (t < level_ptr[l + 1]) ilu0_row(rowptr, colind, diag, lu, order[t]);
+    __threadfence_block();
+    __syncthreads();
+  }
+}
+
+template <bool LOWER>
+__device__ __forceinline__ void tri_row(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                                        const int32_t* __restrict__ diag, const double* __restrict__ lu,
+                                        const double* in, double* out, int i) {
+  // forward: x_i = b_i - sum_{j<i} l_ij x_j ; backward: x_i = (y_i - sum_{j>i} u_ij x_j) / u_ii
+  double acc = in[i];
+  if (LOWER) {
+    for (int e = rowptr[i]; e < diag[i]; ++e) acc -= lu[e] * __ldcg(out + colind[e]);
+    out[i] = acc;
+  } else {
+    for (int e = diag[i] + 1; e < rowptr[i + 1]; ++e) acc -= lu[e] * __ldcg(out + colind[e]);
+    out[i] = acc / lu[diag[i]];
+  }
+}
+
+template <bool LOWER>
+__global__ void k_tri_level(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                            const int32_t* __restrict__ diag, const double* __restrict__ lu,
+                            const int32_t* __restrict__ order, int begin, int end, const double* in,
+                            double* out, const KrylovScalars* __restrict__ S) {
+  if (S && S->done) return;
+  const int t = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < end) tri_row<LOWER>(rowptr, colind, diag, lu, in, out, order[t]);
+}
+
+template <bool LOWER>
+__global__ void __launch_bounds__(1024)
+k_tri_levels_cta(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind, const int32_t* __restrict__ diag,
+                 const double* __restrict__ lu, const int32_t* __restrict__ order, const int32_t* __restrict__ level_ptr,
+                 int l0, int l1, const double* in, double* out,
+                 const KrylovScalars* __restrict__ S) {
+  if (S && S->done) return;
+  for (int l = l0; l < l1; ++l) {
+    const int t = level_ptr[l] + threadIdx.x;
+    if (t < level_ptr[l + 1]) tri_row<LOWER>(rowptr, colind, diag, lu, in, out, order[t]);
+    __threadfence_block();
+    __syncthreads();
+  }
+}
+
+// launch plan of a level schedule: runs of consecutive levels of at most 1024 rows each go to one CTA
+
+static std::vector<LevelRun> plan_runs(const std::vector<int32_t>& level_ptr) {
+  std::vector<LevelRun> runs;
+  const int nl = (int)level_ptr.size() - 1;
+  int l = 0;
+  while (l < nl) {
+    const int sz = level_ptr[l + 1] - level_ptr[l];
+    if (sz <= 1024) {
+      int e = l + 1;
+      while (e < nl && level_ptr[e + 1] - level_ptr[e] <= 1024) ++e;
+      runs.push_back({l, e, true});
+      l = e;
+    } else {
+      runs.push_back({l, l + 1, false});
+      ++l;
+    }
+  }
+  return runs;
+}
+
+void ilu0_setup(tfelcu_solver* s) {
+  Ctx* ctx = s->ctx;
+  const size_t n = s->n;
+  TFELCU_REQUIRE(n < 0x7fffffffull, "ILU(0): too many rows");
+  s->ilu.reset(new Ilu0());
+  Ilu0& I = *s->ilu;
+  I.diag.alloc(n);
+  DevBuf<int> missing(1);
+  ctx->zero(missing.p, 1);
+  k_diag_pos<<<grid_for(n, 256), 256, 0, ctx->stream>>>(s->rowptr, s->colind, n, I.diag.p, missing.p);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  int h_missing = 0; ctx->download(&h_missing, missing.p, 1);
+  TFELCU_REQUIRE(!h_missing, "ILU(0): the matrix has a row without a stored diagonal entry");
+
+  DevBuf<int> level(n);
+  DevBuf<unsigned int> ticket(1);
+  for (int pass = 0; pass < 2; ++pass) {
+    TFELCU_CK(cudaMemsetAsync(level.p, 0xff, n * sizeof(int), ctx->stream));
+    ctx->zero(ticket.p, 1);
+    if (pass == 0) k_levels<true><<<grid_for(n, 128), 128, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, n, ticket.p, level.p);
+    else k_levels<false><<<grid_for(n, 128), 128, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, n, ticket.p, level.p);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+    if (pass == 0) schedule(ctx, level.p, n, I.order_l, I.level_ptr_l);
+    else schedule(ctx, level.p, n, I.order_u, I.level_ptr_u);
+  }
+  I.d_level_ptr_l.alloc(I.level_ptr_l.size());
+  I.d_level_ptr_u.alloc(I.level_ptr_u.size());
+  ctx->upload(I.d_level_ptr_l.p, I.level_ptr_l.data(), I.level_ptr_l.size());
+  ctx->upload(I.d_level_ptr_u.p, I.level_ptr_u.data(), I.level_ptr_u.size());
+
+  // numeric factorisation on a copy of the values, level by level of the L schedule
+  I.lu.alloc(s->nnz);
+  TFELCU_CK(cudaMemcpyAsync(I.lu.p, s->val, s->nnz * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  for (const LevelRun& r : plan_runs(I.level_ptr_l)) {
+    if (r.cta) {
+      k_ilu0_levels_cta<<<1, 1024, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, I.order_l.p, I.d_level_ptr_l.p,
+                                                    r.l0, r.l1, I.lu.p);
+    } else {
+      const int b = I.level_ptr_l[r.l0], e = I.level_ptr_l[r.l1];
+      k_ilu0_level<<<grid_for((size_t)(e - b), 128), 128, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, I.order_l.p, b, e, I.lu.p);
+    }
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+  }
+  ctx->sync();
+}
+
+static void tri_launches(tfelcu_solver* s, const double* d_in, double* d_out, bool lower) {
+  Ctx* ctx = s->ctx;
+  Ilu0& I = *s->ilu;
+  const std::vector<int32_t>& lp = lower ? I.level_ptr_l : I.level_ptr_u;
+  const int32_t* order = lower ? I.order_l.p : I.order_u.p;
+  const int32_t* d_lp = lower ? I.d_level_ptr_l.p : I.d_level_ptr_u.p;
+  const KrylovScalars* S = s->scal.p;
+  std::vector<LevelRun>& runs = lower ? I.runs_l : I.runs_u;
+  if (runs.empty()) runs = plan_runs(lp);
+  for (const LevelRun& r : runs) {
+    if (r.cta) {
+      if (lower) k_tri_levels_cta<true><<<1, 1024, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, I.lu.p, order, d_lp, r.l0, r.l1, d_in, d_out, S);
+      else k_tri_levels_cta<false><<<1, 1024, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, I.lu.p, order, d_lp, r.l0, r.l1, d_in, d_out, S);
+    } else {
+      const int b = lp[r.l0], e = lp[r.l1];
+      const unsigned g = grid_for((size_t)(e - b), 128);
+      if (lower) k_tri_level<true><<<g, 128, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, I.lu.p, order, b, e, d_in, d_out, S);
+      else k_tri_level<false><<<g, 128, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, I.lu.p, order, b, e, d_in, d_out, S);
+    }
+    ctx->count();
+  }
+  TFELCU_LAUNCH_CHECK();
+}
+
+// out = U^-1 L^-1 in. The backward solve runs in place on the forward result.
+void ilu0_apply(tfelcu_solver* s, const double* d_in, double* d_out) {
+  tri_launches(s, d_in, d_out, true);
+  tri_launches(s, d_out, d_out, false);
+}
+
+// ------------------------------------------------------------------------------------------
+// GMRES(m), modified Gram-Schmidt, left preconditioning
+// ------------------------------------------------------------------------------------------
+
+struct GmresDev {      // device scalars of one restart cycle
+  double target, dtol_abs, bnorm, rnorm;
+  int done;            // 0 running, 1 converged, -1 diverged, -2 breakdown (happy or not)
+  int k;               // columns of the current cycle
+  int its, pad;
+};
+
+__device__ __forceinline__ double blk_sum(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < kVecT / 32; ++w) t += red[w];
+  __syncthreads();
+  return t;
+}
+
+__device__ __forceinline__ double sum_fixed(const double* __restrict__ p, int n) {
+  double t = 0.0;
+  for (int i = 0; i < n; ++i) t += p[i];
+  return t;
+}
+
+// partial sums of a . b
+__global__ void __launch_bounds__(kVecT)
+k_dot(const double* __restrict__ a, const double* __restrict__ b, size_t n, double* __restrict__ partial) {
+  __shared__ double red[kVecT / 32];
+  double v = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) v += a[i] * b[i];
+  const double t = blk_sum(v, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+// t = b - q  (q = A x)
+__global__ void k_sub(const double* __restrict__ b, const double* __restrict__ q, size_t n, double* __restrict__ t) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) t[i] = b[i] - q[i];
+}
+
+__global__ void k_jacobi_apply(const double* __restrict__ dinv, const double* __restrict__ in, size_t n, double* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = dinv ? dinv[i] * in[i] : in[i];
+}
+
+// ||M^-1 b|| -> tolerances
+__global__ void k_gmres_init(const double* __restrict__ partial, int np, double rtol, double atol, double dtol,
+                             GmresDev* __restrict__ G) {
+  if (threadIdx.x || blockIdx.x) return;
+  const double bn = sqrt(sum_fixed(partial, np));
+  G->bnorm = bn; G->target = fmax(rtol * bn, atol); G->dtol_abs = dtol * bn; G->rnorm = bn;
+  G->done = 0; G->k = 0; G->its = 0;
+}
+
+// start of a cycle: rnorm = ||v0||; test; g = rnorm e_0
+__global__ void k_gmres_cycle_start(const double* __restrict__ partial, int np, GmresDev* __restrict__ G,
+                                    double* __restrict__ g, int m) {
+  if (threadIdx.x || blockIdx.x) return;
+  const double rn = sqrt(sum_fixed(partial, np));
+  G->rnorm = rn; G->k = 0;
+  if (!(rn == rn)) G->done = -2;
+  else if (rn <= G->target) G->done = 1;
+  else if (rn > G->dtol_abs) G->done = -1;
+  for (int i = 0; i <= m; ++i) g[i] = 0.0;
+  g[0] = rn;
+}
+
+// v *= 1 / sqrt(sum partial)   (normalisation by a norm whose square is in partial sums)
+__global__ void __launch_bounds__(kVecT)
+k_scale_by_norm(double* __restrict__ v, size_t n, const double* __restrict__ partial, int np, const GmresDev* __restrict__ G) {
+  if (G->done) return;
+  const double nr = sqrt(sum_fixed(partial, np));
+  if (nr == 0.0) return;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) v[i] /= nr;
+}
+
+// One modified Gram-Schmidt step, fused: apply the previous projection (h_prev = sum of partial_prev, w -= h_prev v_prev)
+// and start the next dot product (partial_next of w . v_next; v_next == w gives the final norm).
+// Every CTA owns a fixed slice of the vectors, so it only needs its own updated entries.
+__global__ void __launch_bounds__(kVecT)
+k_mgs_step(double* __restrict__ w, const double* __restrict__ v_prev, const double* __restrict__ partial_prev, int np,
+           double* __restrict__ h_out, const double* __restrict__ v_next, int next_is_w, size_t n,
+           double* __restrict__ partial_next, const GmresDev* __restrict__ G) {
+  __shared__ double red[kVecT / 32];
+  if (G->done) return;
+  double h = 0.0;
+  if (v_prev) {
+    h = sum_fixed(partial_prev, np);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *h_out = h;
+  }
+  double acc = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double wi = w[i];
+    if (v_prev) { wi -= h * v_prev[i]; w[i] = wi; }
+    acc += wi * (next_is_w ? wi : v_next[i]);
+  }
+  const double t = blk_sum(acc, red);
+  if (threadIdx.x == 0) partial_next[blockIdx.x] = t;
+}
+
+// Givens rotations of column k of the Hessenberg matrix + residual estimate + stopping test (one thread).
+// H is stored column-major with leading dimension m + 1.
+__global__ void k_gmres_givens(double* __restrict__ H, double* __restrict__ cs, double* __restrict__ sn, double* __restrict__ g,
+                               const double* __restrict__ partial_norm, int np, int k, int m, uint32_t maxits,
+                               GmresDev* __restrict__ G) {
+  if (threadIdx.x || blockIdx.x || G->done) return;
+  double* Hk = H + (size_t)k * (m + 1);
+  const double hn = sqrt(sum_fixed(partial_norm, np));
+  Hk[k + 1] = hn;
+  for (int j = 0; j < k; ++j) {
+    const double a = Hk[j], b = Hk[j + 1];
+    Hk[j] = cs[j] * a + sn[j] * b;
+    Hk[j + 1] = -sn[j] * a + cs[j] * b;
+  }
+  const double a = Hk[k], b = Hk[k + 1];
+  const double rr = hypot(a, b);
+  cs[k] = rr == 0.0 ? 1.0 : a / rr; sn[k] = rr == 0.0 ? 0.0 : b / rr;
+  Hk[k] = rr; Hk[k + 1] = 0.0;
+  g[k + 1] = -sn[k] * g[k]; g[k] = cs[k] * g[k];
+  G->its += 1; G->k = k + 1;
+  const double rn = fabs(g[k + 1]);
+  G->rnorm = rn;
+  if (!(rn == rn)) G->done = -2;
+  else if (rn <= G->target) G->done = 1;
+  else if (rn > G->dtol_abs) G->done = -1;
+  else if (hn == 0.0) G->done = -2;
+  else if ((uint32_t)G->its >= maxits) G->done = 2;   // out of iterations
+}
+
+// y = R^-1 g (back substitution, one CTA), k columns
+__global__ void __launch_bounds__(256)
+k_gmres_backsolve(const double* __restrict__ H, const double* __restrict__ g, int k, int m, double* __restrict__ y) {
+  __shared__ double red[256 / 32];
+  for (int i = k - 1; i >= 0; --i) {
+    double acc = 0.0;
+    for (int j = i + 1 + threadIdx.x; j < k; j += 256) acc += H[(size_t)j * (m + 1) + i] * y[j];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      y[i] = (g[i] - t) / H[(size_t)i * (m + 1) + i];
+    }
+    __syncthreads();
+  }
+}
+
+// x += sum_j y_j v_j, j ascending
+__global__ void k_gmres_update_x(const double* __restrict__ V, const double* __restrict__ y, int k, size_t n, size_t ld,
+                                 double* __restrict__ x) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double xi = x[i];
+    for (int j = 0; j < k; ++j) xi += y[j] * V[(size_t)j * ld + i];
+    x[i] = xi;
+  }
+}
+
+static void precond(tfelcu_solver* s, const double* d_in, double* d_out) {
+  Ctx* ctx = s->ctx;
+  switch (s->params.precond) {
+    case TFELCU_PC_ILU0: ilu0_apply(s, d_in, d_out); break;
+    case TFELCU_PC_BLOCK_JACOBI: block_jacobi_apply(s, d_in, d_out); break;
+    default:
+      k_jacobi_apply<<<vgrid(s), kVecT, 0, ctx->stream>>>(s->params.precond == TFELCU_PC_JACOBI ? s->dinv.p : nullptr, d_in, s->n, d_out);
+      ctx->count(); TFELCU_LAUNCH_CHECK();
+  }
+}
+
+void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep) {
+  Ctx* ctx = s->ctx;
+  const size_t n = s->n;
+  const int vg = vgrid(s);
+  const uint64_t launches0 = ctx->launches;
+  uint64_t n_spmv = 0;
+  uint32_t maxits = s->params.maxits;
+  // restart length: the dictionary's, bounded by maxits and by the memory the Krylov basis may take
+  long long m = s->params.restart;
+  if (m > (long long)maxits) m = maxits;
+  if (m < 1) m = 1;
+  size_t free_b = 0, total_b = 0;
+  TFELCU_CK(cudaMemGetInfo(&free_b, &total_b));
+  const size_t ld = (n + 3) & ~(size_t)3;
+  if (!s->basis.n || s->basis.n < (size_t)(m + 1) * ld) {
+    const size_t have = s->basis.bytes();
+    long long fit = (long long)((free_b + have) * 0.8 / (8.0 * (double)(ld ? ld : 1))) - 1;
+    if (m > fit) m = fit;
+    TFELCU_REQUIRE(m >= 1, "GMRES: not enough device memory for a Krylov basis");
+    s->basis.release();
+    s->basis.alloc((size_t)(m + 1) * ld);
+    s->gmres_m = (int)m;
+  } else if (s->gmres_m > 0 && m > s->gmres_m) m = s->gmres_m;
+  const int M = (int)m;
+  s->hess.alloc((size_t)(M + 1) * M + 4 * (size_t)(M + 1));
+  double* H = s->hess.p;
+  double* cs = H + (size_t)(M + 1) * M;
+  double* sn = cs + (M + 1);
+  double* g = sn + (M + 1);
+  double* y = g + (M + 1);
+  DevBuf<GmresDev> Gd(1);
+  GmresDev* G = Gd.p;
+  double* V = s->basis.p;
+  double* t = s->r.p;          // work vector
+  double* P0 = s->partial.p;   // two alternating partial-sum buffers
+  double* P1 = s->partial.p + s->n_partial;
+
+  ctx->zero(s->x.p, n);                                      // x0 = 0 (solver.cpp:165-166)
+  ctx->zero(s->scal.p, 1);
+  precond(s, s->b.p, s->q.p);
+  k_dot<<<vg, kVecT, 0, ctx->stream>>>(s->q.p, s->q.p, n, P0);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  k_gmres_init<<<1, 32, 0, ctx->stream>>>(P0, vg, s->params.rtol, s->params.atol, s->params.dtol, G);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+
+  GmresDev h;
+  std::memset(&h, 0, sizeof(h));
+  bool first_cycle = true;
+  while (true) {
+    // v0 = M^-1 (b - A x)
+    if (first_cycle) {
+      TFELCU_CK(cudaMemcpyAsync(V, s->q.p, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+      spmv_launch(s, s->x.p, s->q.p, nullptr, nullptr); ++n_spmv;
+      k_sub<<<vg, kVecT, 0, ctx->stream>>>(s->b.p, s->q.p, n, t);
+      ctx->count(); TFELCU_LAUNCH_CHECK();
+      precond(s, t, V);
+    }
+    first_cycle = false;
+    k_dot<<<vg, kVecT, 0, ctx->stream>>>(V, V, n, P0);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+    k_gmres_cycle_start<<<1, 32, 0, ctx->stream>>>(P0, vg, G, g, M);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+    ctx->download(&h, G, 1);
+    if (h.done) break;
+    k_scale_by_norm<<<vg, kVecT, 0, ctx->stream>>>(V, n, P0, vg, G);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+    int k = 0;
+    for (; k < M; ++k) {
+      double* w = V + (size_t)(k + 1) * ld;
+      spmv_launch(s, V + (size_t)k * ld, t, nullptr, nullptr); ++n_spmv;
+      precond(s, t, w);
+      double* Hk = H + (size_t)k * (M + 1);
+      // MGS: k + 2 fused steps; step j projects out v_{j-1} and starts the product with v_j (the last: with w)
+      for (int j = 0; j <= k + 1; ++j) {
+        const double* v_prev = j > 0 ? V + (size_t)(j - 1) * ld : nullptr;
+        const bool last = (j == k + 1);
+        k_mgs_step<<<vg, kVecT, 0, ctx->stream>>>(w, v_prev, (j & 1) ? P0 : P1, vg, j > 0 ? Hk + (j - 1) : nullptr,
+                                                 last ? w : V + (size_t)j * ld, last ? 1 : 0, n, (j & 1) ? P1 : P0, G);
+        ctx->count();
+      }
+      TFELCU_LAUNCH_CHECK();
+      double* Pn = ((k + 1) & 1) ? P1 : P0;
+      k_gmres_givens<<<1, 32, 0, ctx->stream>>>(H, cs, sn, g, Pn, vg, k, M, maxits, G);
+      ctx->count(); TFELCU_LAUNCH_CHECK();
+      k_scale_by_norm<<<vg, kVecT, 0, ctx->stream>>>(w, n, Pn, vg, G);   // skipped on device once done
+      ctx->count(); TFELCU_LAUNCH_CHECK();
+      ctx->download(&h, G, 1);
+      if (h.done) { ++k; break; }
+    }
+    const int cols = h.k;
+    if (cols > 0) {
+      k_gmres_backsolve<<<1, 256, 0, ctx->stream>>>(H, g, cols, M, y);
+      ctx->count(); TFELCU_LAUNCH_CHECK();
+      k_gmres_update_x<<<vg, kVecT, 0, ctx->stream>>>(V, y, cols, n, ld, s->x.p);
+      ctx->count(); TFELCU_LAUNCH_CHECK();
+    }
+    if (h.done) break;
+    if ((uint32_t)h.its >= maxits) break;
+  }
+  rep->its = (uint32_t)h.its;
+  rep->converged = h.done == 1 ? 1 : (h.done == 2 || h.done == 0 ? 0 : h.done);
+  rep->rnorm = h.rnorm;
+  rep->bnorm = h.bnorm;
+  rep->n_spmv = n_spmv;
+  rep->n_launches = ctx->launches - launches0;
+}
+
+}  // namespace tfelcu

@@ -1,0 +1,369 @@
+// solver::cuda::* -- Krylov solvers behind solver::basic_solver (src/core/solver.hpp:29-40).
+// This file: operator set-up, the preconditioned conjugate gradient method (Jacobi / block Jacobi / none) and
+// the fused vector kernels. GMRES + ILU(0) live in krylov.cu.
+//
+// Dirichlet rows of the reference are identity rows whose columns are NOT eliminated
+// (bilinear_form.hpp:159-165,183-186), so A is not symmetric when boundary data are non-zero. CG starts from the
+// lift x0 = b on identity rows, 0 elsewhere: r0 then vanishes on those rows, every search direction does too,
+// and the iteration runs on the symmetric interior block A_II with right-hand side b_I - A_ID g.
+//
+// Convergence: ||r||_2 <= max(rtol ||b||_2, atol); divergence: ||r||_2 > dtol ||b||_2 (the dictionary keys of
+// solver.hpp:125-133). All reductions are per-CTA partial sums combined in a fixed order: bitwise reproducible.
+#include "solver.cuh"
+
+namespace tfelcu {
+
+constexpr int kVecThreads = 256;
+
+static int vec_grid(tfelcu_solver* s) {
+  // grid-stride kernels sized to the machine: 4 CTAs of 256 threads per SM
+  size_t want = (s->n + kVecThreads - 1) / kVecThreads;
+  const size_t cap = (size_t)s->ctx->sm_count * 4;
+  if (want > cap) want = cap;
+  return want < 1 ? 1 : (int)want;
+}
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < kVecThreads / 32; ++w) t += red[w];
+  __syncthreads();
+  return t;   // valid on thread 0
+}
+
+// every thread of every CTA sums the same partials in the same order
+__device__ __forceinline__ double sum_partials(const double* __restrict__ partial, int n) {
+  double t = 0.0;
+  for (int i = 0; i < n; ++i) t += partial[i];
+  return t;
+}
+
+__global__ void k_extract_diag(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                               const double* __restrict__ val, size_t n, int invert, double* __restrict__ d) {
+  const size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double v = 1.0;
+  for (int e = rowptr[r]; e < rowptr[r + 1]; ++e)
+    if (colind[e] == (int32_t)r) v = val[e];
+  d[r] = invert ? 1.0 / v : v;
+}
+
+// x0: the Dirichlet lift (identity rows take their right-hand side), zero elsewhere
+__global__ void k_initial_guess(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                                const double* __restrict__ val, const double* __restrict__ b, size_t n,
+                                double* __restrict__ x) {
+  const size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int rs = rowptr[r];
+  const bool identity = (rowptr[r + 1] - rs == 1) && colind[rs] == (int32_t)r && val[rs] == 1.0;
+  x[r] = identity ? b[r] : 0.0;
+}
+
+// r = b - q, partial sums of b.b
+__global__ void __launch_bounds__(kVecThreads)
+k_residual(const double* __restrict__ b, const double* __restrict__ q, size_t n, double* __restrict__ r,
+           double* __restrict__ partial_bb) {
+  __shared__ double red[kVecThreads / 32];
+  double bb = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double bi = b[i];
+    r[i] = bi - q[i];
+    bb += bi * bi;
+  }
+  const double t = block_sum(bb, red);
+  if (threadIdx.x == 0) partial_bb[blockIdx.x] = t;
+}
+
+// z = M^-1 r (Jacobi: dinv * r, none: r), p = z, partial sums of r.z and r.r
+__global__ void __launch_bounds__(kVecThreads)
+k_cg_start(const double* __restrict__ r, const double* __restrict__ dinv, const double* __restrict__ z_in, size_t n,
+           double* __restrict__ p, double* __restrict__ partial_rz, double* __restrict__ partial_rr) {
+  __shared__ double red[kVecThreads / 32];
+  double rz = 0.0, rr = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double ri = r[i];
+    const double zi = z_in ? z_in[i] : (dinv ? dinv[i] * ri : ri);
+    p[i] = zi;
+    rz += ri * zi; rr += ri * ri;
+  }
+  const double t0 = block_sum(rz, red);
+  const double t1 = block_sum(rr, red);
+  if (threadIdx.x == 0) { partial_rz[blockIdx.x] = t0; partial_rr[blockIdx.x] = t1; }
+}
+
+__global__ void k_cg_set_scalars(const double* __restrict__ partial_bb, const double* __restrict__ partial_rz,
+                                 const double* __restrict__ partial_rr, int n_partial, double rtol, double atol,
+                                 double dtol, KrylovScalars* __restrict__ S) {
+  if (threadIdx.x || blockIdx.x) return;
+  const double bb = sum_partials(partial_bb, n_partial);
+  const double target = fmax(rtol * sqrt(bb), atol);
+  S->bnorm2 = bb; S->target2 = target * target; S->dtol2 = dtol * dtol * bb;
+  S->rz = sum_partials(partial_rz, n_partial);
+  S->rr = sum_partials(partial_rr, n_partial);
+  S->its = 0;
+  S->done = (S->rr <= S->target2) ? 1 : 0;
+}
+
+// alpha = rz / pq; x += alpha p; r -= alpha q; [Jacobi / none: partial sums of r.z] and of r.r
+__global__ void __launch_bounds__(kVecThreads)
+k_cg_update(const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ dinv,
+            int fused_precond, size_t n, const double* __restrict__ partial_pq, int n_pq,
+            double* __restrict__ x, double* __restrict__ r, double* __restrict__ partial_rz,
+            double* __restrict__ partial_rr, KrylovScalars* __restrict__ S) {
+  __shared__ double red[kVecThreads / 32];
+  if (S->done) return;
+  const double pq = sum_partials(partial_pq, n_pq);
+  const double alpha = S->rz / pq;
+  double rz = 0.0, rr = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * q[i];
+    r[i] = ri;
+    rr += ri * ri;
+    if (fused_precond) rz += ri * (dinv ? dinv[i] * ri : ri);
+  }
+  const double t0 = block_sum(rz, red);
+  const double t1 = block_sum(rr, red);
+  if (threadIdx.x == 0) { partial_rz[blockIdx.x] = t0; partial_rr[blockIdx.x] = t1; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { S->pq = pq; S->alpha = alpha; }
+}
+
+// r.z for a preconditioner that is applied by its own kernel
+__global__ void __launch_bounds__(kVecThreads)
+k_dot_partial(const double* __restrict__ a, const double* __restrict__ b, size_t n, double* __restrict__ partial,
+              const KrylovScalars* __restrict__ S) {
+  __shared__ double red[kVecThreads / 32];
+  if (S && S->done) return;
+  double v = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) v += a[i] * b[i];
+  const double t = block_sum(v, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+// beta = rz_new / rz; p = z + beta p; the last CTA-0 thread publishes the new scalars and the stopping test
+__global__ void __launch_bounds__(kVecThreads)
+k_cg_direction(const double* __restrict__ r, const double* __restrict__ dinv, const double* __restrict__ z_in, size_t n,
+               const double* __restrict__ partial_rz, const double* __restrict__ partial_rr, int n_partial,
+               double* __restrict__ p, KrylovScalars* __restrict__ S) {
+  if (S->done) return;
+  const double rz_new = sum_partials(partial_rz, n_partial);
+  const double rr = sum_partials(partial_rr, n_partial);
+  const double rz_old = S->rz;
+  const double beta = rz_new / rz_old;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double zi = z_in ? z_in[i] : (dinv ? dinv[i] * r[i] : r[i]);
+    p[i] = zi + beta * p[i];
+  }
+  // publish after every CTA has read the old scalars: done by a separate tiny kernel (k_cg_commit)
+  if (blockIdx.x == 0 && threadIdx.x == 0) { S->rz_new = rz_new; S->spare0 = rr; S->beta = beta; }
+}
+
+__global__ void k_cg_commit(KrylovScalars* __restrict__ S) {
+  if (threadIdx.x || blockIdx.x || S->done) return;
+  S->rz = S->rz_new; S->rr = S->spare0;
+  S->its += 1;
+  if (!(S->rr == S->rr) || !(S->pq == S->pq) || S->pq == 0.0) S->done = -2;   // NaN / breakdown
+  else if (S->rr <= S->target2) S->done = 1;
+  else if (S->rr > S->dtol2) S->done = -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// block Jacobi: contiguous blocks of bs rows, dense inverse of each diagonal block
+// ------------------------------------------------------------------------------------------
+
+__global__ void k_block_jacobi_setup(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                                     const double* __restrict__ val, size_t n, int bs, double* __restrict__ inv) {
+  const size_t blk = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t r0 = blk * bs;
+  if (r0 >= n) return;
+  double a[8][16];   // [bs][2 bs]: Gauss-Jordan on [D | I]
+  for (int i = 0; i < bs; ++i)
+    for (int j = 0; j < 2 * bs; ++j) a[i][j] = (j == bs + i) ? 1.0 : 0.0;
+  for (int i = 0; i < bs; ++i) {
+    const size_t r = r0 + i;
+    if (r >= n) { a[i][i] = 1.0; continue; }
+    for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+      const long long c = (long long)colind[e] - (long long)r0;
+      if (c >= 0 && c < bs) a[i][c] = val[e];
+    }
+  }
+  for (int k = 0; k < bs; ++k) {
+    int piv = k; double best = fabs(a[k][k]);
+    for (int i = k + 1; i < bs; ++i) if (fabs(a[i][k]) > best) { best = fabs(a[i][k]); piv = i; }
+    if (piv != k) for (int j = 0; j < 2 * bs; ++j) { const double t = a[k][j]; a[k][j] = a[piv][j]; a[piv][j] = t; }
+    const double d = a[k][k] != 0.0 ? 1.0 / a[k][k] : 1.0;
+    for (int j = 0; j < 2 * bs; ++j) a[k][j] *= d;
+    for (int i = 0; i < bs; ++i) {
+      if (i == k) continue;
+      const double f = a[i][k];
+      for (int j = 0; j < 2 * bs; ++j) a[i][j] -= f * a[k][j];
+    }
+  }
+  for (int i = 0; i < bs; ++i)
+    for (int j = 0; j < bs; ++j) inv[(blk * bs + i) * bs + j] = a[i][bs + j];
+}
+
+__global__ void k_block_jacobi_apply(const double* __restrict__ inv, const double* __restrict__ in, size_t n, int bs,
+                                     double* __restrict__ out, const KrylovScalars* __restrict__ S) {
+  if (S && S->done) return;
+  const size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const size_t blk = r / bs; const int i = (int)(r % bs);
+  double acc = 0.0;
+  for (int j = 0; j < bs; ++j) {
+    const size_t c = blk * bs + j;
+    if (c < n) acc += inv[(blk * bs + i) * bs + j] * in[c];
+  }
+  out[r] = acc;
+}
+
+void block_jacobi_setup(tfelcu_solver* s) {
+  Ctx* ctx = s->ctx;
+  int bs = s->params.block_size;
+  if (bs <= 0) bs = 4;
+  TFELCU_REQUIRE(bs <= 8, "block Jacobi supports blocks of up to 8 rows");
+  s->params.block_size = bs;
+  const size_t nb = (s->n + bs - 1) / bs;
+  s->block_inv.alloc(nb * bs * bs);
+  k_block_jacobi_setup<<<grid_for(nb, 128), 128, 0, ctx->stream>>>(s->rowptr, s->colind, s->val, s->n, bs, s->block_inv.p);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+}
+
+void block_jacobi_apply(tfelcu_solver* s, const double* d_in, double* d_out) {
+  Ctx* ctx = s->ctx;
+  k_block_jacobi_apply<<<grid_for(s->n, 256), 256, 0, ctx->stream>>>(s->block_inv.p, d_in, s->n, s->params.block_size,
+                                                                   d_out, s->scal.p);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
+// set-up and the CG driver
+// ------------------------------------------------------------------------------------------
+
+void solver_setup(tfelcu_solver* s) {
+  Ctx* ctx = s->ctx;
+  cudaEvent_t e0, e1;
+  TFELCU_CK(cudaEventCreate(&e0)); TFELCU_CK(cudaEventCreate(&e1));
+  TFELCU_CK(cudaEventRecord(e0, ctx->stream));
+  const size_t n = s->n;
+  s->x.alloc(n); s->b.alloc(n); s->r.alloc(n); s->p.alloc(n); s->q.alloc(n);
+  s->scal.alloc(1);
+  ctx->zero(s->scal.p, 1);
+  spmv_plan(s);
+  int np = spmv_partial_count(s);
+  const int vg = vec_grid(s);
+  if (vg > np) np = vg;
+  s->n_partial = np;
+  s->partial.alloc((size_t)np * 4);
+  ctx->zero(s->partial.p, (size_t)np * 4);
+  const int pc = s->params.precond;
+  if (pc == TFELCU_PC_JACOBI) {
+    s->dinv.alloc(n);
+    k_extract_diag<<<grid_for(n, 256), 256, 0, ctx->stream>>>(s->rowptr, s->colind, s->val, n, 1, s->dinv.p);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+  } else if (pc == TFELCU_PC_BLOCK_JACOBI) {
+    s->z.alloc(n);
+    block_jacobi_setup(s);
+  } else if (pc == TFELCU_PC_ILU0) {
+    s->z.alloc(n);
+    ilu0_setup(s);
+  }
+  TFELCU_CK(cudaEventRecord(e1, ctx->stream));
+  TFELCU_CK(cudaEventSynchronize(e1));
+  float ms = 0.f; TFELCU_CK(cudaEventElapsedTime(&ms, e0, e1));
+  s->t_setup_s = ms * 1e-3;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+}
+
+static void apply_precond(tfelcu_solver* s, const double* d_in, double* d_out) {
+  if (s->params.precond == TFELCU_PC_BLOCK_JACOBI) block_jacobi_apply(s, d_in, d_out);
+  else if (s->params.precond == TFELCU_PC_ILU0) ilu0_apply(s, d_in, d_out);
+  else fail("preconditioner has no stand-alone apply");
+}
+
+void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep) {
+  Ctx* ctx = s->ctx;
+  const size_t n = s->n;
+  const int vg = vec_grid(s);
+  const int pc = s->params.precond;
+  const bool fused = (pc == TFELCU_PC_JACOBI || pc == TFELCU_PC_NONE);
+  const double* dinv = pc == TFELCU_PC_JACOBI ? s->dinv.p : nullptr;
+  double* P_pq = s->partial.p;
+  double* P_rz = s->partial.p + s->n_partial;
+  double* P_rr = s->partial.p + 2 * (size_t)s->n_partial;
+  double* P_bb = s->partial.p + 3 * (size_t)s->n_partial;
+  KrylovScalars* S = s->scal.p;
+  uint64_t n_spmv = 0;
+  const uint64_t launches0 = ctx->launches;
+
+  ctx->zero(S, 1);
+  k_initial_guess<<<grid_for(n, 256), 256, 0, ctx->stream>>>(s->rowptr, s->colind, s->val, s->b.p, n, s->x.p);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  spmv_launch(s, s->x.p, s->q.p, nullptr, nullptr); ++n_spmv;
+  k_residual<<<vg, kVecThreads, 0, ctx->stream>>>(s->b.p, s->q.p, n, s->r.p, P_bb);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  if (!fused) apply_precond(s, s->r.p, s->z.p);
+  k_cg_start<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, dinv, fused ? nullptr : s->z.p, n, s->p.p, P_rz, P_rr);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  k_cg_set_scalars<<<1, 32, 0, ctx->stream>>>(P_bb, P_rz, P_rr, vg, s->params.rtol, s->params.atol, s->params.dtol, S);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+
+  int check = s->params.check_every > 0 ? s->params.check_every : 50;
+  KrylovScalars h;
+  ctx->download(&h, S, 1);
+  uint32_t issued = 0;
+  const uint32_t maxits = s->params.maxits;
+  while (!h.done && issued < maxits) {
+    uint32_t chunk = (uint32_t)check;
+    if (issued + chunk > maxits) chunk = maxits - issued;
+    for (uint32_t it = 0; it < chunk; ++it) {
+      const int n_pq = spmv_launch(s, s->p.p, s->q.p, P_pq, S); ++n_spmv;
+      k_cg_update<<<vg, kVecThreads, 0, ctx->stream>>>(s->p.p, s->q.p, dinv, fused ? 1 : 0, n, P_pq, n_pq,
+                                                      s->x.p, s->r.p, P_rz, P_rr, S);
+      ctx->count(); TFELCU_LAUNCH_CHECK();
+      if (!fused) {
+        apply_precond(s, s->r.p, s->z.p);
+        k_dot_partial<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, s->z.p, n, P_rz, S);
+        ctx->count(); TFELCU_LAUNCH_CHECK();
+      }
+      k_cg_direction<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, dinv, fused ? nullptr : s->z.p, n, P_rz, P_rr, vg,
+                                                         s->p.p, S);
+      ctx->count(); TFELCU_LAUNCH_CHECK();
+      k_cg_commit<<<1, 32, 0, ctx->stream>>>(S);
+      ctx->count(); TFELCU_LAUNCH_CHECK();
+    }
+    issued += chunk;
+    ctx->download(&h, S, 1);
+  }
+  rep->its = (uint32_t)h.its;
+  rep->converged = h.done == 1 ? 1 : (h.done == 0 ? 0 : h.done);
+  rep->rnorm = sqrt(h.rr);
+  rep->bnorm = sqrt(h.bnorm2);
+  rep->n_spmv = n_spmv;
+  rep->n_launches = ctx->launches - launches0;
+}
+
+void solver_solve(tfelcu_solver* s, const double* d_rhs, double* d_x, tfelcu_solver_report* rep) {
+  Ctx* ctx = s->ctx;
+  TFELCU_REQUIRE(s->rowptr != nullptr, "solver has no operator: call set_operator first");
+  std::memset(rep, 0, sizeof(*rep));
+  cudaEvent_t e0, e1;
+  TFELCU_CK(cudaEventCreate(&e0)); TFELCU_CK(cudaEventCreate(&e1));
+  TFELCU_CK(cudaEventRecord(e0, ctx->stream));
+  TFELCU_CK(cudaMemcpyAsync(s->b.p, d_rhs, s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (s->params.method == TFELCU_METHOD_CG) solve_cg(s, rep);
+  else if (s->params.method == TFELCU_METHOD_GMRES) solve_gmres(s, rep);
+  else fail("unknown Krylov method");
+  TFELCU_CK(cudaMemcpyAsync(d_x, s->x.p, s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  TFELCU_CK(cudaEventRecord(e1, ctx->stream));
+  TFELCU_CK(cudaEventSynchronize(e1));
+  float ms = 0.f; TFELCU_CK(cudaEventElapsedTime(&ms, e0, e1));
+  rep->t_solve_s = ms * 1e-3;
+  rep->t_setup_s = s->t_setup_s;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+}
+
+}  // namespace tfelcu

@@ -1,0 +1,79 @@
+// solver::cuda::* behind solver::basic_solver (src/core/solver.hpp:29-40): device-resident CSR operator,
+// FP64 Krylov methods and preconditioners.
+#pragma once
+
+#include "structs.cuh"
+
+namespace tfelcu {
+
+// device-side scalars of a Krylov iteration (one cache line, read by every kernel)
+struct KrylovScalars {
+  double rz, pq, alpha, beta, rr, bnorm2, target2, dtol2;
+  double rz_new, spare0, spare1, spare2;
+  int done;        // 0 running, 1 converged, -1 diverged, -2 breakdown
+  int its;
+  int pad0, pad1;
+};
+
+struct SpmvPlan {
+  int kernel = TFELCU_SPMV_VECTOR;
+  int lanes = 8;                         // lanes per row of the vector kernel
+  // TMA-streamed kernel: row blocks of bounded nnz
+  DevBuf<int32_t> block_row;             // [n_blocks + 1]
+  int n_blocks = 0;
+  int tile_nnz = 0, tile_rows = 0;
+};
+
+// consecutive levels [l0, l1) of a level schedule launched together: one CTA walking several small levels
+// (cta == true) or one grid for a single large level
+struct LevelRun { int l0, l1; bool cta; };
+
+struct Ilu0 {
+  DevBuf<double> lu;                     // factors on the pattern of A
+  DevBuf<int32_t> diag;                  // position of the diagonal in each row
+  DevBuf<int32_t> order_l, order_u;      // rows grouped by level
+  std::vector<int32_t> level_ptr_l, level_ptr_u;
+  DevBuf<int32_t> d_level_ptr_l, d_level_ptr_u;
+  std::vector<LevelRun> runs_l, runs_u;
+};
+
+}  // namespace tfelcu
+
+struct tfelcu_solver {
+  tfelcu::Ctx* ctx = nullptr;
+  tfelcu_solver_params params;
+  size_t n = 0, nnz = 0;
+  const int32_t* rowptr = nullptr;
+  const int32_t* colind = nullptr;
+  const double* val = nullptr;
+  tfelcu::DevBuf<int32_t> own_rowptr, own_colind;
+  tfelcu::DevBuf<double> own_val;
+  tfelcu::SpmvPlan plan;
+  // work space
+  tfelcu::DevBuf<double> x, b, r, p, q, z, dinv, partial;
+  tfelcu::DevBuf<tfelcu::KrylovScalars> scal;
+  tfelcu::DevBuf<double> block_inv;        // block Jacobi: [n_blocks][bs][bs]
+  tfelcu::DevBuf<double> basis, hess;      // GMRES
+  std::unique_ptr<tfelcu::Ilu0> ilu;
+  double t_setup_s = 0.0;
+  int n_partial = 0;
+  int gmres_m = 0;                         // restart length the allocated basis holds
+};
+
+namespace tfelcu {
+
+void solver_setup(tfelcu_solver* s);
+void solver_spmv(tfelcu_solver* s, const double* d_x, double* d_y);
+void solver_solve(tfelcu_solver* s, const double* d_rhs, double* d_x, tfelcu_solver_report* rep);
+void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep);
+void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep);
+void spmv_plan(tfelcu_solver* s);
+// y = A x; when dot_partial != nullptr also writes per-CTA partial sums of x . y and returns their number
+int spmv_launch(tfelcu_solver* s, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal);
+int spmv_partial_count(tfelcu_solver* s);
+void ilu0_setup(tfelcu_solver* s);
+void ilu0_apply(tfelcu_solver* s, const double* d_in, double* d_out);
+void block_jacobi_setup(tfelcu_solver* s);
+void block_jacobi_apply(tfelcu_solver* s, const double* d_in, double* d_out);
+
+}  // namespace tfelcu
