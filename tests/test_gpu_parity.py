@@ -1,0 +1,291 @@
+"""GPU: the CUDA path (through the C ABI) against the committed reference fixtures (tests/golden) and the
+plain-C oracle on the same inputs. Integer structure bit-exact, values to 1e-12 (tests/parity.py),
+solutions to the solver rtol 1e-8 in relative L2 (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+import cuda_runner
+import oracle as orc
+import oracle_runner
+import problems
+from parity import assert_int_equal, assert_values_close, matrix_entries_close
+
+pytestmark = pytest.mark.gpu
+
+SKIP_KEYS = ("meta_json", "solution", "pin_parent_cell", "pin_parent_subdomain", "dirichlet_flags")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from tfel_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def compare(got, ref, rowptr_key="csr_rowptr"):
+    for key, r in ref.items():
+        if key in SKIP_KEYS or key.startswith("_"):
+            continue
+        assert key in got, key
+        if r.dtype.kind in "ui":
+            assert_int_equal(got[key], r, key)
+        elif key == "csr_val":
+            matrix_entries_close(ref[rowptr_key], got[key], r, 1e-12)
+        else:
+            assert_values_close(got[key], r, 1e-12, key)
+
+
+@pytest.mark.parametrize("scatter", ["rows", "colored"])
+@pytest.mark.parametrize("problem", problems.GOLDEN_CASES, ids=lambda p: p.golden)
+def test_cuda_matches_reference_fixture(ctx, problem, scatter, golden_dir):
+    gold = dict(np.load(os.path.join(golden_dir, problem.golden + ".npz")))
+    got = cuda_runner.run(ctx, problem, scatter=scatter)
+    try:
+        compare(got, gold)
+    finally:
+        cuda_runner.close(got["_built"])
+
+
+@pytest.mark.parametrize("problem", [problems.poisson("p1", 57), problems.poisson("p2", 23), problems.poissong("p2", 19),
+                                     problems.tet("p1", 7), problems.tet("p1b", 5), problems.tet("p2", 5),
+                                     problems.stokes(13), problems.navier_stokes(9), problems.laplace2(11)],
+                         ids=lambda p: "%s_n%d" % (p.name, p.mesh[1]))
+def test_cuda_matches_oracle(ctx, problem):
+    ref = oracle_runner.run(problem)
+    got = cuda_runner.run(ctx, problem)
+    try:
+        compare(got, ref)
+    finally:
+        cuda_runner.close(got["_built"])
+
+
+def test_host_mesh_upload_equals_device_generator(ctx):
+    p = problems.poisson("p2", 9)
+    a = cuda_runner.run(ctx, p, generator="device")
+    b = cuda_runner.run(ctx, p, generator="host")
+    try:
+        for k in ("vertices", "cells", "dof_map", "csr_rowptr", "csr_colind", "csr_val", "linear_form"):
+            assert np.array_equal(a[k], b[k]), k
+    finally:
+        cuda_runner.close(a["_built"]); cuda_runner.close(b["_built"])
+
+
+def test_assembly_is_bitwise_reproducible(ctx):
+    p = problems.stokes(10)
+    runs = []
+    for scatter in ("rows", "colored"):
+        for _ in range(2):
+            got = cuda_runner.run(ctx, p, scatter=scatter)
+            runs.append(got["csr_val"].copy())
+            cuda_runner.close(got["_built"])
+    assert np.array_equal(runs[0], runs[1])
+    assert np.array_equal(runs[2], runs[3])
+    # both strategies add the cells of a row in ascending cell order: same bits
+    assert np.array_equal(runs[0], runs[2])
+
+
+def test_accumulate_twice_and_clear(ctx):
+    """a += x; a += x doubles the entries but keeps identity rows; clear() restores them."""
+    p = problems.poisson("p1", 12)
+    B = cuda_runner.build(ctx, p)
+    try:
+        cuda_runner.assemble(B)
+        _, _, v1 = B.matrix.csr()
+        B.matrix.assemble(p.quad, cuda_runner.lower(p.bilinear))
+        rp, ci, v2 = B.matrix.csr()
+        dofs, _ = B.spaces[0].dirichlet()
+        diag_pos = np.array([rp[r] for r in dofs])
+        is_dir = np.zeros(v1.shape[0], dtype=bool); is_dir[diag_pos] = True
+        assert np.array_equal(v2[~is_dir], 2.0 * v1[~is_dir])
+        assert np.all(v2[is_dir] == 1.0)
+        B.matrix.clear()
+        _, _, v0 = B.matrix.csr()
+        assert np.all(v0[is_dir] == 1.0) and np.all(v0[~is_dir] == 0.0)
+    finally:
+        cuda_runner.close(B)
+
+
+def test_spmv_kernels_match_oracle(ctx):
+    from tfel_b200 import capi
+    ref = oracle_runner.run(problems.stokes(12))
+    a = (ref["csr_rowptr"], ref["csr_colind"], ref["csr_val"])
+    x = np.random.RandomState(1).standard_normal(a[0].shape[0] - 1)
+    y_ref = orc.spmv(*a, x)
+    for kern in ("vector", "stream"):
+        s = capi.Solver(ctx, spmv=kern)
+        s.set_operator(a)
+        y = s.spmv(x)
+        s.close()
+        assert_values_close(y, y_ref, 1e-14, kern)
+
+
+def test_spmv_empty_and_ragged_rows(ctx):
+    from tfel_b200 import capi
+    rs = np.random.RandomState(2)
+    n = 5000
+    lens = rs.randint(0, 40, n); lens[::7] = 0; lens[123] = 900
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    colind = np.concatenate([np.sort(rs.choice(n, l, replace=False)) for l in lens]).astype(np.int32)
+    val = rs.standard_normal(colind.shape[0]); x = rs.standard_normal(n)
+    y_ref = orc.spmv(rowptr, colind, val, x)
+    for kern in ("vector", "stream"):
+        s = capi.Solver(ctx, spmv=kern)
+        s.set_operator((rowptr, colind, val))
+        y = s.spmv(x)
+        s.close()
+        assert_values_close(y, y_ref, 1e-13, kern)
+
+
+@pytest.mark.parametrize("precond", ["none", "jacobi", "block_jacobi", "ilu0"])
+def test_cg_solution_parity(ctx, precond):
+    """config 1/2 shape: Poisson P1, CG; solution within rtol 1e-8 (relative L2) of the oracle's."""
+    from tfel_b200 import capi
+    p = problems.poissong("p1", 40)
+    ref = oracle_runner.run(p)
+    a = (ref["csr_rowptr"], ref["csr_colind"], ref["csr_val"])
+    x_ref, _, _ = orc.gmres_ilu(*a, ref["rhs"], restart=300, levels=2, rtol=1e-13)
+    B = cuda_runner.build(ctx, p)
+    try:
+        cuda_runner.assemble(B)
+        s = capi.Solver(ctx, method="cg", precond=precond, maxits=5000, rtol=1e-10)
+        x, rep = B.matrix.solve(B.vector, s)
+        s.close()
+        assert rep["converged"] == 1, rep
+        assert np.linalg.norm(x - x_ref) <= 1e-8 * np.linalg.norm(x_ref)
+    finally:
+        cuda_runner.close(B)
+
+
+def test_cg_iteration_count_matches_oracle(ctx):
+    from tfel_b200 import capi
+    ref = oracle_runner.run(problems.poisson("p1", 64))
+    a = (ref["csr_rowptr"], ref["csr_colind"], ref["csr_val"])
+    x_ref, its_ref, _ = orc.cg_jacobi(*a, ref["rhs"], rtol=1e-8)
+    s = capi.Solver(ctx, method="cg", precond="jacobi", maxits=5000, rtol=1e-8, check_every=1)
+    s.set_operator(a)
+    x, rep = s.solve(ref["rhs"])
+    s.close()
+    assert abs(int(rep["its"]) - its_ref) <= 2, (rep, its_ref)
+    assert np.linalg.norm(x - x_ref) <= 1e-8 * np.linalg.norm(x_ref)
+
+
+def test_ilu0_factors_match_oracle(ctx):
+    """GMRES + ILU(0) on Stokes: same iteration count as the oracle's restatement of PETSc's
+    left-preconditioned GMRES (the factors and triangular solves agree to rounding)."""
+    from tfel_b200 import capi
+    ref = oracle_runner.run(problems.stokes(8))
+    a = (ref["csr_rowptr"], ref["csr_colind"], ref["csr_val"])
+    x_ref, its_ref, _ = orc.gmres_ilu(*a, ref["rhs"], restart=200, levels=0, rtol=1e-8, maxits=2000)
+    s = capi.Solver(ctx, method="gmres", precond="ilu0", maxits=2000, restart=200, rtol=1e-8)
+    s.set_operator(a)
+    x, rep = s.solve(ref["rhs"])
+    s.close()
+    assert rep["converged"] == 1, rep
+    assert abs(int(rep["its"]) - its_ref) <= 2, (rep, its_ref)
+    x13, _, _ = orc.gmres_ilu(*a, ref["rhs"], restart=400, levels=0, rtol=1e-13, maxits=4000)
+    assert np.linalg.norm(x - x13) <= 1e-6 * np.linalg.norm(x13)
+
+
+@pytest.mark.parametrize("problem,kw", [
+    (problems.stokes(10), dict(method="gmres", precond="ilu0", restart=300)),
+    (problems.navier_stokes(8), dict(method="gmres", precond="ilu0", restart=300)),
+    (problems.tet("p2", 4), dict(method="cg", precond="block_jacobi", block_size=4)),
+    (problems.tet("p1", 6), dict(method="gmres", precond="jacobi", restart=100)),
+    (problems.laplace2(12), dict(method="gmres", precond="none", restart=50)),
+], ids=["stokes", "ns", "tet_p2", "tet_p1", "laplace2"])
+def test_solution_parity(ctx, problem, kw):
+    from tfel_b200 import capi
+    ref = oracle_runner.run(problem)
+    a = (ref["csr_rowptr"], ref["csr_colind"], ref["csr_val"])
+    x_ref, _, rn = orc.gmres_ilu(*a, ref["rhs"], restart=500, levels=1, rtol=1e-13, maxits=5000)
+    B = cuda_runner.build(ctx, problem)
+    try:
+        cuda_runner.assemble(B)
+        s = capi.Solver(ctx, maxits=20000, rtol=1e-11, **kw)
+        x, rep = B.matrix.solve(B.vector, s)
+        s.close()
+        assert rep["converged"] == 1, rep
+        assert np.linalg.norm(x - x_ref) <= 1e-8 * np.linalg.norm(x_ref), rep
+    finally:
+        cuda_runner.close(B)
+
+
+def test_tet_p2_known_answer(ctx):
+    """u = |x|^2 is reproduced exactly by the new tetrahedron P2 element (test/tetrahedron_cube.cpp problem)."""
+    from tfel_b200 import capi
+    p = problems.tet("p2", 4)
+    B = cuda_runner.build(ctx, p)
+    try:
+        cuda_runner.assemble(B)
+        s = capi.Solver(ctx, method="cg", precond="jacobi", maxits=5000, rtol=1e-13)
+        x, rep = B.matrix.solve(B.vector, s)
+        s.close()
+        xyz = B.spaces[0].dof_coordinates()
+        assert np.abs(x - (xyz ** 2).sum(1)).max() < 1e-9
+    finally:
+        cuda_runner.close(B)
+
+
+def test_rank0_integrals(ctx):
+    """form.hpp:87-125 known answers: int x_2 = 1/2 on the cube (test/tetrahedron_cube.cpp:56-58);
+    int (sin x + sin y) = 4 pi on [0, pi]^2 (test/quadrature_2d.cpp:10-18)."""
+    from tfel_b200 import capi
+    m = capi.Mesh.cube(ctx, 1, 1, 1, 3, 3, 3)
+    v = capi.integrate(m, "qfSym35pTet", [dict(factors=[("x", problems.x1)])])
+    m.close()
+    assert abs(v - 0.5) < 1e-13
+    m = capi.Mesh.square(ctx, np.pi, np.pi, 40, 40)
+    v = capi.integrate(m, "qf5pT", [dict(factors=[("x", problems.X.sin(problems.x0) + problems.X.sin(problems.x1))])])
+    m.close()
+    assert abs(v - 4 * np.pi) < 1e-9
+
+
+def test_errors_are_reported(ctx):
+    from tfel_b200 import capi
+    m = capi.Mesh.square(ctx, 1, 1, 3, 3)
+    with pytest.raises(capi.TfelCudaError):
+        capi.Space(m, 7)
+    sp = capi.Space(m, "p1")
+    a = capi.Matrix(sp)
+    with pytest.raises(capi.TfelCudaError):
+        a.assemble("qfSym4pTet", [dict(test=(0, 0), trial=(0, 0))])   # tetrahedron rule on a triangle mesh
+    with pytest.raises(capi.TfelCudaError):
+        a.assemble("qf5pT", [dict(test=(1, 0), trial=(0, 0))])        # component out of range
+    s = capi.Solver(ctx)
+    with pytest.raises(capi.TfelCudaError):
+        s.solve(np.zeros(4))                                            # no operator
+    s.close(); a.close(); sp.close(); m.close()
+
+
+def test_full_size_structure_properties(ctx):
+    """Size-independent properties at a size the oracle does not run in seconds (n = 1024):
+    dofs (n+1)^2, nnz 7 (n-1)^2 + 4n, 4n Dirichlet dofs, row sums of the stiffness matrix vanish on
+    interior rows whose neighbours are all interior, symmetry of the interior block via x.Ay = y.Ax."""
+    from tfel_b200 import capi
+    n = 1024
+    p = problems.poisson("p1", n)
+    B = cuda_runner.build(ctx, p)
+    try:
+        cuda_runner.assemble(B)
+        assert B.spaces[0].n_dof == (n + 1) ** 2
+        assert B.matrix.nnz == 7 * (n - 1) ** 2 + 4 * n
+        dofs, _ = B.spaces[0].dirichlet()
+        assert dofs.shape[0] == 4 * n
+        s = capi.Solver(ctx)
+        s.set_operator(B.matrix)
+        ones = np.ones(B.matrix.n_rows)
+        y = s.spmv(ones)
+        isd = np.zeros(B.matrix.n_rows, dtype=bool); isd[dofs] = True
+        assert np.all(y[isd] == 1.0)
+        assert np.abs(y[~isd]).max() < 1e-11
+        rs = np.random.RandomState(0)
+        u = rs.standard_normal(B.matrix.n_rows); w = rs.standard_normal(B.matrix.n_rows)
+        u[isd] = 0; w[isd] = 0
+        au = s.spmv(u); aw = s.spmv(w)
+        assert abs(np.dot(w[~isd], au[~isd]) - np.dot(u[~isd], aw[~isd])) <= 1e-10 * abs(np.dot(w[~isd], au[~isd]))
+        s.close()
+    finally:
+        cuda_runner.close(B)
