@@ -93,7 +93,8 @@ typedef struct {
   int32_t block_size;          /* TFELCU_PC_BLOCK_JACOBI */
   int32_t check_every;         /* CG: iterations between host convergence polls (0 = default) */
   int32_t spmv_kernel;         /* TFELCU_SPMV_* */
-  int32_t reserved;
+  int32_t profile_every;       /* > 0: bracket the SpMV launch of every profile_every-th iteration with CUDA events
+                                  (at most 512 samples per solve) and report their average duration */
 } tfelcu_solver_params;
 
 typedef struct {
@@ -103,6 +104,9 @@ typedef struct {
   double t_setup_s, t_solve_s; /* device time, CUDA events */
   uint64_t n_launches;         /* kernels launched by the solve */
   uint64_t n_spmv;
+  double spmv_avg_ms;          /* profile_every > 0: average duration of the sampled SpMV launches */
+  uint32_t spmv_samples;
+  uint32_t pad;
 } tfelcu_solver_report;
 
 /* ---- context ------------------------------------------------------------------------ */

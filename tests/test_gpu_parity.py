@@ -83,8 +83,9 @@ def test_assembly_is_bitwise_reproducible(ctx):
             cuda_runner.close(got["_built"])
     assert np.array_equal(runs[0], runs[1])
     assert np.array_equal(runs[2], runs[3])
-    # both strategies add the cells of a row in ascending cell order: same bits
-    assert np.array_equal(runs[0], runs[2])
+    # the two strategies add the cells of a row in different orders (ascending cell id / colour by colour):
+    # equal to rounding, not bitwise
+    assert np.abs(runs[0] - runs[2]).max() <= 1e-13 * np.abs(runs[0]).max()
 
 
 def test_accumulate_twice_and_clear(ctx):

@@ -47,13 +47,14 @@ class SolverParams(C.Structure):
     _fields_ = [("method", C.c_int32), ("precond", C.c_int32), ("maxits", C.c_uint32),
                 ("restart", C.c_uint32), ("rtol", C.c_double), ("atol", C.c_double),
                 ("dtol", C.c_double), ("block_size", C.c_int32), ("check_every", C.c_int32),
-                ("spmv_kernel", C.c_int32), ("reserved", C.c_int32)]
+                ("spmv_kernel", C.c_int32), ("profile_every", C.c_int32)]
 
 
 class SolverReport(C.Structure):
     _fields_ = [("its", C.c_uint32), ("converged", C.c_int32), ("rnorm", C.c_double),
                 ("bnorm", C.c_double), ("t_setup_s", C.c_double), ("t_solve_s", C.c_double),
-                ("n_launches", C.c_uint64), ("n_spmv", C.c_uint64)]
+                ("n_launches", C.c_uint64), ("n_spmv", C.c_uint64), ("spmv_avg_ms", C.c_double),
+                ("spmv_samples", C.c_uint32), ("pad", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -465,10 +466,10 @@ class Solver:
     solver::petsc::gmres_ilu (solver.hpp:125-133) plus method / precond."""
 
     def __init__(self, ctx, method="cg", precond="jacobi", maxits=2000, restart=1000, rtol=1e-8, atol=1e-50,
-                 dtol=1e20, block_size=0, check_every=0, spmv="auto"):
+                 dtol=1e20, block_size=0, check_every=0, spmv="auto", profile_every=0):
         self.ctx = ctx
         p = SolverParams(METHOD[method], PRECOND[precond], int(maxits), int(restart), float(rtol), float(atol),
-                         float(dtol), int(block_size), int(check_every), SPMV[spmv], 0)
+                         float(dtol), int(block_size), int(check_every), SPMV[spmv], int(profile_every))
         self.h = C.c_void_p()
         _ck(lib().tfelcu_solver_create(ctx.h, C.byref(p), C.byref(self.h)))
         self.n = 0

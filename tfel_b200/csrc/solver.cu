@@ -311,6 +311,17 @@ void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep) {
   k_cg_set_scalars<<<1, 32, 0, ctx->stream>>>(P_bb, P_rz, P_rr, vg, s->params.rtol, s->params.atol, s->params.dtol, S);
   ctx->count(); TFELCU_LAUNCH_CHECK();
 
+  // optional SpMV sampling for the roofline report: events around every profile_every-th launch
+  const int prof_every = s->params.profile_every;
+  std::vector<cudaEvent_t> prof;
+  auto sample_begin = [&](uint32_t it) -> bool {
+    if (prof_every <= 0 || it % (uint32_t)prof_every || prof.size() >= 1024) return false;
+    cudaEvent_t a, b;
+    TFELCU_CK(cudaEventCreate(&a)); TFELCU_CK(cudaEventCreate(&b));
+    prof.push_back(a); prof.push_back(b);
+    TFELCU_CK(cudaEventRecord(a, ctx->stream));
+    return true;
+  };
   int check = s->params.check_every > 0 ? s->params.check_every : 50;
   KrylovScalars h;
   ctx->download(&h, S, 1);
@@ -320,7 +331,9 @@ void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep) {
     uint32_t chunk = (uint32_t)check;
     if (issued + chunk > maxits) chunk = maxits - issued;
     for (uint32_t it = 0; it < chunk; ++it) {
+      const bool sampled = sample_begin(issued + it);
       const int n_pq = spmv_launch(s, s->p.p, s->q.p, P_pq, S); ++n_spmv;
+      if (sampled) TFELCU_CK(cudaEventRecord(prof.back(), ctx->stream));
       k_cg_update<<<vg, kVecThreads, 0, ctx->stream>>>(s->p.p, s->q.p, dinv, fused ? 1 : 0, n, P_pq, n_pq,
                                                       s->x.p, s->r.p, P_rz, P_rr, S);
       ctx->count(); TFELCU_LAUNCH_CHECK();
@@ -337,6 +350,18 @@ void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep) {
     }
     issued += chunk;
     ctx->download(&h, S, 1);
+  }
+  if (!prof.empty()) {
+    // samples taken after convergence (the kernels return at once) are discarded
+    double total = 0.0; uint32_t cnt = 0;
+    for (size_t e = 0; e + 1 < prof.size(); e += 2) {
+      float ms = 0.f;
+      TFELCU_CK(cudaEventElapsedTime(&ms, prof[e], prof[e + 1]));
+      if ((e / 2) * (size_t)prof_every < (size_t)h.its) { total += ms; ++cnt; }
+      cudaEventDestroy(prof[e]); cudaEventDestroy(prof[e + 1]);
+    }
+    rep->spmv_avg_ms = cnt ? total / cnt : 0.0;
+    rep->spmv_samples = cnt;
   }
   rep->its = (uint32_t)h.its;
   rep->converged = h.done == 1 ? 1 : (h.done == 0 ? 0 : h.done);
