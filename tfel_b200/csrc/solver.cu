@@ -16,9 +16,9 @@ namespace tfelcu {
 constexpr int kVecThreads = 256;
 
 static int vec_grid(tfelcu_solver* s) {
-  // grid-stride kernels sized to the machine: 4 CTAs of 256 threads per SM
-  size_t want = (s->n + kVecThreads - 1) / kVecThreads;
-  const size_t cap = (size_t)s->ctx->sm_count * 4;
+  // grid-stride kernels sized to the machine: 8 CTAs of 256 threads per SM, two entries per thread and pass
+  size_t want = (s->n + 2 * kVecThreads - 1) / (2 * kVecThreads);
+  const size_t cap = (size_t)s->ctx->sm_count * 8;
   if (want > cap) want = cap;
   return want < 1 ? 1 : (int)want;
 }
@@ -34,11 +34,27 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return t;   // valid on thread 0
 }
 
-// every thread of every CTA sums the same partials in the same order
+// single-thread sum of per-CTA partials (tiny scalar kernels)
 __device__ __forceinline__ double sum_partials(const double* __restrict__ partial, int n) {
   double t = 0.0;
   for (int i = 0; i < n; ++i) t += partial[i];
   return t;
+}
+
+// the same sum formed by every CTA: warp 0 adds lane-strided slices and combines them with a butterfly, which
+// gives every lane (and every CTA) the same bits; broadcast through shared memory
+__device__ __forceinline__ double cta_sum_partials(const double* __restrict__ partial, int n, double* sh) {
+  if (threadIdx.x < 32) {
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) t += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) sh[0] = t;
+  }
+  __syncthreads();
+  const double v = sh[0];
+  __syncthreads();
+  return v;
 }
 
 __global__ void k_extract_diag(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
@@ -114,11 +130,31 @@ k_cg_update(const double* __restrict__ p, const double* __restrict__ q, const do
             double* __restrict__ x, double* __restrict__ r, double* __restrict__ partial_rz,
             double* __restrict__ partial_rr, KrylovScalars* __restrict__ S) {
   __shared__ double red[kVecThreads / 32];
+  __shared__ double bc[1];
   if (S->done) return;
-  const double pq = sum_partials(partial_pq, n_pq);
+  const double pq = cta_sum_partials(partial_pq, n_pq, bc);
   const double alpha = S->rz / pq;
   double rz = 0.0, rr = 0.0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  const size_t n2 = n / 2;
+  const double2* p2 = reinterpret_cast<const double2*>(p);
+  const double2* q2 = reinterpret_cast<const double2*>(q);
+  const double2* d2 = reinterpret_cast<const double2*>(dinv);
+  double2* x2 = reinterpret_cast<double2*>(x);
+  double2* r2 = reinterpret_cast<double2*>(r);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    const double2 pv = p2[i], qv = q2[i];
+    double2 xv = x2[i], rv = r2[i];
+    xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+    rv.x -= alpha * qv.x; rv.y -= alpha * qv.y;
+    x2[i] = xv; r2[i] = rv;
+    rr += rv.x * rv.x; rr += rv.y * rv.y;
+    if (fused_precond) {
+      if (dinv) { const double2 dv = d2[i]; rz += rv.x * (dv.x * rv.x); rz += rv.y * (dv.y * rv.y); }
+      else { rz += rv.x * rv.x; rz += rv.y * rv.y; }
+    }
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const size_t i = n - 1;
     x[i] += alpha * p[i];
     const double ri = r[i] - alpha * q[i];
     r[i] = ri;
@@ -143,27 +179,49 @@ k_dot_partial(const double* __restrict__ a, const double* __restrict__ b, size_t
   if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
 
-// beta = rz_new / rz; p = z + beta p; the last CTA-0 thread publishes the new scalars and the stopping test
+// beta = rz_new / rz; p = z + beta p; the new scalars are published by a separate tiny kernel (k_cg_commit) after
+// every CTA has read the old ones
 __global__ void __launch_bounds__(kVecThreads)
 k_cg_direction(const double* __restrict__ r, const double* __restrict__ dinv, const double* __restrict__ z_in, size_t n,
-               const double* __restrict__ partial_rz, const double* __restrict__ partial_rr, int n_partial,
+               const double* __restrict__ partial_rz, int n_partial,
                double* __restrict__ p, KrylovScalars* __restrict__ S) {
+  __shared__ double bc[1];
   if (S->done) return;
-  const double rz_new = sum_partials(partial_rz, n_partial);
-  const double rr = sum_partials(partial_rr, n_partial);
+  const double rz_new = cta_sum_partials(partial_rz, n_partial, bc);
   const double rz_old = S->rz;
   const double beta = rz_new / rz_old;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  const size_t n2 = n / 2;
+  const double2* r2 = reinterpret_cast<const double2*>(r);
+  const double2* d2 = reinterpret_cast<const double2*>(dinv);
+  const double2* z2 = reinterpret_cast<const double2*>(z_in);
+  double2* p2 = reinterpret_cast<double2*>(p);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    double2 zv;
+    if (z_in) zv = z2[i];
+    else { zv = r2[i]; if (dinv) { const double2 dv = d2[i]; zv.x *= dv.x; zv.y *= dv.y; } }
+    double2 pv = p2[i];
+    pv.x = zv.x + beta * pv.x; pv.y = zv.y + beta * pv.y;
+    p2[i] = pv;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const size_t i = n - 1;
     const double zi = z_in ? z_in[i] : (dinv ? dinv[i] * r[i] : r[i]);
     p[i] = zi + beta * p[i];
   }
-  // publish after every CTA has read the old scalars: done by a separate tiny kernel (k_cg_commit)
-  if (blockIdx.x == 0 && threadIdx.x == 0) { S->rz_new = rz_new; S->spare0 = rr; S->beta = beta; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    S->rz_new = rz_new; S->beta = beta;
+  }
 }
 
-__global__ void k_cg_commit(KrylovScalars* __restrict__ S) {
-  if (threadIdx.x || blockIdx.x || S->done) return;
-  S->rz = S->rz_new; S->rr = S->spare0;
+// one warp: r.r from its partial sums, then the scalars of the next iteration and the stopping test
+__global__ void k_cg_commit(const double* __restrict__ partial_rr, int n_partial, KrylovScalars* __restrict__ S) {
+  if (blockIdx.x || threadIdx.x >= 32 || S->done) return;
+  double t = 0.0;
+  for (int i = threadIdx.x; i < n_partial; i += 32) t += partial_rr[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (threadIdx.x) return;
+  S->rz = S->rz_new; S->rr = t;
   S->its += 1;
   if (!(S->rr == S->rr) || !(S->pq == S->pq) || S->pq == 0.0) S->done = -2;   // NaN / breakdown
   else if (S->rr <= S->target2) S->done = 1;
@@ -342,10 +400,9 @@ void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep) {
         k_dot_partial<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, s->z.p, n, P_rz, S);
         ctx->count(); TFELCU_LAUNCH_CHECK();
       }
-      k_cg_direction<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, dinv, fused ? nullptr : s->z.p, n, P_rz, P_rr, vg,
-                                                         s->p.p, S);
+      k_cg_direction<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, dinv, fused ? nullptr : s->z.p, n, P_rz, vg, s->p.p, S);
       ctx->count(); TFELCU_LAUNCH_CHECK();
-      k_cg_commit<<<1, 32, 0, ctx->stream>>>(S);
+      k_cg_commit<<<1, 32, 0, ctx->stream>>>(P_rr, vg, S);
       ctx->count(); TFELCU_LAUNCH_CHECK();
     }
     issued += chunk;

@@ -18,9 +18,10 @@ struct KrylovScalars {
 struct SpmvPlan {
   int kernel = TFELCU_SPMV_VECTOR;
   int lanes = 8;                         // lanes per row of the vector kernel
-  // TMA-streamed kernel: row blocks of bounded nnz
-  DevBuf<int32_t> block_row;             // [n_blocks + 1]
+  // TMA-streamed kernel: slabs of bounded rows and entries
+  DevBuf<int32_t> desc;                  // [n_blocks][4]: first row, end row, first entry, end entry
   int n_blocks = 0;
+  int row_lanes = 1;                     // threads per row of the in-slab row reduction
   int tile_nnz = 0, tile_rows = 0;
 };
 

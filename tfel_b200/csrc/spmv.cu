@@ -11,14 +11,17 @@
 //
 // Algorithmic bytes per product: 12 nnz + 4 (n + 1) + 8 n (x once) + 8 n (y).
 #include "solver.cuh"
+#include "sortutil.cuh"
 
 namespace tfelcu {
 
-constexpr int kStreamThreads = 256;
-constexpr int kStreamStages = 3;
+constexpr int kConsumers = 256;          // consumer threads (8 warps); warp 8 is the producer
+constexpr int kStreamThreads = kConsumers + 32;
+constexpr int kStreamStages = 4;
 constexpr int kTileNnz = 2048;          // capacity of one slab (entries)
 constexpr int kTilePad = 8;             // slack for 16-byte aligned bulk copies
-constexpr int kRowWeight = 4;           // a row counts as len + kRowWeight when slabs are cut
+constexpr int kTileRows = 256;          // rows of one slab (one consumer thread per row when LANES == 1)
+constexpr int kRowPtrCap = kTileRows + 12;
 
 // ------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D bulk copy global -> shared (SASS: UBLKCP / SYNCS)
@@ -34,6 +37,9 @@ __device__ __forceinline__ void mbar_fence_init() {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -55,23 +61,39 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ void consumer_barrier() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------
-// slab boundaries: slab b starts at the first row r with rowptr[r] + kRowWeight * r >= b * S
+// slabs: consecutive rows whose weight sum_r max(len_r, unit) stays below the tile capacity; with
+// unit = kTileNnz / kTileRows * LANES a slab has at most kTileRows / LANES rows and kTileNnz entries.
+// Slab b starts at the first row whose exclusive weight prefix reaches b * S.
 // ------------------------------------------------------------------------------------------
 
-__global__ void k_slab_rows(const int32_t* __restrict__ rowptr, size_t n, long long S, int n_blocks,
-                            int32_t* __restrict__ block_row) {
+__global__ void k_row_weights(const int32_t* __restrict__ rowptr, size_t n, int unit, unsigned long long* __restrict__ w) {
+  const size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int len = rowptr[r + 1] - rowptr[r];
+  w[r] = (unsigned long long)(len > unit ? len : unit);
+}
+
+__global__ void k_slab_desc(const unsigned long long* __restrict__ cum, const int32_t* __restrict__ rowptr, size_t n,
+                            unsigned long long S, int n_blocks, int4* __restrict__ desc) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b > n_blocks) return;
-  if (b == n_blocks) { block_row[b] = (int32_t)n; return; }
-  const long long target = (long long)b * S;
-  size_t lo = 0, hi = n;
-  while (lo < hi) {
-    const size_t mid = lo + (hi - lo) / 2;
-    if ((long long)rowptr[mid] + (long long)kRowWeight * (long long)mid < target) lo = mid + 1; else hi = mid;
+  if (b >= n_blocks) return;
+  int r[2];
+  for (int k = 0; k < 2; ++k) {
+    const unsigned long long target = (unsigned long long)(b + k) * S;
+    size_t lo = 0, hi = n;
+    while (lo < hi) {
+      const size_t mid = lo + (hi - lo) / 2;
+      if (cum[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    r[k] = (int)lo;
   }
-  block_row[b] = (int32_t)lo;
+  if (b == n_blocks - 1) r[1] = (int)n;
+  desc[b] = make_int4(r[0], r[1], rowptr[r[0]], rowptr[r[1]]);
 }
 
 __global__ void k_max_row_len(const int32_t* __restrict__ rowptr, size_t n, int* __restrict__ out) {
@@ -89,37 +111,51 @@ void spmv_plan(tfelcu_solver* s) {
   k_max_row_len<<<grid_for(s->n, 256), 256, 0, ctx->stream>>>(s->rowptr, s->n, mx.p);
   ctx->count(); TFELCU_LAUNCH_CHECK();
   int max_len = 0; ctx->download(&max_len, mx.p, 1);
-  const long long S = (long long)kTileNnz - max_len - kRowWeight;
+  P.row_lanes = avg > 12.0 ? 4 : 1;
+  const int unit = kTileNnz / kTileRows * P.row_lanes;
+  const long long S = (long long)kTileNnz - kTilePad - (max_len > unit ? max_len : unit);
   int want = s->params.spmv_kernel;
   if (want == TFELCU_SPMV_AUTO) want = TFELCU_SPMV_TMA_STREAM;
   if (want == TFELCU_SPMV_TMA_STREAM && (S < kTileNnz / 2 || s->n == 0)) want = TFELCU_SPMV_VECTOR;   // very long rows
   P.kernel = want;
   if (want != TFELCU_SPMV_TMA_STREAM) return;
-  const long long total = (long long)s->nnz + (long long)kRowWeight * (long long)s->n;
-  P.n_blocks = (int)((total + S - 1) / S);
-  if (P.n_blocks < 1) P.n_blocks = 1;
-  P.tile_nnz = kTileNnz; P.tile_rows = kTileNnz / kRowWeight;
-  P.block_row.alloc((size_t)P.n_blocks + 1);
-  k_slab_rows<<<grid_for((size_t)P.n_blocks + 1, 256), 256, 0, ctx->stream>>>(s->rowptr, s->n, S, P.n_blocks, P.block_row.p);
+  DevBuf<unsigned long long> w(s->n), cum(s->n);
+  k_row_weights<<<grid_for(s->n, 256), 256, 0, ctx->stream>>>(s->rowptr, s->n, unit, w.p);
   ctx->count(); TFELCU_LAUNCH_CHECK();
+  exclusive_sum(ctx, w.p, cum.p, s->n);
+  unsigned long long last_cum = 0, last_w = 0;
+  ctx->download(&last_cum, cum.p + (s->n - 1), 1);
+  ctx->download(&last_w, w.p + (s->n - 1), 1);
+  const unsigned long long total = last_cum + last_w;
+  P.n_blocks = (int)((total + (unsigned long long)S - 1) / (unsigned long long)S);
+  if (P.n_blocks < 1) P.n_blocks = 1;
+  P.tile_nnz = kTileNnz; P.tile_rows = kTileRows / P.row_lanes;
+  P.desc.alloc((size_t)P.n_blocks * 4);
+  k_slab_desc<<<grid_for((size_t)P.n_blocks, 256), 256, 0, ctx->stream>>>(cum.p, s->rowptr, s->n, (unsigned long long)S,
+                                                                          P.n_blocks, reinterpret_cast<int4*>(P.desc.p));
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  ctx->sync();
 }
 
 // ------------------------------------------------------------------------------------------
-// TMA-streamed kernel
+// TMA-streamed kernel: warp 8 = producer (bulk copies of [val | colind | rowptr] slabs, kStreamStages deep),
+// warps 0-7 = consumers (products with all gathers of a thread in flight, then one row per LANES threads)
 // ------------------------------------------------------------------------------------------
 
 struct StreamSmem {
   double val[kStreamStages][kTileNnz + kTilePad];
   int32_t col[kStreamStages][kTileNnz + kTilePad];
+  int32_t rp[kStreamStages][kRowPtrCap];
+  int32_t meta[kStreamStages][8];   // r0, r1, first copied entry a0, entries copied, first copied row r0a, e0, e1
   uint64_t full[kStreamStages];
-  int32_t meta[kStreamStages][4];   // r0, r1, aligned first entry, entries copied
-  double red[kStreamThreads / 32];
+  uint64_t empty[kStreamStages];
+  double red[kConsumers / 32];
 };
 
-template <bool DOT>
+template <bool DOT, int LANES>
 __global__ void __launch_bounds__(kStreamThreads, 2)
 k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind, const double* __restrict__ val,
-              const int32_t* __restrict__ block_row, int n_blocks, const double* __restrict__ x,
+              const int4* __restrict__ desc, int n_blocks, const double* __restrict__ x,
               double* __restrict__ y, double* __restrict__ dot_partial, const KrylovScalars* __restrict__ scal) {
   extern __shared__ __align__(128) unsigned char raw[];
   StreamSmem& S = *reinterpret_cast<StreamSmem*>(raw);
@@ -129,73 +165,97 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
   }
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int s = 0; s < kStreamStages; ++s) mbar_init(&S.full[s], 1);
+    for (int s = 0; s < kStreamStages; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], kConsumers); }
     mbar_fence_init();
   }
   __syncthreads();
-
-  // producer (thread 0): one slab = two bulk copies landing on the stage's mbarrier
-  auto issue = [&](int b, int stage) {
-    const int r0 = block_row[b], r1 = block_row[b + 1];
-    const int e0 = rowptr[r0], e1 = rowptr[r1];
-    const int a0 = e0 & ~3, a1 = (e1 + 3) & ~3;
-    const int cnt = a1 - a0;
-    S.meta[stage][0] = r0; S.meta[stage][1] = r1; S.meta[stage][2] = a0; S.meta[stage][3] = cnt;
-    if (cnt > 0) {
-      mbar_expect_tx(&S.full[stage], (uint32_t)cnt * 12u);
-      bulk_g2s(S.val[stage], val + a0, (uint32_t)cnt * 8u, &S.full[stage]);
-      bulk_g2s(S.col[stage], colind + a0, (uint32_t)cnt * 4u, &S.full[stage]);
-    } else {
-      mbar_expect_tx(&S.full[stage], 0u);
-    }
-  };
-
   const int first = blockIdx.x, step = gridDim.x;
-  if (tid == 0)
-    for (int s = 0; s < kStreamStages; ++s)
-      if (first + s * step < n_blocks) issue(first + s * step, s);
-  __syncthreads();   // meta of the first slabs is visible
 
+  if (tid >= kConsumers) {
+    // ---- producer warp: lane 0 issues, one slab descriptor prefetched ahead --------------------
+    if (tid == kConsumers) {
+      int4 d = first < n_blocks ? __ldg(desc + first) : make_int4(0, 0, 0, 0);
+      int it = 0;
+      for (int b = first; b < n_blocks; b += step, ++it) {
+        const int stage = it % kStreamStages;
+        const int4 cur = d;
+        if (b + step < n_blocks) d = __ldg(desc + b + step);
+        if (it >= kStreamStages) mbar_wait(&S.empty[stage], (uint32_t)(it / kStreamStages - 1) & 1u);
+        const int r0 = cur.x, r1 = cur.y, e0 = cur.z, e1 = cur.w;
+        const int a0 = e0 & ~3, a1 = (e1 + 3) & ~3;
+        const int cnt = a1 - a0;
+        const int r0a = r0 & ~3;
+        const int rcnt = ((r1 + 1 + 3) & ~3) - r0a;
+        int32_t* m = S.meta[stage];
+        m[0] = r0; m[1] = r1; m[2] = a0; m[3] = cnt; m[4] = r0a; m[5] = e0; m[6] = e1;
+        mbar_expect_tx(&S.full[stage], (uint32_t)cnt * 12u + (uint32_t)rcnt * 4u);
+        if (cnt > 0) {
+          bulk_g2s(S.val[stage], val + a0, (uint32_t)cnt * 8u, &S.full[stage]);
+          bulk_g2s(S.col[stage], colind + a0, (uint32_t)cnt * 4u, &S.full[stage]);
+        }
+        bulk_g2s(S.rp[stage], rowptr + r0a, (uint32_t)rcnt * 4u, &S.full[stage]);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers -----------------------------------------------------------------------------
   double dot = 0.0;
   int it = 0;
   for (int b = first; b < n_blocks; b += step, ++it) {
     const int stage = it % kStreamStages;
-    const uint32_t parity = (uint32_t)(it / kStreamStages) & 1u;
-    mbar_wait(&S.full[stage], parity);
-    const int r0 = S.meta[stage][0], r1 = S.meta[stage][1], a0 = S.meta[stage][2], cnt = S.meta[stage][3];
+    mbar_wait(&S.full[stage], (uint32_t)(it / kStreamStages) & 1u);
+    const int32_t* m = S.meta[stage];
+    const int r0 = m[0], r1 = m[1], a0 = m[2], r0a = m[4];
+    const int lo = m[5] - a0, hi = m[6] - a0;   // entries of this slab's rows inside the copied window
     double* vs = S.val[stage];
     const int32_t* cs = S.col[stage];
-    // products, entry-strided: every gather is independent of the others
-    for (int e = tid; e < cnt; e += kStreamThreads) {
-      const int ge = a0 + e;
-      // entries before the first row / after the last row of the slab belong to neighbours: skip the gather
-      const int32_t c = cs[e];
-      vs[e] = (ge >= rowptr[r0] && ge < rowptr[r1]) ? vs[e] * __ldg(x + c) : 0.0;
+    const int32_t* rp = S.rp[stage];
+    // products: all gathers of a thread are issued before the first use
+    constexpr int U = kTileNnz / kConsumers;
+    int c[U]; double xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = tid + u * kConsumers;
+      c[u] = (e >= lo && e < hi) ? cs[e] : -1;
     }
-    __syncthreads();
-    // one thread per row, ascending column order
-    for (int r = r0 + tid; r < r1; r += kStreamThreads) {
-      const int rs = rowptr[r] - a0, re = rowptr[r + 1] - a0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = tid + u * kConsumers;
+      if (c[u] >= 0) vs[e] *= xv[u];
+    }
+    consumer_barrier();
+    // rows: LANES threads per row; LANES == 1 sums in ascending column order like a scalar CSR loop
+    {
+      const int r = r0 + tid / LANES;
+      const int lane = tid % LANES;
       double sum = 0.0;
-      for (int e = rs; e < re; ++e) sum += vs[e];
-      y[r] = sum;
-      if (DOT) dot += __ldg(x + r) * sum;
+      const bool has = r < r1;
+      if (has) {
+        const int rs = rp[r - r0a] - a0, re = rp[r + 1 - r0a] - a0;
+        for (int e = rs + lane; e < re; e += LANES) sum += vs[e];
+      }
+      if (LANES > 1) {
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      }
+      if (has && lane == 0) {
+        y[r] = sum;
+        if (DOT) dot += __ldg(x + r) * sum;
+      }
     }
     fence_proxy_async();   // generic-proxy accesses of this stage are ordered before the next bulk copy into it
-    __syncthreads();
-    if (tid == 0) {
-      const int nb = b + kStreamStages * step;
-      if (nb < n_blocks) issue(nb, stage);
-    }
-    __syncthreads();       // meta written by thread 0 for a later iteration of this stage
+    mbar_arrive(&S.empty[stage]);
   }
   if (DOT) {
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_down_sync(0xffffffffu, dot, o);
     if ((tid & 31) == 0) S.red[tid >> 5] = dot;
-    __syncthreads();
+    consumer_barrier();
     if (tid == 0) {
       double t = 0.0;
-      for (int w = 0; w < kStreamThreads / 32; ++w) t += S.red[w];
+      for (int w = 0; w < kConsumers / 32; ++w) t += S.red[w];
       dot_partial[blockIdx.x] = t;
     }
   }
@@ -260,16 +320,19 @@ int spmv_launch(tfelcu_solver* s, const double* d_x, double* d_y, double* dot_pa
     const size_t smem = sizeof(StreamSmem);
     static bool configured = false;
     if (!configured) {
-      TFELCU_CK(cudaFuncSetAttribute(k_spmv_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      TFELCU_CK(cudaFuncSetAttribute(k_spmv_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TFELCU_CK(cudaFuncSetAttribute(k_spmv_stream<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TFELCU_CK(cudaFuncSetAttribute(k_spmv_stream<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TFELCU_CK(cudaFuncSetAttribute(k_spmv_stream<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TFELCU_CK(cudaFuncSetAttribute(k_spmv_stream<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = true;
     }
-    if (dot_partial)
-      k_spmv_stream<true><<<grid, kStreamThreads, smem, ctx->stream>>>(s->rowptr, s->colind, s->val, s->plan.block_row.p,
-                                                                      s->plan.n_blocks, d_x, d_y, dot_partial, scal);
-    else
-      k_spmv_stream<false><<<grid, kStreamThreads, smem, ctx->stream>>>(s->rowptr, s->colind, s->val, s->plan.block_row.p,
-                                                                       s->plan.n_blocks, d_x, d_y, nullptr, scal);
+    const int4* desc = reinterpret_cast<const int4*>(s->plan.desc.p);
+#define TFELCU_STREAM(D, L)                                                                                        \
+    k_spmv_stream<D, L><<<grid, kStreamThreads, smem, ctx->stream>>>(s->rowptr, s->colind, s->val, desc, s->plan.n_blocks, \
+                                                                    d_x, d_y, dot_partial, scal)
+    if (s->plan.row_lanes == 4) { if (dot_partial) TFELCU_STREAM(true, 4); else TFELCU_STREAM(false, 4); }
+    else { if (dot_partial) TFELCU_STREAM(true, 1); else TFELCU_STREAM(false, 1); }
+#undef TFELCU_STREAM
     ctx->count(); TFELCU_LAUNCH_CHECK();
     return grid;
   }
