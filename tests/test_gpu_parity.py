@@ -192,7 +192,9 @@ def test_ilu0_factors_match_oracle(ctx):
 
 @pytest.mark.parametrize("problem,kw", [
     (problems.stokes(10), dict(method="gmres", precond="ilu0", restart=300)),
-    (problems.navier_stokes(8), dict(method="gmres", precond="ilu0", restart=300)),
+    # ILU(0) of the indefinite Navier-Stokes matrix is so ill-conditioned that a 1e-11 preconditioned residual
+    # leaves a 1e-7 error (the oracle's ILU(0)-GMRES behaves the same): full GMRES with Jacobi scaling instead
+    (problems.navier_stokes(8), dict(method="gmres", precond="jacobi", restart=900)),
     (problems.tet("p2", 4), dict(method="cg", precond="block_jacobi", block_size=4)),
     (problems.tet("p1", 6), dict(method="gmres", precond="jacobi", restart=100)),
     (problems.laplace2(12), dict(method="gmres", precond="none", restart=50)),

@@ -64,7 +64,8 @@ __global__ void k_extract_diag(const int32_t* __restrict__ rowptr, const int32_t
   double v = 1.0;
   for (int e = rowptr[r]; e < rowptr[r + 1]; ++e)
     if (colind[e] == (int32_t)r) v = val[e];
-  d[r] = invert ? 1.0 / v : v;
+  if (invert) d[r] = v != 0.0 ? 1.0 / v : 1.0;   // a zero diagonal (pressure block of Stokes) is left unscaled
+  else d[r] = v;
 }
 
 // x0: the Dirichlet lift (identity rows take their right-hand side), zero elsewhere
@@ -123,11 +124,12 @@ __global__ void k_cg_set_scalars(const double* __restrict__ partial_bb, const do
   S->done = (S->rr <= S->target2) ? 1 : 0;
 }
 
-// alpha = rz / pq; x += alpha p; r -= alpha q; [Jacobi / none: partial sums of r.z] and of r.r
+// alpha = rz / pq; r -= alpha q; [Jacobi / none: partial sums of r.z] and of r.r. The companion update
+// x += alpha p is done by k_cg_direction, which reads p anyway (two vector passes less per iteration).
 __global__ void __launch_bounds__(kVecThreads)
-k_cg_update(const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ dinv,
+k_cg_update(const double* __restrict__ q, const double* __restrict__ dinv,
             int fused_precond, size_t n, const double* __restrict__ partial_pq, int n_pq,
-            double* __restrict__ x, double* __restrict__ r, double* __restrict__ partial_rz,
+            double* __restrict__ r, double* __restrict__ partial_rz,
             double* __restrict__ partial_rr, KrylovScalars* __restrict__ S) {
   __shared__ double red[kVecThreads / 32];
   __shared__ double bc[1];
@@ -136,17 +138,14 @@ k_cg_update(const double* __restrict__ p, const double* __restrict__ q, const do
   const double alpha = S->rz / pq;
   double rz = 0.0, rr = 0.0;
   const size_t n2 = n / 2;
-  const double2* p2 = reinterpret_cast<const double2*>(p);
   const double2* q2 = reinterpret_cast<const double2*>(q);
   const double2* d2 = reinterpret_cast<const double2*>(dinv);
-  double2* x2 = reinterpret_cast<double2*>(x);
   double2* r2 = reinterpret_cast<double2*>(r);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
-    const double2 pv = p2[i], qv = q2[i];
-    double2 xv = x2[i], rv = r2[i];
-    xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+    const double2 qv = q2[i];
+    double2 rv = r2[i];
     rv.x -= alpha * qv.x; rv.y -= alpha * qv.y;
-    x2[i] = xv; r2[i] = rv;
+    r2[i] = rv;
     rr += rv.x * rv.x; rr += rv.y * rv.y;
     if (fused_precond) {
       if (dinv) { const double2 dv = d2[i]; rz += rv.x * (dv.x * rv.x); rz += rv.y * (dv.y * rv.y); }
@@ -155,7 +154,6 @@ k_cg_update(const double* __restrict__ p, const double* __restrict__ q, const do
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const size_t i = n - 1;
-    x[i] += alpha * p[i];
     const double ri = r[i] - alpha * q[i];
     r[i] = ri;
     rr += ri * ri;
@@ -179,17 +177,19 @@ k_dot_partial(const double* __restrict__ a, const double* __restrict__ b, size_t
   if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
 
-// beta = rz_new / rz; p = z + beta p; the new scalars are published by a separate tiny kernel (k_cg_commit) after
-// every CTA has read the old ones
+// x += alpha p (alpha of this iteration, published by k_cg_update); beta = rz_new / rz; p = z + beta p; the new
+// scalars are published by a separate tiny kernel (k_cg_commit) after every CTA has read the old ones
 __global__ void __launch_bounds__(kVecThreads)
 k_cg_direction(const double* __restrict__ r, const double* __restrict__ dinv, const double* __restrict__ z_in, size_t n,
                const double* __restrict__ partial_rz, int n_partial,
-               double* __restrict__ p, KrylovScalars* __restrict__ S) {
+               double* __restrict__ p, double* __restrict__ x, KrylovScalars* __restrict__ S) {
   __shared__ double bc[1];
   if (S->done) return;
   const double rz_new = cta_sum_partials(partial_rz, n_partial, bc);
   const double rz_old = S->rz;
   const double beta = rz_new / rz_old;
+  const double alpha = S->alpha;
+  double2* x2 = reinterpret_cast<double2*>(x);
   const size_t n2 = n / 2;
   const double2* r2 = reinterpret_cast<const double2*>(r);
   const double2* d2 = reinterpret_cast<const double2*>(dinv);
@@ -200,12 +200,16 @@ k_cg_direction(const double* __restrict__ r, const double* __restrict__ dinv, co
     if (z_in) zv = z2[i];
     else { zv = r2[i]; if (dinv) { const double2 dv = d2[i]; zv.x *= dv.x; zv.y *= dv.y; } }
     double2 pv = p2[i];
+    double2 xv = x2[i];
+    xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+    x2[i] = xv;
     pv.x = zv.x + beta * pv.x; pv.y = zv.y + beta * pv.y;
     p2[i] = pv;
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const size_t i = n - 1;
     const double zi = z_in ? z_in[i] : (dinv ? dinv[i] * r[i] : r[i]);
+    x[i] += alpha * p[i];
     p[i] = zi + beta * p[i];
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -392,15 +396,15 @@ void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep) {
       const bool sampled = sample_begin(issued + it);
       const int n_pq = spmv_launch(s, s->p.p, s->q.p, P_pq, S); ++n_spmv;
       if (sampled) TFELCU_CK(cudaEventRecord(prof.back(), ctx->stream));
-      k_cg_update<<<vg, kVecThreads, 0, ctx->stream>>>(s->p.p, s->q.p, dinv, fused ? 1 : 0, n, P_pq, n_pq,
-                                                      s->x.p, s->r.p, P_rz, P_rr, S);
+      k_cg_update<<<vg, kVecThreads, 0, ctx->stream>>>(s->q.p, dinv, fused ? 1 : 0, n, P_pq, n_pq, s->r.p, P_rz, P_rr, S);
       ctx->count(); TFELCU_LAUNCH_CHECK();
       if (!fused) {
         apply_precond(s, s->r.p, s->z.p);
         k_dot_partial<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, s->z.p, n, P_rz, S);
         ctx->count(); TFELCU_LAUNCH_CHECK();
       }
-      k_cg_direction<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, dinv, fused ? nullptr : s->z.p, n, P_rz, vg, s->p.p, S);
+      k_cg_direction<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, dinv, fused ? nullptr : s->z.p, n, P_rz, vg, s->p.p,
+                                                         s->x.p, S);
       ctx->count(); TFELCU_LAUNCH_CHECK();
       k_cg_commit<<<1, 32, 0, ctx->stream>>>(P_rr, vg, S);
       ctx->count(); TFELCU_LAUNCH_CHECK();

@@ -22,6 +22,7 @@ struct SpmvPlan {
   DevBuf<int32_t> desc;                  // [n_blocks][4]: first row, end row, first entry, end entry
   int n_blocks = 0;
   int row_lanes = 1;                     // threads per row of the in-slab row reduction
+  int cfg = 0;                           // tile shape (spmv.cu: kCfgs)
   int tile_nnz = 0, tile_rows = 0;
 };
 

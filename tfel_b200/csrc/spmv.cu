@@ -1,10 +1,13 @@
 // FP64 CSR sparse matrix-vector product (what PETSc's MatMult does for the reference, solver.cpp:169).
 // The operator is the reference's own CSR (int32 indices, rows / columns ascending, solver.cpp:71-96).
 //
-//  k_spmv_stream  (default): persistent CTAs stream contiguous [val | colind] slabs of the matrix into shared
-//                 memory with TMA bulk copies (cp.async.bulk + mbarrier, 3-stage ring), form the products
-//                 val * x[col] with entry-strided (coalesced, conflict-free) accesses, then reduce each row
-//                 sequentially in ascending column order -- the same order and rounding as a scalar CSR loop.
+//  k_spmv_stream  (default): persistent CTAs; a producer warp streams contiguous [val | colind | rowptr] slabs of
+//                 the matrix into a shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier); consumer
+//                 threads own one row each (LANES == 1): they read their entries from shared memory, issue all
+//                 gathers x[col] of a group of 8 entries before the first use, and sum in ascending column order --
+//                 the same order as a scalar CSR loop. Consecutive rows of a finite element matrix have
+//                 consecutive columns, so the gathers of a warp coalesce. Warps run decoupled: the only
+//                 synchronisation is the full / empty mbarrier pair of a ring stage.
 //  k_spmv_vector  : a sub-warp of 2..32 lanes per row, shuffle reduction; used for validation and for matrices
 //                 whose rows do not fit a slab.
 // Both can fuse the dot product x . (A x) of conjugate gradients (per-CTA partial sums, fixed order).
@@ -13,15 +16,11 @@
 #include "solver.cuh"
 #include "sortutil.cuh"
 
+#include <cstdlib>
+
 namespace tfelcu {
 
-constexpr int kConsumers = 256;          // consumer threads (8 warps); warp 8 is the producer
-constexpr int kStreamThreads = kConsumers + 32;
-constexpr int kStreamStages = 4;
-constexpr int kTileNnz = 2048;          // capacity of one slab (entries)
 constexpr int kTilePad = 8;             // slack for 16-byte aligned bulk copies
-constexpr int kTileRows = 256;          // rows of one slab (one consumer thread per row when LANES == 1)
-constexpr int kRowPtrCap = kTileRows + 12;
 
 // ------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D bulk copy global -> shared (SASS: UBLKCP / SYNCS)
@@ -58,16 +57,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void consumer_barrier() {
-  asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
-}
 
 // ------------------------------------------------------------------------------------------
 // slabs: consecutive rows whose weight sum_r max(len_r, unit) stays below the tile capacity; with
-// unit = kTileNnz / kTileRows * LANES a slab has at most kTileRows / LANES rows and kTileNnz entries.
+// unit = tile_nnz / tile_rows a slab has at most tile_rows rows and tile_nnz entries.
 // Slab b starts at the first row whose exclusive weight prefix reaches b * S.
 // ------------------------------------------------------------------------------------------
 
@@ -101,6 +94,17 @@ __global__ void k_max_row_len(const int32_t* __restrict__ rowptr, size_t n, int*
   if (r < n) atomicMax(out, rowptr[r + 1] - rowptr[r]);
 }
 
+// tile shapes of the streamed kernel: (entries, consumer threads, ring stages, CTAs per SM)
+struct StreamCfg { int tile_nnz, consumers, stages, ctas_per_sm; };
+static const StreamCfg kCfgs[] = {
+    {1024, 128, 3, 5},   // 0: default (measured best inside CG on configs[1]: 0.261 ms, 6.68 TB/s)
+    {2048, 256, 4, 2},   // 1
+    {1024, 128, 4, 4},   // 2
+    {2048, 256, 2, 4},   // 3
+    {512, 64, 4, 8},     // 4
+};
+constexpr int kNumCfgs = (int)(sizeof(kCfgs) / sizeof(kCfgs[0]));
+
 void spmv_plan(tfelcu_solver* s) {
   Ctx* ctx = s->ctx;
   SpmvPlan& P = s->plan;
@@ -111,12 +115,19 @@ void spmv_plan(tfelcu_solver* s) {
   k_max_row_len<<<grid_for(s->n, 256), 256, 0, ctx->stream>>>(s->rowptr, s->n, mx.p);
   ctx->count(); TFELCU_LAUNCH_CHECK();
   int max_len = 0; ctx->download(&max_len, mx.p, 1);
-  P.row_lanes = avg > 12.0 ? 4 : 1;
-  const int unit = kTileNnz / kTileRows * P.row_lanes;
-  const long long S = (long long)kTileNnz - kTilePad - (max_len > unit ? max_len : unit);
+  P.cfg = 0;
+  if (const char* e = std::getenv("TFELCU_SPMV_CFG")) {   // tuning knob
+    const int c = std::atoi(e);
+    if (c >= 0 && c < kNumCfgs) P.cfg = c;
+  }
+  const StreamCfg& C = kCfgs[P.cfg];
+  P.row_lanes = avg > 16.0 ? 4 : 1;
+  const int tile_rows = C.consumers / P.row_lanes;
+  const int unit = C.tile_nnz / tile_rows;
+  const long long S = (long long)C.tile_nnz - kTilePad - (max_len > unit ? max_len : unit);
   int want = s->params.spmv_kernel;
   if (want == TFELCU_SPMV_AUTO) want = TFELCU_SPMV_TMA_STREAM;
-  if (want == TFELCU_SPMV_TMA_STREAM && (S < kTileNnz / 2 || s->n == 0)) want = TFELCU_SPMV_VECTOR;   // very long rows
+  if (want == TFELCU_SPMV_TMA_STREAM && (S < C.tile_nnz / 2 || s->n == 0)) want = TFELCU_SPMV_VECTOR;   // very long rows
   P.kernel = want;
   if (want != TFELCU_SPMV_TMA_STREAM) return;
   DevBuf<unsigned long long> w(s->n), cum(s->n);
@@ -129,7 +140,7 @@ void spmv_plan(tfelcu_solver* s) {
   const unsigned long long total = last_cum + last_w;
   P.n_blocks = (int)((total + (unsigned long long)S - 1) / (unsigned long long)S);
   if (P.n_blocks < 1) P.n_blocks = 1;
-  P.tile_nnz = kTileNnz; P.tile_rows = kTileRows / P.row_lanes;
+  P.tile_nnz = C.tile_nnz; P.tile_rows = tile_rows;
   P.desc.alloc((size_t)P.n_blocks * 4);
   k_slab_desc<<<grid_for((size_t)P.n_blocks, 256), 256, 0, ctx->stream>>>(cum.p, s->rowptr, s->n, (unsigned long long)S,
                                                                           P.n_blocks, reinterpret_cast<int4*>(P.desc.p));
@@ -138,56 +149,57 @@ void spmv_plan(tfelcu_solver* s) {
 }
 
 // ------------------------------------------------------------------------------------------
-// TMA-streamed kernel: warp 8 = producer (bulk copies of [val | colind | rowptr] slabs, kStreamStages deep),
-// warps 0-7 = consumers (products with all gathers of a thread in flight, then one row per LANES threads)
+// TMA-streamed kernel
 // ------------------------------------------------------------------------------------------
 
+template <int TILE_NNZ, int CONSUMERS, int STAGES>
 struct StreamSmem {
-  double val[kStreamStages][kTileNnz + kTilePad];
-  int32_t col[kStreamStages][kTileNnz + kTilePad];
-  int32_t rp[kStreamStages][kRowPtrCap];
-  int32_t meta[kStreamStages][8];   // r0, r1, first copied entry a0, entries copied, first copied row r0a, e0, e1
-  uint64_t full[kStreamStages];
-  uint64_t empty[kStreamStages];
-  double red[kConsumers / 32];
+  double val[STAGES][TILE_NNZ + kTilePad];
+  int32_t col[STAGES][TILE_NNZ + kTilePad];
+  int32_t rp[STAGES][CONSUMERS + 12];
+  int32_t meta[STAGES][4];   // r0, r1, first copied entry a0, first copied row r0a
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  double red[CONSUMERS / 32];
 };
 
-template <bool DOT, int LANES>
-__global__ void __launch_bounds__(kStreamThreads, 2)
+template <bool DOT, int LANES, int TILE_NNZ, int CONSUMERS, int STAGES, int CTAS>
+__global__ void __launch_bounds__(CONSUMERS + 32, CTAS)
 k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind, const double* __restrict__ val,
               const int4* __restrict__ desc, int n_blocks, const double* __restrict__ x,
               double* __restrict__ y, double* __restrict__ dot_partial, const KrylovScalars* __restrict__ scal) {
   extern __shared__ __align__(128) unsigned char raw[];
-  StreamSmem& S = *reinterpret_cast<StreamSmem*>(raw);
+  using Smem = StreamSmem<TILE_NNZ, CONSUMERS, STAGES>;
+  Smem& S = *reinterpret_cast<Smem*>(raw);
   if (scal && scal->done) {
     if (DOT && threadIdx.x == 0) dot_partial[blockIdx.x] = 0.0;
     return;
   }
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int s = 0; s < kStreamStages; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], kConsumers); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], CONSUMERS); }
     mbar_fence_init();
   }
   __syncthreads();
   const int first = blockIdx.x, step = gridDim.x;
 
-  if (tid >= kConsumers) {
+  if (tid >= CONSUMERS) {
     // ---- producer warp: lane 0 issues, one slab descriptor prefetched ahead --------------------
-    if (tid == kConsumers) {
+    if (tid == CONSUMERS) {
       int4 d = first < n_blocks ? __ldg(desc + first) : make_int4(0, 0, 0, 0);
       int it = 0;
       for (int b = first; b < n_blocks; b += step, ++it) {
-        const int stage = it % kStreamStages;
+        const int stage = it % STAGES;
         const int4 cur = d;
         if (b + step < n_blocks) d = __ldg(desc + b + step);
-        if (it >= kStreamStages) mbar_wait(&S.empty[stage], (uint32_t)(it / kStreamStages - 1) & 1u);
+        if (it >= STAGES) mbar_wait(&S.empty[stage], (uint32_t)(it / STAGES - 1) & 1u);
         const int r0 = cur.x, r1 = cur.y, e0 = cur.z, e1 = cur.w;
         const int a0 = e0 & ~3, a1 = (e1 + 3) & ~3;
         const int cnt = a1 - a0;
         const int r0a = r0 & ~3;
         const int rcnt = ((r1 + 1 + 3) & ~3) - r0a;
         int32_t* m = S.meta[stage];
-        m[0] = r0; m[1] = r1; m[2] = a0; m[3] = cnt; m[4] = r0a; m[5] = e0; m[6] = e1;
+        m[0] = r0; m[1] = r1; m[2] = a0; m[3] = r0a;
         mbar_expect_tx(&S.full[stage], (uint32_t)cnt * 12u + (uint32_t)rcnt * 4u);
         if (cnt > 0) {
           bulk_g2s(S.val[stage], val + a0, (uint32_t)cnt * 8u, &S.full[stage]);
@@ -199,63 +211,56 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
     return;
   }
 
-  // ---- consumers -----------------------------------------------------------------------------
+  // ---- consumers: LANES threads per row ---------------------------------------------------------
   double dot = 0.0;
   int it = 0;
+  const int row_in_slab = tid / LANES, lane = tid % LANES;
   for (int b = first; b < n_blocks; b += step, ++it) {
-    const int stage = it % kStreamStages;
-    mbar_wait(&S.full[stage], (uint32_t)(it / kStreamStages) & 1u);
+    const int stage = it % STAGES;
+    mbar_wait(&S.full[stage], (uint32_t)(it / STAGES) & 1u);
     const int32_t* m = S.meta[stage];
-    const int r0 = m[0], r1 = m[1], a0 = m[2], r0a = m[4];
-    const int lo = m[5] - a0, hi = m[6] - a0;   // entries of this slab's rows inside the copied window
-    double* vs = S.val[stage];
+    const int r0 = m[0], r1 = m[1], a0 = m[2], r0a = m[3];
+    const double* vs = S.val[stage];
     const int32_t* cs = S.col[stage];
     const int32_t* rp = S.rp[stage];
-    // products: all gathers of a thread are issued before the first use
-    constexpr int U = kTileNnz / kConsumers;
-    int c[U]; double xv[U];
+    const int r = r0 + row_in_slab;
+    const bool has = r < r1;
+    double sum = 0.0;
+    if (has) {
+      const int rs = rp[r - r0a] - a0, re = rp[r + 1 - r0a] - a0;
+      constexpr int U = 8;
+      for (int e = rs + lane; e < re; e += U * LANES) {
+        int c[U]; double v[U], xv[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int e = tid + u * kConsumers;
-      c[u] = (e >= lo && e < hi) ? cs[e] : -1;
-    }
+        for (int u = 0; u < U; ++u) {
+          const int eu = e + u * LANES;
+          const bool ok = eu < re;
+          c[u] = ok ? cs[eu] : -1;
+          v[u] = ok ? vs[eu] : 0.0;
+        }
 #pragma unroll
-    for (int u = 0; u < U; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+        for (int u = 0; u < U; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int e = tid + u * kConsumers;
-      if (c[u] >= 0) vs[e] *= xv[u];
-    }
-    consumer_barrier();
-    // rows: LANES threads per row; LANES == 1 sums in ascending column order like a scalar CSR loop
-    {
-      const int r = r0 + tid / LANES;
-      const int lane = tid % LANES;
-      double sum = 0.0;
-      const bool has = r < r1;
-      if (has) {
-        const int rs = rp[r - r0a] - a0, re = rp[r + 1 - r0a] - a0;
-        for (int e = rs + lane; e < re; e += LANES) sum += vs[e];
-      }
-      if (LANES > 1) {
-#pragma unroll
-        for (int o = LANES / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      }
-      if (has && lane == 0) {
-        y[r] = sum;
-        if (DOT) dot += __ldg(x + r) * sum;
+        for (int u = 0; u < U; ++u) sum += v[u] * xv[u];
       }
     }
-    fence_proxy_async();   // generic-proxy accesses of this stage are ordered before the next bulk copy into it
-    mbar_arrive(&S.empty[stage]);
+    mbar_arrive(&S.empty[stage]);   // shared-memory reads of this stage are done
+    if (LANES > 1) {
+#pragma unroll
+      for (int o = LANES / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if (has && lane == 0) {
+      y[r] = sum;
+      if (DOT) dot += __ldg(x + r) * sum;
+    }
   }
   if (DOT) {
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_down_sync(0xffffffffu, dot, o);
     if ((tid & 31) == 0) S.red[tid >> 5] = dot;
-    consumer_barrier();
+    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
     if (tid == 0) {
       double t = 0.0;
-      for (int w = 0; w < kConsumers / 32; ++w) t += S.red[w];
+      for (int w = 0; w < CONSUMERS / 32; ++w) t += S.red[w];
       dot_partial[blockIdx.x] = t;
     }
   }
@@ -303,7 +308,7 @@ k_spmv_vector(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
 }
 
 static int stream_grid(tfelcu_solver* s) {
-  int g = s->ctx->sm_count * 2;
+  int g = s->ctx->sm_count * kCfgs[s->plan.cfg].ctas_per_sm;
   if (g > s->plan.n_blocks) g = s->plan.n_blocks;
   return g < 1 ? 1 : g;
 }
@@ -313,26 +318,43 @@ int spmv_partial_count(tfelcu_solver* s) {
   return (int)grid_for(s->n * (size_t)s->plan.lanes, 256);
 }
 
+template <bool DOT, int LANES, int TILE_NNZ, int CONSUMERS, int STAGES, int CTAS>
+static void launch_stream(tfelcu_solver* s, int grid, const double* d_x, double* d_y, double* dot_partial,
+                          const KrylovScalars* scal) {
+  auto kern = k_spmv_stream<DOT, LANES, TILE_NNZ, CONSUMERS, STAGES, CTAS>;
+  const size_t smem = sizeof(StreamSmem<TILE_NNZ, CONSUMERS, STAGES>);
+  static bool configured = false;   // one flag per instantiation
+  if (!configured) {
+    TFELCU_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  kern<<<grid, CONSUMERS + 32, smem, s->ctx->stream>>>(s->rowptr, s->colind, s->val, reinterpret_cast<const int4*>(s->plan.desc.p),
+                                                      s->plan.n_blocks, d_x, d_y, dot_partial, scal);
+}
+
+template <int TILE_NNZ, int CONSUMERS, int STAGES, int CTAS>
+static void launch_stream_cfg(tfelcu_solver* s, int grid, const double* d_x, double* d_y, double* dot_partial,
+                              const KrylovScalars* scal) {
+  if (s->plan.row_lanes == 4) {
+    if (dot_partial) launch_stream<true, 4, TILE_NNZ, CONSUMERS, STAGES, CTAS>(s, grid, d_x, d_y, dot_partial, scal);
+    else launch_stream<false, 4, TILE_NNZ, CONSUMERS, STAGES, CTAS>(s, grid, d_x, d_y, dot_partial, scal);
+  } else {
+    if (dot_partial) launch_stream<true, 1, TILE_NNZ, CONSUMERS, STAGES, CTAS>(s, grid, d_x, d_y, dot_partial, scal);
+    else launch_stream<false, 1, TILE_NNZ, CONSUMERS, STAGES, CTAS>(s, grid, d_x, d_y, dot_partial, scal);
+  }
+}
+
 int spmv_launch(tfelcu_solver* s, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal) {
   Ctx* ctx = s->ctx;
   if (s->plan.kernel == TFELCU_SPMV_TMA_STREAM) {
     const int grid = stream_grid(s);
-    const size_t smem = sizeof(StreamSmem);
-    static bool configured = false;
-    if (!configured) {
-      TFELCU_CK(cudaFuncSetAttribute(k_spmv_stream<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      TFELCU_CK(cudaFuncSetAttribute(k_spmv_stream<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      TFELCU_CK(cudaFuncSetAttribute(k_spmv_stream<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      TFELCU_CK(cudaFuncSetAttribute(k_spmv_stream<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
+    switch (s->plan.cfg) {
+      case 1: launch_stream_cfg<2048, 256, 4, 2>(s, grid, d_x, d_y, dot_partial, scal); break;
+      case 2: launch_stream_cfg<1024, 128, 4, 4>(s, grid, d_x, d_y, dot_partial, scal); break;
+      case 3: launch_stream_cfg<2048, 256, 2, 4>(s, grid, d_x, d_y, dot_partial, scal); break;
+      case 4: launch_stream_cfg<512, 64, 4, 8>(s, grid, d_x, d_y, dot_partial, scal); break;
+      default: launch_stream_cfg<1024, 128, 3, 5>(s, grid, d_x, d_y, dot_partial, scal); break;
     }
-    const int4* desc = reinterpret_cast<const int4*>(s->plan.desc.p);
-#define TFELCU_STREAM(D, L)                                                                                        \
-    k_spmv_stream<D, L><<<grid, kStreamThreads, smem, ctx->stream>>>(s->rowptr, s->colind, s->val, desc, s->plan.n_blocks, \
-                                                                    d_x, d_y, dot_partial, scal)
-    if (s->plan.row_lanes == 4) { if (dot_partial) TFELCU_STREAM(true, 4); else TFELCU_STREAM(false, 4); }
-    else { if (dot_partial) TFELCU_STREAM(true, 1); else TFELCU_STREAM(false, 1); }
-#undef TFELCU_STREAM
     ctx->count(); TFELCU_LAUNCH_CHECK();
     return grid;
   }
