@@ -151,6 +151,9 @@ int tfelcu_mesh_boundary_download(const tfelcu_mesh* mesh, uint32_t* el, uint32_
 int tfelcu_fes_create(tfelcu_ctx* ctx, tfelcu_mesh* mesh, int fe, tfelcu_fes** fes);
 int tfelcu_fes_destroy(tfelcu_fes* fes);
 int tfelcu_fes_info(const tfelcu_fes* fes, int* fe, size_t* n_dof, int* n_dof_per_cell);
+/* first dof of every entity kind (fes.hpp:33-72 numbers vertices, then edges, faces, cell): offsets[0..3] for kinds
+ * 0..3, offsets[4] = n_dof; a kind without dofs has offsets[sd] == offsets[sd + 1] */
+int tfelcu_fes_kind_offsets(const tfelcu_fes* fes, size_t* offsets /* [5] */);
 int tfelcu_fes_download_dof_map(const tfelcu_fes* fes, uint32_t* dof_map /* [K][n_dof_per_cell] */);
 int tfelcu_fes_download_g2l(const tfelcu_fes* fes, uint32_t* g2l /* [n_dof][2] */);
 /* get_dof_space_coordinate, fes.hpp:190-202, for dofs[n] (host); x[n][dim] (host) */
@@ -174,6 +177,14 @@ int tfelcu_fes_dirichlet_get(const tfelcu_fes* fes, uint32_t* dofs, double* valu
  * performs clear() (identity rows of the Dirichlet dofs registered SO FAR, :159-165). */
 int tfelcu_matrix_create(tfelcu_ctx* ctx, int n_test, tfelcu_fes* const* test,
                          int n_trial, tfelcu_fes* const* trial, tfelcu_matrix** m);
+/* Row-block distribution (one process per GPU): the form holds only the rows this rank owns -- up to 8 contiguous
+ * segments [row_begin[i], row_end[i]) of GLOBAL rows (block layout [u0 | u1 | p]), ascending, disjoint, each inside one
+ * component: e.g. the vertex dofs and the edge dofs of a horizontal strip of gen_square_mesh for every P2 component.
+ * The segments of all ranks must tile [0, n_rows). Local rows are the segments concatenated; columns stay global.
+ * The reference has no distributed mode. */
+int tfelcu_matrix_create_rows(tfelcu_ctx* ctx, int n_test, tfelcu_fes* const* test, int n_trial, tfelcu_fes* const* trial,
+                              int n_segments, const size_t* row_begin, const size_t* row_end, tfelcu_matrix** m);
+int tfelcu_matrix_local_rows(const tfelcu_matrix* m, size_t* n_local);
 int tfelcu_matrix_destroy(tfelcu_matrix* m);
 int tfelcu_matrix_clear(tfelcu_matrix* m);
 int tfelcu_matrix_info(const tfelcu_matrix* m, size_t* n_rows, size_t* n_cols, size_t* nnz);
@@ -190,6 +201,8 @@ int tfelcu_matrix_color_count(tfelcu_matrix* m, int* n_colors);
 /* ---- linear form / vectors ------------------------------------------------------------------
  * linear_form<fes> (linear_form.hpp:9-20); also plain device vectors in the block layout. */
 int tfelcu_vector_create(tfelcu_ctx* ctx, int n_test, tfelcu_fes* const* test, tfelcu_vector** v);
+int tfelcu_vector_create_rows(tfelcu_ctx* ctx, int n_test, tfelcu_fes* const* test, int n_segments,
+                              const size_t* row_begin, const size_t* row_end, tfelcu_vector** v);
 int tfelcu_vector_destroy(tfelcu_vector* v);
 int tfelcu_vector_clear(tfelcu_vector* v);
 int tfelcu_vector_size(const tfelcu_vector* v, size_t* n);
@@ -221,6 +234,8 @@ int tfelcu_matrix_solve(tfelcu_matrix* m, const tfelcu_vector* b, tfelcu_solver*
 int tfelcu_matrix_make_rhs(const tfelcu_matrix* m, const tfelcu_vector* b, double* rhs);
 /* y = A x with the solver's SpMV kernel; x, y host or device. Timed variant for the roofline:
  * runs `reps` launches and returns the average kernel time (CUDA events on the context stream). */
+/* distributed operator: owned entries of every rank -> full vector in reference numbering on every rank */
+int tfelcu_solver_gather(tfelcu_solver* s, const double* x_local, double* x_global);
 int tfelcu_solver_spmv(tfelcu_solver* s, const double* x, double* y);
 int tfelcu_solver_spmv_bench(tfelcu_solver* s, int reps, double* avg_ms, double* algorithmic_bytes);
 

@@ -296,3 +296,34 @@ def test_full_size_structure_properties(ctx):
         s.close()
     finally:
         cuda_runner.close(B)
+
+
+@pytest.mark.parametrize("problem", [problems.poissong("p2", 14), problems.stokes(9), problems.tet("p1b", 4)],
+                         ids=lambda p: p.name)
+def test_owned_row_segments_equal_rows_of_the_full_form(ctx, problem):
+    """The row-distributed form restricted to any rank's segments holds exactly those rows of the
+    reference CSR, bit for bit (no second GPU needed for this part of the multi-GPU path)."""
+    from tfel_b200 import capi, dist as tdist
+    B = cuda_runner.build(ctx, problem)
+    try:
+        cuda_runner.assemble(B)
+        rp, ci, val = B.matrix.csr()
+        b_full = B.vector.download()
+        offs = [s.kind_offsets() for s in B.spaces]
+        for P, rank in ((3, 0), (3, 1), (3, 2), (8, 5)):
+            segs = tdist.strip_segments(offs, P, rank)
+            A = capi.Matrix(B.spaces, B.spaces, rows=segs)
+            b = capi.Vector(B.spaces, rows=segs)
+            A.assemble(problem.quad, cuda_runner.lower(problem.bilinear), B.fields)
+            b.assemble(problem.quad, cuda_runner.lower(problem.linear), B.fields)
+            lrp, lci, lval = A.csr()
+            rows = np.concatenate([np.arange(s[0], s[1]) for s in segs])
+            sel = np.concatenate([np.arange(rp[g], rp[g + 1]) for g in rows])
+            assert np.array_equal(np.diff(lrp), np.diff(rp)[rows])
+            assert np.array_equal(lci, ci[sel])
+            assert np.array_equal(lval, val[sel])
+            assert np.array_equal(b.download(), b_full[rows])
+            assert np.array_equal(A.make_rhs(b), B.matrix.make_rhs(B.vector)[rows])
+            A.close(); b.close()
+    finally:
+        cuda_runner.close(B)

@@ -68,19 +68,19 @@ SYMBOLS = [
     "tfelcu_mesh_create", "tfelcu_mesh_gen_square", "tfelcu_mesh_gen_cube", "tfelcu_mesh_destroy",
     "tfelcu_mesh_info", "tfelcu_mesh_download", "tfelcu_mesh_geometry", "tfelcu_mesh_boundary",
     "tfelcu_mesh_boundary_download",
-    "tfelcu_fes_create", "tfelcu_fes_destroy", "tfelcu_fes_info", "tfelcu_fes_download_dof_map",
+    "tfelcu_fes_create", "tfelcu_fes_destroy", "tfelcu_fes_info", "tfelcu_fes_kind_offsets", "tfelcu_fes_download_dof_map",
     "tfelcu_fes_download_g2l", "tfelcu_fes_dof_coordinates", "tfelcu_fes_boundary_dofs",
     "tfelcu_fes_boundary_dofs_get", "tfelcu_fes_add_dirichlet", "tfelcu_fes_add_dirichlet_const",
     "tfelcu_fes_dirichlet_count", "tfelcu_fes_dirichlet_get",
-    "tfelcu_matrix_create", "tfelcu_matrix_destroy", "tfelcu_matrix_clear", "tfelcu_matrix_info",
+    "tfelcu_matrix_create", "tfelcu_matrix_create_rows", "tfelcu_matrix_local_rows", "tfelcu_matrix_destroy", "tfelcu_matrix_clear", "tfelcu_matrix_info",
     "tfelcu_matrix_set_scatter", "tfelcu_matrix_assemble", "tfelcu_matrix_download_csr",
     "tfelcu_matrix_color_count",
-    "tfelcu_vector_create", "tfelcu_vector_destroy", "tfelcu_vector_clear", "tfelcu_vector_size",
+    "tfelcu_vector_create", "tfelcu_vector_create_rows", "tfelcu_vector_destroy", "tfelcu_vector_clear", "tfelcu_vector_size",
     "tfelcu_vector_assemble", "tfelcu_vector_download", "tfelcu_vector_upload", "tfelcu_vector_device_ptr",
     "tfelcu_integrate",
     "tfelcu_solver_create", "tfelcu_solver_destroy", "tfelcu_solver_set_operator",
     "tfelcu_solver_set_operator_csr", "tfelcu_solver_solve", "tfelcu_matrix_solve", "tfelcu_matrix_make_rhs",
-    "tfelcu_solver_spmv", "tfelcu_solver_spmv_bench",
+    "tfelcu_solver_gather", "tfelcu_solver_spmv", "tfelcu_solver_spmv_bench",
 ]
 
 _lib = None
@@ -234,6 +234,12 @@ class Space:
             lib().tfelcu_fes_destroy(self.h)
             self.h = C.c_void_p()
 
+    def kind_offsets(self):
+        """first dof of the vertex / edge / face / cell dofs, then n_dof"""
+        out = (C.c_size_t * 5)()
+        _ck(lib().tfelcu_fes_kind_offsets(self.h, out))
+        return [int(v) for v in out]
+
     def dof_map(self):
         out = np.zeros((self.mesh.n_cells, self.nd), dtype=np.uint32)
         _ck(lib().tfelcu_fes_download_dof_map(self.h, _ptr(out)))
@@ -357,14 +363,19 @@ class _Integrand:
 class Matrix:
     """bilinear_form<te, tr> and its sparse_matrix (bilinear_form.hpp:9-19, solver.hpp:236-283)."""
 
-    def __init__(self, test, trial=None, scatter=None):
+    def __init__(self, test, trial=None, scatter=None, rows=None):
+        """rows: None (all rows) or a list of (begin, end) global row segments this rank owns"""
         test = list(test) if isinstance(test, (list, tuple)) else [test]
         trial = test if trial is None else (list(trial) if isinstance(trial, (list, tuple)) else [trial])
         self.test, self.trial, self.ctx = test, trial, test[0].ctx
         self.h = C.c_void_p()
         te = (C.c_void_p * len(test))(*[s.h for s in test])
         tr = (C.c_void_p * len(trial))(*[s.h for s in trial])
-        _ck(lib().tfelcu_matrix_create(self.ctx.h, len(test), te, len(trial), tr, C.byref(self.h)))
+        if rows is None:
+            _ck(lib().tfelcu_matrix_create(self.ctx.h, len(test), te, len(trial), tr, C.byref(self.h)))
+        else:
+            rb = (C.c_size_t * len(rows))(*[int(r[0]) for r in rows]); re = (C.c_size_t * len(rows))(*[int(r[1]) for r in rows])
+            _ck(lib().tfelcu_matrix_create_rows(self.ctx.h, len(test), te, len(trial), tr, len(rows), rb, re, C.byref(self.h)))
         if scatter is not None:
             _ck(lib().tfelcu_matrix_set_scatter(self.h, SCATTER[scatter]))
         self._info()
@@ -373,6 +384,9 @@ class Matrix:
         nr = C.c_size_t(); nc = C.c_size_t(); nnz = C.c_size_t()
         _ck(lib().tfelcu_matrix_info(self.h, C.byref(nr), C.byref(nc), C.byref(nnz)))
         self.n_rows, self.n_cols, self.nnz = nr.value, nc.value, nnz.value
+        nl = C.c_size_t()
+        _ck(lib().tfelcu_matrix_local_rows(self.h, C.byref(nl)))
+        self.n_local = nl.value
 
     def close(self):
         if self.h:
@@ -390,7 +404,7 @@ class Matrix:
 
     def csr(self, values=True):
         self._info()
-        rowptr = np.zeros(self.n_rows + 1, dtype=np.int32); colind = np.zeros(self.nnz, dtype=np.int32)
+        rowptr = np.zeros(self.n_local + 1, dtype=np.int32); colind = np.zeros(self.nnz, dtype=np.int32)
         val = np.zeros(self.nnz) if values else None
         _ck(lib().tfelcu_matrix_download_csr(self.h, _ptr(rowptr), _ptr(colind), _ptr(val)))
         return (rowptr, colind, val) if values else (rowptr, colind)
@@ -401,7 +415,7 @@ class Matrix:
         return n.value
 
     def make_rhs(self, b):
-        out = np.zeros(self.n_rows)
+        out = np.zeros(self.n_local)
         _ck(lib().tfelcu_matrix_make_rhs(self.h, b.h, _ptr(out)))
         return out
 
@@ -416,12 +430,16 @@ class Matrix:
 class Vector:
     """linear_form<fes> (linear_form.hpp:9-20)."""
 
-    def __init__(self, test):
+    def __init__(self, test, rows=None):
         test = list(test) if isinstance(test, (list, tuple)) else [test]
         self.test, self.ctx = test, test[0].ctx
         self.h = C.c_void_p()
         te = (C.c_void_p * len(test))(*[s.h for s in test])
-        _ck(lib().tfelcu_vector_create(self.ctx.h, len(test), te, C.byref(self.h)))
+        if rows is None:
+            _ck(lib().tfelcu_vector_create(self.ctx.h, len(test), te, C.byref(self.h)))
+        else:
+            rb = (C.c_size_t * len(rows))(*[int(r[0]) for r in rows]); re = (C.c_size_t * len(rows))(*[int(r[1]) for r in rows])
+            _ck(lib().tfelcu_vector_create_rows(self.ctx.h, len(test), te, len(rows), rb, re, C.byref(self.h)))
         n = C.c_size_t()
         _ck(lib().tfelcu_vector_size(self.h, C.byref(n)))
         self.n = n.value
@@ -483,7 +501,8 @@ class Solver:
         """a: Matrix (device resident, zero copy) or (rowptr, colind, val) host CSR."""
         if isinstance(a, Matrix):
             _ck(lib().tfelcu_solver_set_operator(self.h, a.h))
-            self.n = a.n_rows
+            self.n = a.n_local
+            self.n_global = a.n_rows
         else:
             rowptr, colind, val = a
             rowptr = np.ascontiguousarray(rowptr, dtype=np.int32); colind = np.ascontiguousarray(colind, dtype=np.int32)
@@ -507,6 +526,15 @@ class Solver:
             y = np.zeros(self.n)
         _ck(lib().tfelcu_solver_spmv(self.h, _ptr(x), _ptr(y)))
         return y
+
+    def gather(self, x_local, out=None):
+        """owned entries of every rank -> full vector in reference numbering (on every rank)"""
+        if isinstance(x_local, np.ndarray):
+            x_local = np.ascontiguousarray(x_local, dtype=np.float64)
+        if out is None:
+            out = np.zeros(self.n_global)
+        _ck(lib().tfelcu_solver_gather(self.h, _ptr(x_local), _ptr(out)))
+        return out
 
     def spmv_bench(self, reps=20):
         ms = C.c_double(); nbytes = C.c_double()

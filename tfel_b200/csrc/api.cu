@@ -289,6 +289,23 @@ int tfelcu_fes_info(const tfelcu_fes* fes, int* fe, size_t* n_dof, int* n_dof_pe
   });
 }
 
+int tfelcu_fes_kind_offsets(const tfelcu_fes* fes, size_t* offsets) {
+  return guarded([&] {
+    TFELCU_REQUIRE(fes && offsets, "null pointer");
+    const int dim = fes->mesh->dim;
+    size_t next = fes->n_dof;
+    for (int sd = 4; sd >= 0; --sd) {
+      if (sd > dim || !tfelcu::fe_dofs_on(dim, fes->fe, sd)) { offsets[sd] = next; continue; }
+      offsets[sd] = fes->kind_offset[sd];
+      next = offsets[sd];
+    }
+    offsets[4] = fes->n_dof;
+    // kinds without dofs collapse onto the start of the next kind that has some
+    for (int sd = 3; sd >= 0; --sd)
+      if (sd > dim || !tfelcu::fe_dofs_on(dim, fes->fe, sd)) offsets[sd] = offsets[sd + 1];
+  });
+}
+
 int tfelcu_fes_download_dof_map(const tfelcu_fes* fes, uint32_t* dof_map) {
   return guarded([&] {
     TFELCU_REQUIRE(fes && dof_map, "null pointer");
@@ -383,23 +400,39 @@ int tfelcu_fes_dirichlet_get(const tfelcu_fes* fes, uint32_t* dofs, double* valu
 
 // ---- bilinear form / matrix -----------------------------------------------------------------------
 
+static void matrix_create_impl(tfelcu_ctx* ctx, int n_test, tfelcu_fes* const* test, int n_trial, tfelcu_fes* const* trial,
+                               int n_seg, const size_t* row_begin, const size_t* row_end, tfelcu_matrix** m) {
+  TFELCU_REQUIRE(ctx && test && trial && m, "null pointer");
+  use_device(ctx);
+  std::unique_ptr<tfelcu_matrix> A(new tfelcu_matrix());
+  A->ctx = ctx;
+  fill_space(A->test, n_test, test, "test space");
+  fill_space(A->trial, n_trial, trial, "trial space");
+  TFELCU_REQUIRE(A->test.fes[0]->mesh == A->trial.fes[0]->mesh, "test and trial spaces live on different meshes");
+  A->mesh = A->test.fes[0]->mesh;
+  A->n_rows = A->test.total(); A->n_cols = A->trial.total();
+  A->rows = tfelcu::make_row_map(A->test, n_seg, row_begin, row_end);
+  tfelcu::matrix_snapshot_dirichlet(A.get());
+  tfelcu::matrix_build_pattern(A.get());
+  ctx->sync();
+  *m = A.release();
+}
+
 int tfelcu_matrix_create(tfelcu_ctx* ctx, int n_test, tfelcu_fes* const* test, int n_trial, tfelcu_fes* const* trial,
                          tfelcu_matrix** m) {
+  return guarded([&] { matrix_create_impl(ctx, n_test, test, n_trial, trial, 0, nullptr, nullptr, m); });
+}
+
+int tfelcu_matrix_create_rows(tfelcu_ctx* ctx, int n_test, tfelcu_fes* const* test, int n_trial, tfelcu_fes* const* trial,
+                              int n_segments, const size_t* row_begin, const size_t* row_end, tfelcu_matrix** m) {
   return guarded([&] {
-    TFELCU_REQUIRE(ctx && test && trial && m, "null pointer");
-    use_device(ctx);
-    std::unique_ptr<tfelcu_matrix> A(new tfelcu_matrix());
-    A->ctx = ctx;
-    fill_space(A->test, n_test, test, "test space");
-    fill_space(A->trial, n_trial, trial, "trial space");
-    TFELCU_REQUIRE(A->test.fes[0]->mesh == A->trial.fes[0]->mesh, "test and trial spaces live on different meshes");
-    A->mesh = A->test.fes[0]->mesh;
-    A->n_rows = A->test.total(); A->n_cols = A->trial.total();
-    tfelcu::matrix_snapshot_dirichlet(A.get());
-    tfelcu::matrix_build_pattern(A.get());
-    ctx->sync();
-    *m = A.release();
+    TFELCU_REQUIRE(row_begin && row_end, "null row ranges");
+    matrix_create_impl(ctx, n_test, test, n_trial, trial, n_segments, row_begin, row_end, m);
   });
+}
+
+int tfelcu_matrix_local_rows(const tfelcu_matrix* m, size_t* n_local) {
+  return guarded([&] { TFELCU_REQUIRE(m && n_local, "null pointer"); *n_local = m->rows.n_local(); });
 }
 
 int tfelcu_matrix_destroy(tfelcu_matrix* m) {
@@ -454,7 +487,7 @@ int tfelcu_matrix_download_csr(const tfelcu_matrix* m, int32_t* rowptr, int32_t*
     TFELCU_REQUIRE(m != nullptr, "null matrix");
     use_device(m->ctx);
     if (val) tfelcu::matrix_ensure_cleared(const_cast<tfelcu_matrix*>(m));
-    copy_out(m->ctx, rowptr, m->rowptr.p, m->n_rows + 1);
+    copy_out(m->ctx, rowptr, m->rowptr.p, m->rows.n_local() + 1);
     copy_out(m->ctx, colind, m->colind.p, m->nnz);
     copy_out(m->ctx, val, m->val.p, m->nnz);
   });
@@ -471,16 +504,28 @@ int tfelcu_matrix_color_count(tfelcu_matrix* m, int* n_colors) {
 
 // ---- linear form / vectors --------------------------------------------------------------------------
 
+static void vector_create_impl(tfelcu_ctx* ctx, int n_test, tfelcu_fes* const* test, int n_seg, const size_t* row_begin,
+                               const size_t* row_end, tfelcu_vector** v) {
+  TFELCU_REQUIRE(ctx && test && v, "null pointer");
+  use_device(ctx);
+  std::unique_ptr<tfelcu_vector> b(new tfelcu_vector());
+  b->ctx = ctx;
+  fill_space(b->space, n_test, test, "test space");
+  b->rows = tfelcu::make_row_map(b->space, n_seg, row_begin, row_end);
+  b->data.alloc(b->rows.n_local());
+  ctx->zero(b->data.p, b->rows.n_local());
+  *v = b.release();
+}
+
 int tfelcu_vector_create(tfelcu_ctx* ctx, int n_test, tfelcu_fes* const* test, tfelcu_vector** v) {
+  return guarded([&] { vector_create_impl(ctx, n_test, test, 0, nullptr, nullptr, v); });
+}
+
+int tfelcu_vector_create_rows(tfelcu_ctx* ctx, int n_test, tfelcu_fes* const* test, int n_segments, const size_t* row_begin,
+                              const size_t* row_end, tfelcu_vector** v) {
   return guarded([&] {
-    TFELCU_REQUIRE(ctx && test && v, "null pointer");
-    use_device(ctx);
-    std::unique_ptr<tfelcu_vector> b(new tfelcu_vector());
-    b->ctx = ctx;
-    fill_space(b->space, n_test, test, "test space");
-    b->data.alloc(b->space.total());
-    ctx->zero(b->data.p, b->space.total());
-    *v = b.release();
+    TFELCU_REQUIRE(row_begin && row_end, "null row ranges");
+    vector_create_impl(ctx, n_test, test, n_segments, row_begin, row_end, v);
   });
 }
 
@@ -551,15 +596,26 @@ int tfelcu_solver_destroy(tfelcu_solver* s) {
   return guarded([&] { if (s) { use_device(s->ctx); s->ctx->sync(); delete s; } });
 }
 
+// the solver works on the device arrays of the bilinear form (zero copy); a form that holds only the rows this rank
+// owns makes the solve distributed
+static void attach_matrix(tfelcu_solver* s, tfelcu_matrix* m) {
+  s->own_rowptr.release(); s->own_colind.release(); s->own_val.release();
+  s->n = m->rows.n_local(); s->n_global = m->n_rows; s->nnz = m->nnz;
+  s->rowptr = m->rowptr.p; s->colind = m->colind.p; s->val = m->val.p;
+  s->dist.reset();
+  if (!m->rows.whole()) {
+    s->dist.reset(new tfelcu::DistPlan());
+    s->dist->rows = m->rows;
+  }
+}
+
 int tfelcu_solver_set_operator(tfelcu_solver* s, tfelcu_matrix* m) {
   return guarded([&] {
     TFELCU_REQUIRE(s && m, "null pointer");
     TFELCU_REQUIRE(m->n_rows == m->n_cols, "the operator of a linear solve must be square");
     use_device(s->ctx);
     tfelcu::matrix_ensure_cleared(m);
-    s->own_rowptr.release(); s->own_colind.release(); s->own_val.release();
-    s->n = m->n_rows; s->nnz = m->nnz;
-    s->rowptr = m->rowptr.p; s->colind = m->colind.p; s->val = m->val.p;
+    attach_matrix(s, m);
     tfelcu::solver_setup(s);
   });
 }
@@ -580,8 +636,9 @@ int tfelcu_solver_set_operator_csr(tfelcu_solver* s, size_t n, const int32_t* ro
       TFELCU_CK(cudaMemcpyAsync(s->own_val.p, val, (size_t)nnz * sizeof(double), cudaMemcpyDefault, ctx->stream));
     }
     ctx->sync();
-    s->n = n; s->nnz = (size_t)nnz;
+    s->n = n; s->n_global = n; s->nnz = (size_t)nnz;
     s->rowptr = s->own_rowptr.p; s->colind = s->own_colind.p; s->val = s->own_val.p;
+    s->dist.reset();
     tfelcu::solver_setup(s);
   });
 }
@@ -607,15 +664,20 @@ int tfelcu_solver_solve(tfelcu_solver* s, const double* rhs, double* x, tfelcu_s
 // rhs of bilinear_form::solve: b with the Dirichlet rows replaced by their values (bilinear_form.hpp:126-137)
 namespace {
 __global__ void k_make_rhs(const double* __restrict__ b, const uint8_t* __restrict__ dir_row,
-                           const double* __restrict__ dir_value, size_t n, double* __restrict__ rhs) {
+                           const double* __restrict__ dir_value, tfelcu::RowMap R, double* __restrict__ rhs) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i < n) rhs[i] = dir_row[i] ? dir_value[i] : b[i];
+  if (i >= R.local_off[R.n]) return;
+  const unsigned long long g = R.to_global(i);
+  rhs[i] = dir_row[g] ? dir_value[g] : b[i];
 }
 
 void make_rhs(const tfelcu_matrix* m, const tfelcu_vector* b, double* d_rhs) {
-  TFELCU_REQUIRE(b->data.n == m->n_rows, "linear form and bilinear form have different test spaces");
+  bool same = b->space.total() == m->n_rows && b->rows.n == m->rows.n;
+  for (int c = 0; same && c < m->rows.n; ++c) same = b->rows.g_begin[c] == m->rows.g_begin[c] && b->rows.g_end[c] == m->rows.g_end[c];
+  TFELCU_REQUIRE(same, "linear form and bilinear form have different test spaces or own different rows");
   Ctx* ctx = m->ctx;
-  k_make_rhs<<<tfelcu::grid_for(m->n_rows, 256), 256, 0, ctx->stream>>>(b->data.p, m->dir_row.p, m->dir_value.p, m->n_rows, d_rhs);
+  if (!m->rows.n_local()) return;
+  k_make_rhs<<<tfelcu::grid_for(m->rows.n_local(), 256), 256, 0, ctx->stream>>>(b->data.p, m->dir_row.p, m->dir_value.p, m->rows, d_rhs);
   ctx->count(); TFELCU_LAUNCH_CHECK();
 }
 }  // namespace
@@ -624,9 +686,9 @@ int tfelcu_matrix_make_rhs(const tfelcu_matrix* m, const tfelcu_vector* b, doubl
   return guarded([&] {
     TFELCU_REQUIRE(m && b && rhs, "null pointer");
     use_device(m->ctx);
-    DevBuf<double> d(m->n_rows);
+    DevBuf<double> d(m->rows.n_local());
     make_rhs(m, b, d.p);
-    copy_out(m->ctx, rhs, d.p, m->n_rows);
+    copy_out(m->ctx, rhs, d.p, m->rows.n_local());
   });
 }
 
@@ -638,20 +700,49 @@ int tfelcu_matrix_solve(tfelcu_matrix* m, const tfelcu_vector* b, tfelcu_solver*
     Ctx* ctx = m->ctx;
     // s.set_operator(a) on every solve, like bilinear_form.hpp:139
     tfelcu::matrix_ensure_cleared(m);
-    s->own_rowptr.release(); s->own_colind.release(); s->own_val.release();
-    s->n = m->n_rows; s->nnz = m->nnz;
-    s->rowptr = m->rowptr.p; s->colind = m->colind.p; s->val = m->val.p;
+    attach_matrix(s, m);
     tfelcu::solver_setup(s);
     tfelcu_solver_report local;
     tfelcu_solver_report* rep = report ? report : &local;
-    DevBuf<double> rhs(m->n_rows);
+    const size_t n_local = m->rows.n_local();
+    DevBuf<double> rhs(n_local);
     make_rhs(m, b, rhs.p);
-    if (tfelcu::is_device_pointer(x)) {
-      tfelcu::solver_solve(s, rhs.p, x, rep);
+    // the solution comes back in reference numbering, complete on every rank (an element of the trial space)
+    const bool x_on_device = tfelcu::is_device_pointer(x);
+    DevBuf<double> dx_full;
+    double* d_x = x;
+    if (!x_on_device) { dx_full.alloc(m->n_cols); d_x = dx_full.p; }
+    if (s->dist) {
+      DevBuf<double> x_local(n_local);
+      tfelcu::solver_solve(s, rhs.p, x_local.p, rep);
+      tfelcu::dist_gather(s, x_local.p, d_x);
+      ctx->sync();
     } else {
-      DevBuf<double> dx(m->n_rows);
-      tfelcu::solver_solve(s, rhs.p, dx.p, rep);
-      copy_out(ctx, x, dx.p, m->n_rows);
+      tfelcu::solver_solve(s, rhs.p, d_x, rep);
+    }
+    if (!x_on_device) copy_out(ctx, x, d_x, m->n_cols);
+  });
+}
+
+int tfelcu_solver_gather(tfelcu_solver* s, const double* x_local, double* x_global) {
+  return guarded([&] {
+    TFELCU_REQUIRE(s && x_local && x_global, "null pointer");
+    TFELCU_REQUIRE(s->rowptr != nullptr, "solver has no operator: call set_operator first");
+    use_device(s->ctx);
+    Ctx* ctx = s->ctx;
+    if (!s->dist) {   // nothing to gather
+      TFELCU_CK(cudaMemcpyAsync(x_global, x_local, s->n * sizeof(double), cudaMemcpyDefault, ctx->stream));
+      ctx->sync();
+      return;
+    }
+    Staged<double> xl(ctx, x_local, s->n);
+    if (tfelcu::is_device_pointer(x_global)) {
+      tfelcu::dist_gather(s, xl.p, x_global);
+      ctx->sync();
+    } else {
+      DevBuf<double> full(s->n_global);
+      tfelcu::dist_gather(s, xl.p, full.p);
+      copy_out(ctx, x_global, full.p, s->n_global);
     }
   });
 }
@@ -663,12 +754,18 @@ int tfelcu_solver_spmv(tfelcu_solver* s, const double* x, double* y) {
     use_device(s->ctx);
     Ctx* ctx = s->ctx;
     Staged<double> dx(ctx, x, s->n);
+    const double* in = dx.p;
+    if (s->dist) {   // owned entries + halo from the neighbours
+      TFELCU_CK(cudaMemcpyAsync(s->p.p, dx.p, s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      tfelcu::dist_halo_exchange(s, s->p.p, nullptr);
+      in = s->p.p;
+    }
     if (tfelcu::is_device_pointer(y)) {
-      tfelcu::solver_spmv(s, dx.p, y);
+      tfelcu::solver_spmv(s, in, y);
       ctx->sync();
     } else {
       DevBuf<double> dy(s->n);
-      tfelcu::solver_spmv(s, dx.p, dy.p);
+      tfelcu::solver_spmv(s, in, dy.p);
       copy_out(ctx, y, dy.p, s->n);
     }
   });

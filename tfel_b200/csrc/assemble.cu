@@ -280,7 +280,8 @@ __device__ __forceinline__ int find_in_row(const int32_t* __restrict__ colind, i
 
 struct RowBlock {
   const double* vertices; const uint32_t* cells;
-  const uint32_t* map_tr; uint32_t off_te, off_tr; size_t n_rows_comp;
+  const uint32_t* map_tr; uint32_t off_te, off_tr;
+  size_t row_begin, row_end, local_off;   // owned dofs of the test component and the local row of the first one
   const uint32_t* adj_ptr; const uint32_t* adj;
   const uint8_t* dir_row; const int32_t* rowptr; const int32_t* colind; double* val;
   int init_mode;   // STAGED only: 1 = values are uninitialised (pending clear()): write them fresh
@@ -291,19 +292,20 @@ __global__ void __launch_bounds__(kRowsPerCta) k_assemble_rows(const __grid_cons
   extern __shared__ double sm[];
   for (int idx = threadIdx.x; idx < F.n_stage; idx += blockDim.x) sm[idx] = __ldg(F.tables + idx);
   double* stage = sm + F.n_stage;
-  const size_t r0 = (size_t)blockIdx.x * kRowsPerCta;
-  size_t r1 = r0 + kRowsPerCta; if (r1 > B.n_rows_comp) r1 = B.n_rows_comp;
+  const size_t r0 = B.row_begin + (size_t)blockIdx.x * kRowsPerCta;
+  size_t r1 = r0 + kRowsPerCta; if (r1 > B.row_end) r1 = B.row_end;
+  const size_t to_local = B.local_off - B.row_begin;   // local row = dof + to_local (mod 2^64)
   int seg0 = 0, seg_len = 0;
   if constexpr (STAGED) {
-    seg0 = B.rowptr[B.off_te + r0];
-    seg_len = B.rowptr[B.off_te + r1] - seg0;
+    seg0 = B.rowptr[r0 + to_local];
+    seg_len = B.rowptr[r1 + to_local] - seg0;
     for (int e = threadIdx.x; e < seg_len; e += blockDim.x) stage[e] = 0.0;
   }
   __syncthreads();
   const size_t r = r0 + threadIdx.x;
   if (r < r1) {
     const size_t grow = B.off_te + r;
-    const int rs = B.rowptr[grow], re = B.rowptr[grow + 1];
+    const int rs = B.rowptr[r + to_local], re = B.rowptr[r + to_local + 1];
     if (!B.dir_row[grow]) {
       // bilinear_form.hpp:64-109 restricted to the cells that touch this row, in ascending cell order
       for (uint32_t a = B.adj_ptr[r]; a < B.adj_ptr[r + 1]; ++a) {
@@ -336,6 +338,7 @@ struct ColorBlock {
   const double* vertices; const uint32_t* cells;
   const uint32_t* map_te; const uint32_t* map_tr; uint32_t off_te, off_tr;
   const uint32_t* color_cells; size_t n_cells;
+  size_t row_begin, row_end, local_off;
   const uint8_t* dir_row; const int32_t* rowptr; const int32_t* colind; double* val;
 };
 
@@ -350,9 +353,12 @@ __global__ void __launch_bounds__(128) k_assemble_colored(const __grid_constant_
   CellGeom<DIM> g;
   load_cell_geometry<DIM>(B.vertices, B.cells + k * (DIM + 1), g);
   for (int i = 0; i < ND_TE; ++i) {
-    const size_t grow = B.off_te + B.map_te[k * ND_TE + i];
+    const size_t r = B.map_te[k * ND_TE + i];
+    if (r < B.row_begin || r >= B.row_end) continue;   // another process owns the row
+    const size_t grow = B.off_te + r;
     if (B.dir_row[grow]) continue;   // bilinear_form.hpp:183-186
-    const int rs = B.rowptr[grow], re = B.rowptr[grow + 1];
+    const size_t lrow = B.local_off + (r - B.row_begin);
+    const int rs = B.rowptr[lrow], re = B.rowptr[lrow + 1];
     double acc[ND_TR];
     element_row<DIM, ND_TE, ND_TR, CONST_COEF>(F, sm, k, i, g, acc);
 #pragma unroll
@@ -365,7 +371,7 @@ __global__ void __launch_bounds__(128) k_assemble_colored(const __grid_constant_
 
 struct VecBlock {
   const double* vertices; const uint32_t* cells;
-  uint32_t off_te; size_t n_rows_comp;
+  size_t row_begin, row_end, local_off;
   const uint32_t* adj_ptr; const uint32_t* adj;
   double* b;
 };
@@ -375,8 +381,8 @@ __global__ void __launch_bounds__(128) k_assemble_vector_rows(const __grid_const
   extern __shared__ double sm[];
   for (int idx = threadIdx.x; idx < F.n_stage; idx += blockDim.x) sm[idx] = __ldg(F.tables + idx);
   __syncthreads();
-  const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= B.n_rows_comp) return;
+  const size_t r = B.row_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B.row_end) return;
   double sum = 0.0;
   // linear_form.hpp:55-63: ordered scatter == ascending cell order per dof
   for (uint32_t a = B.adj_ptr[r]; a < B.adj_ptr[r + 1]; ++a) {
@@ -386,7 +392,7 @@ __global__ void __launch_bounds__(128) k_assemble_vector_rows(const __grid_const
     load_cell_geometry<DIM>(B.vertices, B.cells + k * (DIM + 1), g);
     sum += element_entry<DIM, ND_TE, CONST_COEF>(F, sm, k, i, g) * g.vol;
   }
-  B.b[B.off_te + r] += sum;
+  B.b[B.local_off + (r - B.row_begin)] += sum;
 }
 
 template <int DIM>
@@ -577,7 +583,8 @@ static void ensure_smem(Kern kern, size_t bytes) {
 
 template <int DIM, int ND_TE, int ND_TR>
 static void launch_rows(Ctx* ctx, const FormBuild& fb, const RowBlock& B, bool staged, size_t stage_doubles) {
-  const unsigned grid = grid_for(B.n_rows_comp, kRowsPerCta);
+  if (B.row_end <= B.row_begin) return;
+  const unsigned grid = grid_for(B.row_end - B.row_begin, kRowsPerCta);
   const size_t smem = ((size_t)fb.F.n_stage + (staged ? stage_doubles : 0)) * sizeof(double);
 #define TFELCU_ROWS(CC, ST)                                                                      \
   do {                                                                                           \
@@ -609,7 +616,8 @@ static void launch_colored(Ctx* ctx, const FormBuild& fb, const ColorBlock& B) {
 
 template <int DIM, int ND_TE>
 static void launch_vector(Ctx* ctx, const FormBuild& fb, const VecBlock& B) {
-  const unsigned grid = grid_for(B.n_rows_comp, 128);
+  if (B.row_end <= B.row_begin) return;
+  const unsigned grid = grid_for(B.row_end - B.row_begin, 128);
   const size_t smem = (size_t)fb.F.n_stage * sizeof(double);
   if (fb.const_coef) {
     auto kern = k_assemble_vector_rows<DIM, ND_TE, true>;
@@ -649,21 +657,26 @@ static void assemble_bilinear_dim(tfelcu_matrix* m, int quad, const tfelcu_facto
       if (fb.F.n_terms == 0) continue;   // the block only contributes (already stored) zeros
       fb.F.tables = upload_tables(ctx, fb.tables, table_scratch(ctx));
       const size_t stage_bytes = ((size_t)fb.F.n_stage + m->max_block_nnz) * sizeof(double);
-      const bool staged = single_block && !colored && te->nd == tr->nd && stage_bytes <= 160 * 1024;
+      const bool staged = single_block && m->rows.n == 1 && !colored && te->nd == tr->nd && stage_bytes <= 160 * 1024;
       if (!staged) matrix_ensure_cleared(m);
       if (!colored) {
         fes_transpose(te);
         RowBlock B;
         B.vertices = mesh->vertices.p; B.cells = mesh->cells.p; B.map_tr = tr->dof_map;
-        B.off_te = (uint32_t)m->test.offset[a]; B.off_tr = (uint32_t)m->trial.offset[b]; B.n_rows_comp = te->n_dof;
+        B.off_te = (uint32_t)m->test.offset[a]; B.off_tr = (uint32_t)m->trial.offset[b];
         B.adj_ptr = te->adj_ptr.p; B.adj = te->adj.p; B.dir_row = m->dir_row.p;
         B.rowptr = m->rowptr.p; B.colind = m->colind.p; B.val = m->val.p;
         B.init_mode = m->val_valid ? 0 : 1;
         const int nd_te = te->nd, nd_tr = tr->nd;
-        TFELCU_DISPATCH_ND(DIM, nd_te, NTE,
-          TFELCU_DISPATCH_ND(DIM, nd_tr, NTR,
-            if (staged) { if constexpr (NTE == NTR) launch_rows<DIM, NTE, NTR>(ctx, fb, B, true, m->max_block_nnz); }
-            else launch_rows<DIM, NTE, NTR>(ctx, fb, B, false, 0);))
+        for (int sg = 0; sg < m->rows.n; ++sg) {   // the owned row segments of this test component
+          if (m->rows.comp[sg] != a) continue;
+          B.row_begin = m->rows.g_begin[sg] - m->test.offset[a]; B.row_end = m->rows.g_end[sg] - m->test.offset[a];
+          B.local_off = m->rows.local_off[sg];
+          TFELCU_DISPATCH_ND(DIM, nd_te, NTE,
+            TFELCU_DISPATCH_ND(DIM, nd_tr, NTR,
+              if (staged) { if constexpr (NTE == NTR) launch_rows<DIM, NTE, NTR>(ctx, fb, B, true, m->max_block_nnz); }
+              else launch_rows<DIM, NTE, NTR>(ctx, fb, B, false, 0);))
+        }
         if (staged) m->val_valid = true;
       } else {
         ColorBlock B;
@@ -671,12 +684,17 @@ static void assemble_bilinear_dim(tfelcu_matrix* m, int quad, const tfelcu_facto
         B.off_te = (uint32_t)m->test.offset[a]; B.off_tr = (uint32_t)m->trial.offset[b];
         B.dir_row = m->dir_row.p; B.rowptr = m->rowptr.p; B.colind = m->colind.p; B.val = m->val.p;
         const int nd_te = te->nd, nd_tr = tr->nd;
-        for (int c = 0; c < m->n_colors; ++c) {
-          B.color_cells = m->color_cells.p + m->color_start[c];
-          B.n_cells = m->color_start[c + 1] - m->color_start[c];
-          if (!B.n_cells) continue;
-          TFELCU_DISPATCH_ND(DIM, nd_te, NTE,
-            TFELCU_DISPATCH_ND(DIM, nd_tr, NTR, launch_colored<DIM, NTE, NTR>(ctx, fb, B);))
+        for (int sg = 0; sg < m->rows.n; ++sg) {
+          if (m->rows.comp[sg] != a) continue;
+          B.row_begin = m->rows.g_begin[sg] - m->test.offset[a]; B.row_end = m->rows.g_end[sg] - m->test.offset[a];
+          B.local_off = m->rows.local_off[sg];
+          for (int c = 0; c < m->n_colors; ++c) {
+            B.color_cells = m->color_cells.p + m->color_start[c];
+            B.n_cells = m->color_start[c + 1] - m->color_start[c];
+            if (!B.n_cells) continue;
+            TFELCU_DISPATCH_ND(DIM, nd_te, NTE,
+              TFELCU_DISPATCH_ND(DIM, nd_tr, NTR, launch_colored<DIM, NTE, NTR>(ctx, fb, B);))
+          }
         }
       }
       if (!fb.keep.empty()) ctx->sync();   // device copies of host coefficient data die with fb
@@ -708,10 +726,14 @@ static void assemble_linear_dim(tfelcu_vector* v, int quad, const tfelcu_factor*
     fes_transpose(te);
     VecBlock B;
     B.vertices = te->mesh->vertices.p; B.cells = te->mesh->cells.p;
-    B.off_te = (uint32_t)v->space.offset[a]; B.n_rows_comp = te->n_dof;
     B.adj_ptr = te->adj_ptr.p; B.adj = te->adj.p; B.b = v->data.p;
     const int nd_te = te->nd;
-    TFELCU_DISPATCH_ND(DIM, nd_te, NTE, launch_vector<DIM, NTE>(ctx, fb, B);)
+    for (int sg = 0; sg < v->rows.n; ++sg) {
+      if (v->rows.comp[sg] != a) continue;
+      B.row_begin = v->rows.g_begin[sg] - v->space.offset[a]; B.row_end = v->rows.g_end[sg] - v->space.offset[a];
+      B.local_off = v->rows.local_off[sg];
+      TFELCU_DISPATCH_ND(DIM, nd_te, NTE, launch_vector<DIM, NTE>(ctx, fb, B);)
+    }
     if (!fb.keep.empty()) ctx->sync();
   }
 }

@@ -1,0 +1,248 @@
+// Row-block distribution of the Krylov solve over the GPUs of one box (one process per GPU, NCCL over NVLink).
+// A process owns contiguous ranges of the reference DOF numbering (one per component: horizontal strips of
+// gen_square_mesh, k-slabs of gen_cube_mesh) and the matching rows of the reference CSR with GLOBAL column indices
+// (what the owner-computes assembly produces). Set-up turns the columns into local indices [owned | halo], builds the
+// halo exchange plan with the neighbours and leaves three primitives to the Krylov methods:
+//   dist_halo_exchange   owned entries of a vector -> halo entries of the neighbours (pack kernel + grouped
+//                        ncclSend / ncclRecv)
+//   dist_reduce          per-CTA partial sums -> one value per sum on every process (fixed-order local sum +
+//                        ncclAllReduce), so that every rank takes the same branch of the stopping test
+//   dist_gather          owned entries -> full vector in reference numbering on every process
+// The reference has no distributed mode at all (sequential MATSEQAIJ, solver.hpp:139-143).
+#include "solver.cuh"
+#include "sortutil.cuh"
+
+#include <algorithm>
+#include <utility>
+
+namespace tfelcu {
+
+struct RangeTable {   // owned row segments of every rank, by value in kernel arguments (P <= 16)
+  int n_ranks;
+  int n_seg[16];
+  unsigned long long begin[16][kMaxSeg], end[16][kMaxSeg];
+};
+
+// key of every stored entry: (owner << 32 | global column) for columns another rank owns, all ones otherwise
+__global__ void k_halo_keys(const int32_t* __restrict__ colind, size_t nnz, RangeTable T, int me, uint64_t* __restrict__ keys) {
+  const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  const unsigned long long g = (unsigned long long)(uint32_t)colind[e];
+  int owner = -1;
+  for (int q = 0; q < T.n_ranks && owner < 0; ++q)
+    for (int sg = 0; sg < T.n_seg[q]; ++sg)
+      if (g >= T.begin[q][sg] && g < T.end[q][sg]) { owner = q; break; }
+  keys[e] = (owner == me || owner < 0) ? ~0ull : (((uint64_t)owner << 32) | g);
+}
+
+__global__ void k_localize_columns(const int32_t* __restrict__ colind, size_t nnz, RowMap R, const uint64_t* __restrict__ keys,
+                                   const uint64_t* __restrict__ halo, size_t n_halo, int32_t* __restrict__ out) {
+  const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  const uint64_t key = keys[e];
+  if (key == ~0ull) { out[e] = (int32_t)R.to_local((unsigned long long)(uint32_t)colind[e]); return; }
+  size_t lo = 0, hi = n_halo;
+  while (lo < hi) {
+    const size_t mid = lo + (hi - lo) / 2;
+    if (halo[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  out[e] = (int32_t)(R.local_off[R.n] + lo);
+}
+
+__global__ void k_lower_bounds_u64(const uint64_t* __restrict__ sorted, size_t n, int n_targets, unsigned long long* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n_targets) return;
+  const uint64_t target = (uint64_t)t << 32;
+  size_t lo = 0, hi = n;
+  while (lo < hi) {
+    const size_t mid = lo + (hi - lo) / 2;
+    if (sorted[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  out[t] = lo;
+}
+
+__global__ void k_requests_to_local(const uint64_t* __restrict__ req, size_t n, RowMap R, uint32_t* __restrict__ idx, int* __restrict__ bad) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long l = R.to_local(req[i] & 0xffffffffull);
+  if (l == ~0ull) { atomicExch(bad, 1); idx[i] = 0; }
+  else idx[i] = (uint32_t)l;
+}
+
+__global__ void k_pack(const double* __restrict__ v, const uint32_t* __restrict__ idx, size_t n, double* __restrict__ out,
+                       const KrylovScalars* __restrict__ S) {
+  if (S && S->done) return;
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v[idx[i]];
+}
+
+// block b: fixed-order sum of partial array b (one warp)
+struct ReduceArgs { const double* p[4]; int n[4]; };
+__global__ void k_reduce_many(ReduceArgs A, double* __restrict__ out) {
+  const double* p = A.p[blockIdx.x];
+  const int n = A.n[blockIdx.x];
+  double t = 0.0;
+  for (int i = threadIdx.x; i < n; i += 32) t += p[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (threadIdx.x == 0) out[blockIdx.x] = t;
+}
+
+void dist_setup(tfelcu_solver* s) {
+  Ctx* ctx = s->ctx;
+  DistPlan& D = *s->dist;
+  const int P = ctx->n_ranks, me = ctx->rank;
+  TFELCU_REQUIRE(ctx->comm != nullptr, "distributed solve needs a context created with tfelcu_ctx_create_distributed");
+  TFELCU_REQUIRE(P <= 16, "at most 16 ranks");
+  const RowMap& R = D.rows;
+  const size_t n_local = R.n_local();
+  // 1. everybody's row segments
+  constexpr int W = 2 * kMaxSeg + 1;
+  DevBuf<unsigned long long> mine(W), all((size_t)P * W);
+  unsigned long long h_mine[W];
+  for (int sg = 0; sg < kMaxSeg; ++sg) { h_mine[sg] = R.g_begin[sg]; h_mine[kMaxSeg + sg] = R.g_end[sg]; }
+  h_mine[2 * kMaxSeg] = (unsigned long long)R.n;
+  ctx->upload(mine.p, h_mine, W);
+  TFELCU_NCCL(ncclAllGather(mine.p, all.p, W, ncclUint64, ctx->comm, ctx->stream));
+  std::vector<unsigned long long> h_all((size_t)P * W);
+  ctx->download(h_all.data(), all.p, h_all.size());
+  RangeTable T;
+  T.n_ranks = P;
+  D.all_rows.assign(P, R);
+  std::vector<std::pair<unsigned long long, unsigned long long>> cover;
+  for (int q = 0; q < P; ++q) {
+    RowMap& Q = D.all_rows[q];
+    Q.n = (int)h_all[(size_t)q * W + 2 * kMaxSeg];
+    T.n_seg[q] = Q.n;
+    unsigned long long off = 0;
+    for (int sg = 0; sg < Q.n; ++sg) {
+      T.begin[q][sg] = Q.g_begin[sg] = h_all[(size_t)q * W + sg];
+      T.end[q][sg] = Q.g_end[sg] = h_all[(size_t)q * W + kMaxSeg + sg];
+      Q.local_off[sg] = off;
+      off += Q.g_end[sg] - Q.g_begin[sg];
+      if (Q.g_end[sg] > Q.g_begin[sg]) cover.push_back({Q.g_begin[sg], Q.g_end[sg]});
+    }
+    Q.local_off[Q.n] = off;
+  }
+  std::sort(cover.begin(), cover.end());
+  unsigned long long at = 0;
+  for (const auto& c : cover) {
+    TFELCU_REQUIRE(c.first == at, "the row segments of the ranks must tile [0, n_rows) without gaps or overlaps");
+    at = c.second;
+  }
+  TFELCU_REQUIRE(at == R.n_global, "the row segments of the ranks must cover every row");
+  // 2. halo columns, sorted by (owner, global column)
+  const size_t nnz = s->nnz;
+  DevBuf<uint64_t> keys(nnz), sorted(nnz), halo(nnz);
+  if (nnz) {
+    k_halo_keys<<<grid_for(nnz, 256), 256, 0, ctx->stream>>>(s->colind, nnz, T, me, keys.p);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+  }
+  sort_keys<uint64_t>(ctx, keys.p, sorted.p, nnz, 0, 64);
+  size_t n_halo = unique_keys<uint64_t>(ctx, sorted.p, halo.p, nnz);
+  if (n_halo) {
+    uint64_t last = 0; ctx->download(&last, halo.p + (n_halo - 1), 1);
+    if (last == ~0ull) --n_halo;
+  }
+  D.n_halo = n_halo;
+  TFELCU_REQUIRE(n_local + n_halo < 0x7fffffffull, "too many local columns");
+  D.colind_local.alloc(nnz);
+  if (nnz) {
+    k_localize_columns<<<grid_for(nnz, 256), 256, 0, ctx->stream>>>(s->colind, nnz, R, keys.p, halo.p, n_halo, D.colind_local.p);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+  }
+  DevBuf<unsigned long long> bounds((size_t)P + 1);
+  k_lower_bounds_u64<<<1, 32, 0, ctx->stream>>>(halo.p, n_halo, P, bounds.p);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  std::vector<unsigned long long> h_bounds((size_t)P + 1);
+  ctx->download(h_bounds.data(), bounds.p, (size_t)P + 1);
+  D.recv_off.assign(h_bounds.begin(), h_bounds.end());
+  // 3. what every rank receives from every rank
+  DevBuf<unsigned long long> cnt_mine(P), cnt_all((size_t)P * P);
+  std::vector<unsigned long long> h_cnt(P);
+  for (int q = 0; q < P; ++q) h_cnt[q] = D.recv_off[q + 1] - D.recv_off[q];
+  ctx->upload(cnt_mine.p, h_cnt.data(), (size_t)P);
+  TFELCU_NCCL(ncclAllGather(cnt_mine.p, cnt_all.p, (size_t)P, ncclUint64, ctx->comm, ctx->stream));
+  std::vector<unsigned long long> h_cnt_all((size_t)P * P);
+  ctx->download(h_cnt_all.data(), cnt_all.p, h_cnt_all.size());
+  D.send_off.assign((size_t)P + 1, 0);
+  for (int q = 0; q < P; ++q) D.send_off[q + 1] = D.send_off[q] + (size_t)h_cnt_all[(size_t)q * P + me];
+  const size_t n_send = D.send_off[P];
+  // 4. tell the owners which of their rows we need
+  DevBuf<uint64_t> req(n_send);
+  TFELCU_NCCL(ncclGroupStart());
+  for (int q = 0; q < P; ++q) {
+    if (q == me) continue;
+    const size_t rc = D.recv_off[q + 1] - D.recv_off[q], sc = D.send_off[q + 1] - D.send_off[q];
+    if (rc) TFELCU_NCCL(ncclSend(halo.p + D.recv_off[q], rc, ncclUint64, q, ctx->comm, ctx->stream));
+    if (sc) TFELCU_NCCL(ncclRecv(req.p + D.send_off[q], sc, ncclUint64, q, ctx->comm, ctx->stream));
+  }
+  TFELCU_NCCL(ncclGroupEnd());
+  D.send_idx.alloc(n_send);
+  D.send_buf.alloc(n_send);
+  if (n_send) {
+    DevBuf<int> bad(1);
+    ctx->zero(bad.p, 1);
+    k_requests_to_local<<<grid_for(n_send, 256), 256, 0, ctx->stream>>>(req.p, n_send, R, D.send_idx.p, bad.p);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+    int h_bad = 0; ctx->download(&h_bad, bad.p, 1);
+    TFELCU_REQUIRE(!h_bad, "halo plan: a neighbour asked for a row this rank does not own");
+  }
+  D.red.alloc(8);
+  ctx->sync();
+}
+
+// owned entries of v (length n_local + n_halo) -> halo entries of the neighbours' copies
+void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S) {
+  Ctx* ctx = s->ctx;
+  DistPlan& D = *s->dist;
+  const int P = ctx->n_ranks, me = ctx->rank;
+  const size_t n_send = D.send_off[P];
+  if (n_send) {
+    k_pack<<<grid_for(n_send, 256), 256, 0, ctx->stream>>>(v, D.send_idx.p, n_send, D.send_buf.p, S);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+  }
+  const size_t n_local = D.rows.n_local();
+  TFELCU_NCCL(ncclGroupStart());
+  for (int q = 0; q < P; ++q) {
+    if (q == me) continue;
+    const size_t rc = D.recv_off[q + 1] - D.recv_off[q], sc = D.send_off[q + 1] - D.send_off[q];
+    if (sc) TFELCU_NCCL(ncclSend(D.send_buf.p + D.send_off[q], sc, ncclDouble, q, ctx->comm, ctx->stream));
+    if (rc) TFELCU_NCCL(ncclRecv(v + n_local + D.recv_off[q], rc, ncclDouble, q, ctx->comm, ctx->stream));
+  }
+  TFELCU_NCCL(ncclGroupEnd());
+}
+
+// out_slot .. out_slot + k - 1 of the reduction buffer <- global sums of k partial arrays; returns the device address
+const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const int* n, int k, int out_slot) {
+  Ctx* ctx = s->ctx;
+  DistPlan& D = *s->dist;
+  ReduceArgs A;
+  for (int i = 0; i < 4; ++i) { A.p[i] = i < k ? partial[i] : nullptr; A.n[i] = i < k ? n[i] : 0; }
+  double* out = D.red.p + out_slot;
+  k_reduce_many<<<k, 32, 0, ctx->stream>>>(A, out);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  TFELCU_NCCL(ncclAllReduce(out, out, (size_t)k, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+  return out;
+}
+
+// x_global (device, n_rows of the global system) <- owned entries of every rank, reference numbering
+void dist_gather(tfelcu_solver* s, const double* x_local, double* x_global) {
+  Ctx* ctx = s->ctx;
+  DistPlan& D = *s->dist;
+  const int P = ctx->n_ranks;
+  TFELCU_NCCL(ncclGroupStart());
+  for (int q = 0; q < P; ++q) {
+    const RowMap& Q = D.all_rows[q];
+    for (int c = 0; c < Q.n; ++c) {
+      const size_t cnt = (size_t)(Q.g_end[c] - Q.g_begin[c]);
+      if (!cnt) continue;
+      double* dst = x_global + Q.g_begin[c];
+      const double* src = q == ctx->rank ? x_local + Q.local_off[c] : dst;
+      TFELCU_NCCL(ncclBroadcast(src, dst, cnt, ncclDouble, q, ctx->comm, ctx->stream));
+    }
+  }
+  TFELCU_NCCL(ncclGroupEnd());
+}
+
+}  // namespace tfelcu

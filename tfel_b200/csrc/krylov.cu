@@ -455,6 +455,7 @@ static void precond(tfelcu_solver* s, const double* d_in, double* d_out) {
 
 void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep) {
   Ctx* ctx = s->ctx;
+  TFELCU_REQUIRE(!s->dist, "GMRES on a row-distributed operator is not available yet (use CG, or one rank)");
   const size_t n = s->n;
   const int vg = vgrid(s);
   const uint64_t launches0 = ctx->launches;

@@ -31,25 +31,32 @@ void matrix_snapshot_dirichlet(tfelcu_matrix* m) {
   }
 }
 
-// keys (row << 32 | col) of one (test component, trial component) block
-__global__ void k_pattern_keys(const uint32_t* __restrict__ map_te, int nd_te, uint32_t off_te,
-                               const uint32_t* __restrict__ map_tr, int nd_tr, uint32_t off_tr, size_t K,
+// keys (local row << 32 | global col) of one (test component, trial component) block, generated from the OWNED rows:
+// entry a of the transposed test dof map is (cell k, local dof i) of row r = dof_map_te[code]; it touches the nd_tr
+// columns of cell k
+__global__ void k_pattern_keys(const uint32_t* __restrict__ adj, size_t a_begin, size_t n_adj,
+                               const uint32_t* __restrict__ map_te, int nd_te, uint32_t off_te,
+                               unsigned long long row_begin, unsigned long long local_off,
+                               const uint32_t* __restrict__ map_tr, int nd_tr, uint32_t off_tr,
                                const uint8_t* __restrict__ dir_row, uint64_t sentinel, uint64_t* __restrict__ keys) {
   const size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  const size_t per_cell = (size_t)nd_te * nd_tr;
-  if (p >= K * per_cell) return;
-  const size_t k = p / per_cell; const int ij = (int)(p % per_cell);
-  const int i = ij / nd_tr, j = ij % nd_tr;
-  const uint32_t row = off_te + map_te[k * nd_te + i];
+  if (p >= n_adj * (size_t)nd_tr) return;
+  const size_t a = a_begin + p / nd_tr; const int j = (int)(p % nd_tr);
+  const uint32_t code = adj[a];
+  const size_t k = code / nd_te;
+  const uint32_t r = map_te[code];
   const uint32_t col = off_tr + map_tr[k * nd_tr + j];
-  keys[p] = dir_row[row] ? sentinel : (((uint64_t)row << 32) | col);
+  const uint64_t lrow = local_off + (r - row_begin);
+  keys[p] = dir_row[off_te + r] ? sentinel : ((lrow << 32) | col);
 }
 
-__global__ void k_dirichlet_keys(const uint8_t* __restrict__ dir_row, size_t n_rows, uint64_t sentinel,
+// identity entry of every owned Dirichlet row
+__global__ void k_dirichlet_keys(const uint8_t* __restrict__ dir_row, RowMap R, uint64_t sentinel,
                                  uint64_t* __restrict__ keys) {
-  const size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (r >= n_rows) return;
-  keys[r] = dir_row[r] ? (((uint64_t)r << 32) | r) : sentinel;
+  const size_t lr = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (lr >= R.local_off[R.n]) return;
+  const unsigned long long g = R.to_global(lr);
+  keys[lr] = dir_row[g] ? (((uint64_t)lr << 32) | g) : sentinel;
 }
 
 __global__ void k_rowptr_from_keys(const uint64_t* __restrict__ keys, size_t nnz, size_t n_rows,
@@ -81,28 +88,44 @@ __global__ void k_max_block_nnz(const int32_t* __restrict__ rowptr, size_t n_row
 
 void matrix_build_pattern(tfelcu_matrix* m) {
   Ctx* ctx = m->ctx;
-  const size_t K = m->mesh->K;
-  size_t per_cell = 0;
-  for (int a = 0; a < m->test.n; ++a)
-    for (int b = 0; b < m->trial.n; ++b) per_cell += (size_t)m->test.fes[a]->nd * m->trial.fes[b]->nd;
-  const size_t n_keys = K * per_cell + m->n_rows;
+  const RowMap& R = m->rows;
+  const size_t n_local = R.n_local();
   TFELCU_REQUIRE(m->n_rows < 0xfffffffeull && m->n_cols < 0xfffffffeull, "matrix too large for 32-bit indices");
-  const uint64_t sentinel = (uint64_t)m->n_rows << 32;   // sorts after every real key
+  // owned slices of the transposed test dof maps, one per row segment
+  size_t a_begin[kMaxSeg], a_count[kMaxSeg];
+  for (int sg = 0; sg < R.n; ++sg) {
+    const int a = R.comp[sg];
+    tfelcu_fes* te = m->test.fes[a];
+    fes_transpose(te);
+    uint32_t lo = 0, hi = 0;
+    ctx->download(&lo, te->adj_ptr.p + (R.g_begin[sg] - m->test.offset[a]), 1);
+    ctx->download(&hi, te->adj_ptr.p + (R.g_end[sg] - m->test.offset[a]), 1);
+    a_begin[sg] = lo; a_count[sg] = hi - lo;
+  }
+  size_t n_keys = n_local;
+  for (int sg = 0; sg < R.n; ++sg)
+    for (int b = 0; b < m->trial.n; ++b) n_keys += a_count[sg] * (size_t)m->trial.fes[b]->nd;
+  const uint64_t sentinel = (uint64_t)n_local << 32;   // sorts after every real key
   DevBuf<uint64_t> keys(n_keys), sorted(n_keys);
   size_t at = 0;
-  for (int a = 0; a < m->test.n; ++a)
+  for (int sg = 0; sg < R.n; ++sg)
     for (int b = 0; b < m->trial.n; ++b) {
+      const int a = R.comp[sg];
       tfelcu_fes* te = m->test.fes[a]; tfelcu_fes* tr = m->trial.fes[b];
-      const size_t n = K * (size_t)te->nd * tr->nd;
-      k_pattern_keys<<<grid_for(n, 256), 256, 0, ctx->stream>>>(te->dof_map, te->nd, (uint32_t)m->test.offset[a],
-                                                              tr->dof_map, tr->nd, (uint32_t)m->trial.offset[b], K,
-                                                              m->dir_row.p, sentinel, keys.p + at);
+      const size_t n = a_count[sg] * (size_t)tr->nd;
+      if (!n) continue;
+      k_pattern_keys<<<grid_for(n, 256), 256, 0, ctx->stream>>>(te->adj.p, a_begin[sg], a_count[sg], te->dof_map, te->nd,
+                                                              (uint32_t)m->test.offset[a], R.g_begin[sg] - m->test.offset[a],
+                                                              R.local_off[sg], tr->dof_map, tr->nd,
+                                                              (uint32_t)m->trial.offset[b], m->dir_row.p, sentinel, keys.p + at);
       ctx->count(); TFELCU_LAUNCH_CHECK();
       at += n;
     }
-  k_dirichlet_keys<<<grid_for(m->n_rows, 256), 256, 0, ctx->stream>>>(m->dir_row.p, m->n_rows, sentinel, keys.p + at);
-  ctx->count(); TFELCU_LAUNCH_CHECK();
-  sort_keys<uint64_t>(ctx, keys.p, sorted.p, n_keys, 0, 32 + bits_for(m->n_rows + 1));
+  if (n_local) {
+    k_dirichlet_keys<<<grid_for(n_local, 256), 256, 0, ctx->stream>>>(m->dir_row.p, R, sentinel, keys.p + at);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+  }
+  sort_keys<uint64_t>(ctx, keys.p, sorted.p, n_keys, 0, 32 + bits_for(n_local + 1));
   size_t nnz = unique_keys<uint64_t>(ctx, sorted.p, keys.p, n_keys);
   if (nnz) {
     uint64_t last = 0; ctx->download(&last, keys.p + (nnz - 1), 1);
@@ -110,16 +133,20 @@ void matrix_build_pattern(tfelcu_matrix* m) {
   }
   TFELCU_REQUIRE(nnz < 0x7fffffffull, "more than 2^31 stored entries: int32 CSR indices (solver.cpp:71-74) overflow");
   m->nnz = nnz;
-  m->rowptr.alloc(m->n_rows + 1); m->colind.alloc(nnz); m->val.alloc(nnz);
-  k_rowptr_from_keys<<<grid_for(m->n_rows + 1, 256), 256, 0, ctx->stream>>>(keys.p, nnz, m->n_rows, m->rowptr.p);
+  m->rowptr.alloc(n_local + 1); m->colind.alloc(nnz); m->val.alloc(nnz);
+  k_rowptr_from_keys<<<grid_for(n_local + 1, 256), 256, 0, ctx->stream>>>(keys.p, nnz, n_local, m->rowptr.p);
   ctx->count(); TFELCU_LAUNCH_CHECK();
-  k_colind_from_keys<<<grid_for(nnz, 256), 256, 0, ctx->stream>>>(keys.p, nnz, m->colind.p);
-  ctx->count(); TFELCU_LAUNCH_CHECK();
+  if (nnz) {
+    k_colind_from_keys<<<grid_for(nnz, 256), 256, 0, ctx->stream>>>(keys.p, nnz, m->colind.p);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+  }
   DevBuf<unsigned long long> mx(1);
   ctx->zero(mx.p, 1);
-  const size_t n_blocks = (m->n_rows + kRowsPerCta - 1) / kRowsPerCta;
-  k_max_block_nnz<<<grid_for(n_blocks, 256), 256, 0, ctx->stream>>>(m->rowptr.p, m->n_rows, kRowsPerCta, mx.p);
-  ctx->count(); TFELCU_LAUNCH_CHECK();
+  const size_t n_blocks = (n_local + kRowsPerCta - 1) / kRowsPerCta;
+  if (n_blocks) {
+    k_max_block_nnz<<<grid_for(n_blocks, 256), 256, 0, ctx->stream>>>(m->rowptr.p, n_local, kRowsPerCta, mx.p);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+  }
   unsigned long long h = 0; ctx->download(&h, mx.p, 1);
   m->max_block_nnz = (size_t)h;
   m->has_colors = false;
@@ -128,18 +155,21 @@ void matrix_build_pattern(tfelcu_matrix* m) {
 
 // clear(): zero everything, identity on the Dirichlet rows (bilinear_form.hpp:159-165)
 __global__ void k_clear_values(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
-                               const uint8_t* __restrict__ dir_row, size_t n_rows, double* __restrict__ val) {
-  const size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (r >= n_rows) return;
-  const bool dir = dir_row[r];
-  for (int32_t e = rowptr[r]; e < rowptr[r + 1]; ++e) val[e] = (dir && colind[e] == (int32_t)r) ? 1.0 : 0.0;
+                               const uint8_t* __restrict__ dir_row, RowMap R, double* __restrict__ val) {
+  const size_t lr = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (lr >= R.local_off[R.n]) return;
+  const unsigned long long g = R.to_global(lr);
+  const bool dir = dir_row[g];
+  for (int32_t e = rowptr[lr]; e < rowptr[lr + 1]; ++e) val[e] = (dir && colind[e] == (int32_t)g) ? 1.0 : 0.0;
 }
 
 void matrix_ensure_cleared(tfelcu_matrix* m) {
   if (m->val_valid) return;
   Ctx* ctx = m->ctx;
-  k_clear_values<<<grid_for(m->n_rows, 256), 256, 0, ctx->stream>>>(m->rowptr.p, m->colind.p, m->dir_row.p, m->n_rows, m->val.p);
-  ctx->count(); TFELCU_LAUNCH_CHECK();
+  if (m->rows.n_local()) {
+    k_clear_values<<<grid_for(m->rows.n_local(), 256), 256, 0, ctx->stream>>>(m->rowptr.p, m->colind.p, m->dir_row.p, m->rows, m->val.p);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+  }
   m->val_valid = true;
 }
 

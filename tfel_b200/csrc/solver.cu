@@ -249,7 +249,7 @@ __global__ void k_block_jacobi_setup(const int32_t* __restrict__ rowptr, const i
     if (r >= n) { a[i][i] = 1.0; continue; }
     for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
       const long long c = (long long)colind[e] - (long long)r0;
-      if (c >= 0 && c < bs) a[i][c] = val[e];
+      if (c >= 0 && c < bs && (size_t)colind[e] < n) a[i][c] = val[e];   // halo columns (>= n) are not in a block
     }
   }
   for (int k = 0; k < bs; ++k) {
@@ -311,7 +311,15 @@ void solver_setup(tfelcu_solver* s) {
   TFELCU_CK(cudaEventCreate(&e0)); TFELCU_CK(cudaEventCreate(&e1));
   TFELCU_CK(cudaEventRecord(e0, ctx->stream));
   const size_t n = s->n;
-  s->x.alloc(n); s->b.alloc(n); s->r.alloc(n); s->p.alloc(n); s->q.alloc(n);
+  size_t n_halo = 0;
+  if (s->dist) {
+    TFELCU_REQUIRE(s->params.precond != TFELCU_PC_ILU0, "ILU(0) on a row-distributed operator is not available yet");
+    dist_setup(s);                       // needs the global column indices
+    s->colind = s->dist->colind_local.p;
+    n_halo = s->dist->n_halo;
+  }
+  s->x.alloc(n + n_halo); s->b.alloc(n); s->r.alloc(n); s->p.alloc(n + n_halo); s->q.alloc(n);
+  ctx->zero(s->x.p, n + n_halo); ctx->zero(s->p.p, n + n_halo);
   s->scal.alloc(1);
   ctx->zero(s->scal.p, 1);
   spmv_plan(s);
@@ -361,17 +369,34 @@ void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep) {
   uint64_t n_spmv = 0;
   const uint64_t launches0 = ctx->launches;
 
+  const bool dist = (bool)s->dist;
+  struct Sum { const double* p; int n; };
+  auto global_sums = [&](std::initializer_list<Sum> in, int slot, Sum* out) {
+    // single process: consumers add the per-CTA partials themselves; distributed: one value per sum after an allreduce
+    int k = 0;
+    const double* ptrs[4]; int ns[4];
+    for (const Sum& v : in) { ptrs[k] = v.p; ns[k] = v.n; out[k] = v; ++k; }
+    if (!dist) return;
+    const double* r = dist_reduce(s, ptrs, ns, k, slot);
+    for (int i = 0; i < k; ++i) out[i] = Sum{r + i, 1};
+  };
+
   ctx->zero(S, 1);
   k_initial_guess<<<grid_for(n, 256), 256, 0, ctx->stream>>>(s->rowptr, s->colind, s->val, s->b.p, n, s->x.p);
   ctx->count(); TFELCU_LAUNCH_CHECK();
+  if (dist) dist_halo_exchange(s, s->x.p, nullptr);
   spmv_launch(s, s->x.p, s->q.p, nullptr, nullptr); ++n_spmv;
   k_residual<<<vg, kVecThreads, 0, ctx->stream>>>(s->b.p, s->q.p, n, s->r.p, P_bb);
   ctx->count(); TFELCU_LAUNCH_CHECK();
   if (!fused) apply_precond(s, s->r.p, s->z.p);
   k_cg_start<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, dinv, fused ? nullptr : s->z.p, n, s->p.p, P_rz, P_rr);
   ctx->count(); TFELCU_LAUNCH_CHECK();
-  k_cg_set_scalars<<<1, 32, 0, ctx->stream>>>(P_bb, P_rz, P_rr, vg, s->params.rtol, s->params.atol, s->params.dtol, S);
-  ctx->count(); TFELCU_LAUNCH_CHECK();
+  {
+    Sum g[3];
+    global_sums({Sum{P_bb, vg}, Sum{P_rz, vg}, Sum{P_rr, vg}}, 4, g);
+    k_cg_set_scalars<<<1, 32, 0, ctx->stream>>>(g[0].p, g[1].p, g[2].p, g[0].n, s->params.rtol, s->params.atol, s->params.dtol, S);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+  }
 
   // optional SpMV sampling for the roofline report: events around every profile_every-th launch
   const int prof_every = s->params.profile_every;
@@ -393,20 +418,25 @@ void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep) {
     uint32_t chunk = (uint32_t)check;
     if (issued + chunk > maxits) chunk = maxits - issued;
     for (uint32_t it = 0; it < chunk; ++it) {
+      if (dist) dist_halo_exchange(s, s->p.p, S);
       const bool sampled = sample_begin(issued + it);
       const int n_pq = spmv_launch(s, s->p.p, s->q.p, P_pq, S); ++n_spmv;
       if (sampled) TFELCU_CK(cudaEventRecord(prof.back(), ctx->stream));
-      k_cg_update<<<vg, kVecThreads, 0, ctx->stream>>>(s->q.p, dinv, fused ? 1 : 0, n, P_pq, n_pq, s->r.p, P_rz, P_rr, S);
+      Sum pq[1];
+      global_sums({Sum{P_pq, n_pq}}, 0, pq);
+      k_cg_update<<<vg, kVecThreads, 0, ctx->stream>>>(s->q.p, dinv, fused ? 1 : 0, n, pq[0].p, pq[0].n, s->r.p, P_rz, P_rr, S);
       ctx->count(); TFELCU_LAUNCH_CHECK();
       if (!fused) {
         apply_precond(s, s->r.p, s->z.p);
         k_dot_partial<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, s->z.p, n, P_rz, S);
         ctx->count(); TFELCU_LAUNCH_CHECK();
       }
-      k_cg_direction<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, dinv, fused ? nullptr : s->z.p, n, P_rz, vg, s->p.p,
+      Sum g[2];
+      global_sums({Sum{P_rz, vg}, Sum{P_rr, vg}}, 1, g);
+      k_cg_direction<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, dinv, fused ? nullptr : s->z.p, n, g[0].p, g[0].n, s->p.p,
                                                          s->x.p, S);
       ctx->count(); TFELCU_LAUNCH_CHECK();
-      k_cg_commit<<<1, 32, 0, ctx->stream>>>(P_rr, vg, S);
+      k_cg_commit<<<1, 32, 0, ctx->stream>>>(g[1].p, g[1].n, S);
       ctx->count(); TFELCU_LAUNCH_CHECK();
     }
     issued += chunk;

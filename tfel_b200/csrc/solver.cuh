@@ -39,6 +39,18 @@ struct Ilu0 {
   std::vector<LevelRun> runs_l, runs_u;
 };
 
+// halo exchange plan of a row-block distributed operator (dist.cu)
+struct DistPlan {
+  RowMap rows;                           // rows of this rank
+  std::vector<RowMap> all_rows;          // rows of every rank
+  size_t n_halo = 0;                     // columns owned by other ranks, stored after the owned entries of a vector
+  DevBuf<int32_t> colind_local;          // column indices in [owned | halo] numbering
+  DevBuf<uint32_t> send_idx;             // owned entries to send, grouped by destination rank
+  DevBuf<double> send_buf;
+  std::vector<size_t> send_off, recv_off;   // [n_ranks + 1]
+  DevBuf<double> red;                    // reduction scalars (ncclAllReduce in place)
+};
+
 }  // namespace tfelcu
 
 struct tfelcu_solver {
@@ -60,6 +72,8 @@ struct tfelcu_solver {
   double t_setup_s = 0.0;
   int n_partial = 0;
   int gmres_m = 0;                         // restart length the allocated basis holds
+  std::unique_ptr<tfelcu::DistPlan> dist;  // set when the operator holds only the rows this rank owns
+  size_t n_global = 0;
 };
 
 namespace tfelcu {
@@ -77,5 +91,10 @@ void ilu0_setup(tfelcu_solver* s);
 void ilu0_apply(tfelcu_solver* s, const double* d_in, double* d_out);
 void block_jacobi_setup(tfelcu_solver* s);
 void block_jacobi_apply(tfelcu_solver* s, const double* d_in, double* d_out);
+// ---- dist.cu
+void dist_setup(tfelcu_solver* s);
+void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S);
+const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const int* n, int k, int out_slot);
+void dist_gather(tfelcu_solver* s, const double* x_local, double* x_global);
 
 }  // namespace tfelcu

@@ -69,11 +69,69 @@ struct SpaceList {
   size_t total() const { return offset[n]; }
 };
 
+// Rows a process owns: up to kMaxSeg contiguous segments [g_begin, g_end) of GLOBAL rows (block layout
+// [u0 | u1 | p]), ascending and disjoint, none straddling two components -- e.g. the vertex dofs and the edge dofs of one
+// horizontal strip for every P2 component. Local rows are the segments concatenated. A single process owns one segment
+// per component covering everything.
+constexpr int kMaxSeg = 8;
+
+struct RowMap {
+  int n = 0;
+  unsigned long long g_begin[kMaxSeg] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long g_end[kMaxSeg] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long local_off[kMaxSeg + 1] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // local row of the first row of a segment
+  int comp[kMaxSeg] = {0, 0, 0, 0, 0, 0, 0, 0};                              // component the segment lies in
+  unsigned long long n_global = 0;
+  size_t n_local() const { return (size_t)local_off[n]; }
+  bool whole() const { return local_off[n] == n_global; }
+  // global row of a local row
+  __host__ __device__ unsigned long long to_global(unsigned long long lr) const {
+    int sg = 0;
+    while (sg + 1 < n && lr >= local_off[sg + 1]) ++sg;
+    return g_begin[sg] + (lr - local_off[sg]);
+  }
+  // local row of a global row, or ~0 when another process owns it
+  __host__ __device__ unsigned long long to_local(unsigned long long g) const {
+    for (int sg = 0; sg < n; ++sg)
+      if (g >= g_begin[sg] && g < g_end[sg]) return local_off[sg] + (g - g_begin[sg]);
+    return ~0ull;
+  }
+};
+
+// seg_begin == nullptr: everything
+inline RowMap make_row_map(const SpaceList& L, int n_seg, const size_t* seg_begin, const size_t* seg_end) {
+  RowMap R;
+  R.n_global = L.offset[L.n];
+  if (!seg_begin) {
+    R.n = L.n;
+    for (int c = 0; c < L.n; ++c) {
+      R.g_begin[c] = L.offset[c]; R.g_end[c] = L.offset[c + 1]; R.local_off[c] = L.offset[c]; R.comp[c] = c;
+    }
+    R.local_off[L.n] = L.offset[L.n];
+    return R;
+  }
+  TFELCU_REQUIRE(n_seg >= 0 && n_seg <= kMaxSeg, "at most 8 row segments per process");
+  R.n = n_seg;
+  unsigned long long off = 0, prev_end = 0;
+  for (int sg = 0; sg < n_seg; ++sg) {
+    const unsigned long long b = seg_begin[sg], e = seg_end[sg];
+    TFELCU_REQUIRE(b <= e && e <= R.n_global && b >= prev_end, "row segments must be ascending, disjoint and in range");
+    int c = 0;
+    while (c + 1 < L.n && b >= L.offset[c + 1]) ++c;
+    TFELCU_REQUIRE(e <= L.offset[c + 1] || b == e, "a row segment must lie inside one component");
+    R.g_begin[sg] = b; R.g_end[sg] = e; R.local_off[sg] = off; R.comp[sg] = c;
+    off += e - b; prev_end = e;
+  }
+  R.local_off[n_seg] = off;
+  return R;
+}
+
 }  // namespace tfelcu
 
 struct tfelcu_vector {
   tfelcu::Ctx* ctx = nullptr;
   tfelcu::SpaceList space;
+  tfelcu::RowMap rows;                  // owned rows; data holds rows.n_local() entries
   tfelcu::DevBuf<double> data;
 };
 
@@ -81,7 +139,8 @@ struct tfelcu_matrix {
   tfelcu::Ctx* ctx = nullptr;
   tfelcu_mesh* mesh = nullptr;
   tfelcu::SpaceList test, trial;
-  size_t n_rows = 0, n_cols = 0, nnz = 0;
+  size_t n_rows = 0, n_cols = 0, nnz = 0;   // global sizes; nnz counts the stored entries of the OWNED rows
+  tfelcu::RowMap rows;                  // owned rows: rowptr has rows.n_local() + 1 entries, colind holds global columns
   tfelcu::DevBuf<uint8_t> dir_row;      // [n_rows]: snapshot of the test spaces' Dirichlet flags
   tfelcu::DevBuf<double> dir_value;     // [n_rows]
   uint64_t dir_version[tfelcu::kMaxComp] = {0, 0, 0, 0};
