@@ -131,7 +131,7 @@ def run_reference(args):
     value = cells * args.steps / total
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "Poisson P1 gen_square_mesh n=%d, qf5pT, f=1, CG+Jacobi rtol 1e-8 (bounded sample of the "
                                    "n=4096 workload)" % n, "n": n, "cells": cells},
             "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads if kind == "reference" else 1, "kind": kind,
@@ -155,6 +155,7 @@ def run_own(args):
     import torch
     import torch.distributed as dist
     from tfel_b200 import capi
+    from tfel_b200 import dist as tdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -173,20 +174,25 @@ def run_own(args):
         torch.cuda.synchronize()
 
     n = args.n
-    ctx = capi.Context(local_rank)
+    ctx = tdist.init_context(local_rank)     # distributed (NCCL) when world > 1
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
     peak, peak_src = measured_peaks()
 
     # ---- resident structure (one-time, reported separately) -------------------------------------
-    # weak scaling: every rank owns an n x n/1 square of its own (independent objects, SURVEY.md 8e fallback until the
-    # strip-partitioned solve lands): see DESIGN.md "Multi-GPU"
+    # N > 1: ONE n x n problem, rows of the reference numbering split into horizontal strips (strong scaling);
+    # mesh, DOF map and Dirichlet set are replicated (0.67 GB), every rank owns the CSR rows / vector entries of its strip
+    def make_forms(mesh_, space_):
+        if world == 1:
+            return capi.Matrix(space_, space_), capi.Vector(space_)
+        segs = tdist.strip_segments([space_.kind_offsets()], world, rank)
+        return capi.Matrix(space_, space_, rows=segs), capi.Vector(space_, rows=segs)
+
     t0 = time.perf_counter()
     mesh = capi.Mesh.square(ctx, 1.0, 1.0, n, n)
     space = capi.Space(mesh, "p1")
     space.add_dirichlet_boundary(0.0)
-    a = capi.Matrix(space, space)
-    b = capi.Vector(space)
+    a, b = make_forms(mesh, space)
     ctx.synchronize()
     t_structure = time.perf_counter() - t0
     cells = mesh.n_cells
@@ -237,13 +243,13 @@ def run_own(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    value = world * cells * args.steps / (ms_total * 1e-3)
+    value = cells * args.steps / (ms_total * 1e-3)
 
     # ---- roofline of the dominant kernel (SpMV inside CG), measured live over the timed region ----
-    nnz, N = a.nnz, a.n_rows
+    nnz, N = a.nnz, a.n_local                                          # this rank's rows
     spmv_bytes = 12.0 * nnz + 4.0 * (N + 1) + 16.0 * N
     spmv_avg_ms = float(np.mean(spmv_ms)) if spmv_ms and spmv_ms[0] > 0 else None
-    asm_bytes = 4.0 * 3 * cells + 8.0 * 2 * mesh.n_vertices + 8.0 * nnz + 8.0 * N   # A and b together (52 B/cell)
+    asm_bytes = (4.0 * 3 * cells + 8.0 * 2 * mesh.n_vertices) / world + 8.0 * nnz + 8.0 * N   # A and b together (52 B/cell)
     asm_avg_ms = float(np.mean(asm_ms))
     roofline = {"kernel": "k_spmv_stream<true> (CSR fp64 SpMV + fused p.Ap partials, inside CG)", "bound": "hbm",
                 "achieved": (spmv_bytes / (spmv_avg_ms * 1e-3) / 1e9) if spmv_avg_ms else None, "peak": peak,
@@ -251,7 +257,7 @@ def run_own(args):
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
                 "avg_launch_ms": spmv_avg_ms, "samples_per_solve": int(args.maxits // max(args.profile_every, 1)),
                 "frac_of_nominal_8TBs": (spmv_bytes / (spmv_avg_ms * 1e-3) / 1e9 / 8000.0) if spmv_avg_ms else None}
-    assembly = {"cells_per_s": world * cells / (asm_avg_ms * 1e-3), "ms": asm_avg_ms,
+    assembly = {"cells_per_s": cells / (asm_avg_ms * 1e-3), "ms": asm_avg_ms,
                 "algorithmic_bytes": asm_bytes, "achieved_gbs": asm_bytes / (asm_avg_ms * 1e-3) / 1e9,
                 "frac_of_peak": asm_bytes / (asm_avg_ms * 1e-3) / 1e9 / peak,
                 "kernels": "k_assemble_rows<2,3,3,const,staged> + k_assemble_vector_rows<2,3,const>"}
@@ -278,8 +284,7 @@ def run_own(args):
             m2 = capi.Mesh.create(ctx, verts.numpy(), cells_h.numpy().view(np.uint32))
             s2 = capi.Space(m2, "p1")
             s2.add_dirichlet_boundary(0.0)
-            a2 = capi.Matrix(s2, s2)
-            b2 = capi.Vector(s2)
+            a2, b2 = make_forms(m2, s2)
             a2.assemble("qf5pT", STIFFNESS)
             b2.assemble("qf5pT", SOURCE)
             sv = capi.Solver(ctx, method="cg", precond="jacobi", maxits=args.maxits, rtol=1e-8, check_every=args.check_every)
@@ -301,7 +306,7 @@ def run_own(args):
         te = torch.tensor([max(wall, s_ev.elapsed_time(e_ev) * 1e-3)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * cells * args.e2e_steps / float(te.item()), "unit": "cells/s",
+        e2e = {"value": cells * args.e2e_steps / float(te.item()), "unit": "cells/s",
                "h2d_bytes_per_step": int(verts.numel() * 8 + cells_h.numel() * 4), "d2h_bytes_per_step": int(x_host.numel() * 8),
                "s_per_step": float(te.item()) / args.e2e_steps, "steps": args.e2e_steps,
                "includes": "mesh upload, DOF numbering, boundary + Dirichlet set, CSR pattern, assembly of A and b, CG solve, "
@@ -309,12 +314,14 @@ def run_own(args):
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "configs[1]: 2D Poisson P1 on %dx%d square mesh, qf5pT, f=1, CG + Jacobi to rtol 1e-8"
-                                       % (n, n), "n": n, "cells_per_gpu": cells, "dofs_per_gpu": N, "nnz_per_gpu": nnz,
+                                       % (n, n), "n": n, "cells": cells, "dofs": a.n_rows, "rows_rank0": N, "nnz_rank0": nnz,
                            "l2": "inputs larger than L2 (CSR 1.5 GB, mesh 0.67 GB per pass vs 126 MB)",
-                           "parallelism": "1 mesh per GPU" if world > 1 else "single GPU",
+                           "parallelism": ("%d horizontal strips of rows (reference numbering), NCCL halo exchange + allreduce" % world)
+                           if world > 1 else "single GPU",
                            "structure_build_s": t_structure},
                 "assembly": assembly, "solve": solve, "roofline": roofline, "clocks": clocks,
                 "e2e": e2e, "gpu_launches": int(launches)}

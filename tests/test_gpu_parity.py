@@ -327,3 +327,26 @@ def test_owned_row_segments_equal_rows_of_the_full_form(ctx, problem):
             A.close(); b.close()
     finally:
         cuda_runner.close(B)
+
+
+@pytest.mark.parametrize("name,problem", [("poisson_p1_n1024", problems.poisson("p1", 1024)),
+                                          ("poisson_p1_n2048", problems.poisson("p1", 2048)),
+                                          ("poisson_p1_n4096", problems.poisson("p1", 4096)),
+                                          ("stokes_n256", problems.stokes(256)),
+                                          ("tet_p1_n48", problems.tet("p1", 48))], ids=lambda v: v if isinstance(v, str) else "")
+def test_full_size_fingerprints_match_the_reference(ctx, name, problem, golden_dir):
+    """BASELINE.json sizes (configs[1] at n = 4096 included): DOF map, g2l, Dirichlet set, CSR rowptr / colind hash to
+    the values the UNMODIFIED reference printed (tests/golden/refhash_*.json, oracle/gen_refhash.py); matrix, linear
+    form and right-hand side agree in sum, sum of squares and sum of absolute values to 1e-11."""
+    import json
+    import refhash
+    ref = json.load(open(os.path.join(golden_dir, "refhash_%s.json" % name)))
+    got = cuda_runner.run(ctx, problem)
+    try:
+        assert got["csr_colind"].shape[0] == ref["nnz"]
+        if not problem.composite and problem.dim == 2:   # the hypotenuse couplings the reference stores as exact zeros
+            assert int((np.abs(got["csr_val"]) < 1e-13).sum()) == ref["n_exact_zero"]
+        n = refhash.check(got, ref, None)
+        assert n >= 8, n
+    finally:
+        cuda_runner.close(got["_built"])
