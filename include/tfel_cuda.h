@@ -215,6 +215,12 @@ double* tfelcu_vector_device_ptr(tfelcu_vector* v);
 int tfelcu_integrate(tfelcu_ctx* ctx, tfelcu_mesh* mesh, int quad, const tfelcu_factor* factors,
                      int n_factors, const tfelcu_term* terms, int n_terms, double* result);
 
+/* number of points / dimension of a quadrature formula, and the points of every cell in space coordinates
+ * xq[K][nq][dim] (cell.hpp:456-468; host or device buffer): what free_function leaves (expression.hpp:31-87) are
+ * evaluated at when a host callback has to be tabulated for TFELCU_FACTOR_TABLE */
+int tfelcu_quadrature_size(int quad, int* n_points, int* dim);
+int tfelcu_mesh_quadrature_points(tfelcu_mesh* mesh, int quad, double* xq);
+
 /* ---- solver plugin: solver::basic_solver, src/core/solver.hpp:29-40 ---------------------------- */
 
 int tfelcu_solver_create(tfelcu_ctx* ctx, const tfelcu_solver_params* params, tfelcu_solver** s);

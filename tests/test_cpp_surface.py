@@ -1,0 +1,74 @@
+"""The C++14 face (include/tfel/tfel.hpp): the reference's own programs compile against it unchanged except for the
+solver plugin (CPU: compile + link only; GPU: run and compare with the oracle)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "examples", "bin")
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tfel_b200", "csrc")])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "examples")])
+
+
+def test_reference_programs_compile_against_the_cuda_headers():
+    build()
+    for name in ("poisson", "stokes_2d_p2_p1", "plugin_and_forms"):
+        assert os.path.exists(os.path.join(BIN, name))
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    build()
+    r = subprocess.run([os.path.join(BIN, "poisson"), "4"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_readme_poisson_program(tmp_path):
+    import oracle as orc
+    import oracle_runner
+    import problems
+    build()
+    out = str(tmp_path / "u.bin")
+    r = subprocess.run([os.path.join(BIN, "poisson"), "10", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "dofs 121 dirichlet 40" in r.stdout     # README case
+    ref = oracle_runner.run(problems.poisson("p1", 10))
+    x_ref, _, _ = orc.cg_jacobi(ref["csr_rowptr"], ref["csr_colind"], ref["csr_val"], ref["rhs"], rtol=1e-13)
+    x = np.fromfile(out)
+    assert np.linalg.norm(x - x_ref) <= 1e-8 * np.linalg.norm(x_ref)
+    r = subprocess.run([os.path.join(BIN, "poisson"), "256"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert abs(float(r.stdout.split("max_u")[1]) - 0.0736713) < 2e-5
+
+
+@pytest.mark.gpu
+def test_reference_stokes_program(tmp_path):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    import oracle_runner
+    import problems
+    build()
+    out = str(tmp_path / "x.bin")
+    r = subprocess.run([os.path.join(BIN, "stokes_2d_p2_p1"), "10", out, "1e-12"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "converged 1" in r.stdout
+    ref = oracle_runner.run(problems.stokes(10))
+    x_ref = spl.spsolve(sp.csr_matrix((ref["csr_val"], ref["csr_colind"], ref["csr_rowptr"])).tocsc(), ref["rhs"])
+    x = np.fromfile(out)
+    assert np.linalg.norm(x - x_ref) <= 1e-8 * np.linalg.norm(x_ref)
+
+
+@pytest.mark.gpu
+def test_user_plugin_fields_and_integrals():
+    build()
+    r = subprocess.run([os.path.join(BIN, "plugin_and_forms")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "plugin_and_forms: ok" in r.stdout

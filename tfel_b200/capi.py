@@ -77,7 +77,7 @@ SYMBOLS = [
     "tfelcu_matrix_color_count",
     "tfelcu_vector_create", "tfelcu_vector_create_rows", "tfelcu_vector_destroy", "tfelcu_vector_clear", "tfelcu_vector_size",
     "tfelcu_vector_assemble", "tfelcu_vector_download", "tfelcu_vector_upload", "tfelcu_vector_device_ptr",
-    "tfelcu_integrate",
+    "tfelcu_integrate", "tfelcu_quadrature_size", "tfelcu_mesh_quadrature_points",
     "tfelcu_solver_create", "tfelcu_solver_destroy", "tfelcu_solver_set_operator",
     "tfelcu_solver_set_operator_csr", "tfelcu_solver_solve", "tfelcu_matrix_solve", "tfelcu_matrix_make_rhs",
     "tfelcu_solver_gather", "tfelcu_solver_spmv", "tfelcu_solver_spmv_bench",
@@ -208,6 +208,13 @@ class Mesh:
         vol = np.zeros(self.n_cells); jmt = np.zeros((self.n_cells, self.dim, self.dim))
         _ck(lib().tfelcu_mesh_geometry(self.h, _ptr(vol), _ptr(jmt)))
         return vol, jmt
+
+    def quadrature_points(self, quad):
+        nq = C.c_int(); dim = C.c_int()
+        _ck(lib().tfelcu_quadrature_size(QUAD[quad], C.byref(nq), C.byref(dim)))
+        xq = np.zeros((self.n_cells, nq.value, self.dim))
+        _ck(lib().tfelcu_mesh_quadrature_points(self.h, QUAD[quad], _ptr(xq)))
+        return xq
 
     def boundary(self):
         F = C.c_size_t()

@@ -578,6 +578,26 @@ int tfelcu_integrate(tfelcu_ctx* ctx, tfelcu_mesh* mesh, int quad, const tfelcu_
   });
 }
 
+int tfelcu_quadrature_size(int quad, int* n_points, int* dim) {
+  return guarded([&] {
+    TFELCU_REQUIRE(n_points != nullptr, "null pointer");
+    *n_points = tfelcu::quadrature_size(quad, dim);
+  });
+}
+
+int tfelcu_mesh_quadrature_points(tfelcu_mesh* mesh, int quad, double* xq) {
+  return guarded([&] {
+    TFELCU_REQUIRE(mesh && xq, "null pointer");
+    use_device(mesh->ctx);
+    Ctx* ctx = mesh->ctx;
+    const size_t n = mesh->K * (size_t)tfelcu::quadrature_size(quad, nullptr) * mesh->dim;
+    if (tfelcu::is_device_pointer(xq)) { tfelcu::quadrature_points(ctx, mesh, quad, xq); return; }
+    DevBuf<double> d(n);
+    tfelcu::quadrature_points(ctx, mesh, quad, d.p);
+    copy_out(ctx, xq, d.p, n);
+  });
+}
+
 // ---- solver --------------------------------------------------------------------------------------
 
 int tfelcu_solver_create(tfelcu_ctx* ctx, const tfelcu_solver_params* params, tfelcu_solver** s) {

@@ -746,6 +746,41 @@ void assemble_linear(tfelcu_vector* v, int quad, const tfelcu_factor* factors, i
   else assemble_linear_dim<3>(v, quad, factors, n_factors, terms, n_terms);
 }
 
+// quadrature points in space coordinates [K][nq][dim] (cell.hpp:456-468: x = v0 + sum_m xhat_m (v_{m+1} - v0))
+template <int DIM>
+__global__ void k_quadrature_points(const double* __restrict__ vertices, const uint32_t* __restrict__ cells, size_t K,
+                                    const double* __restrict__ xhat, int nq, double* __restrict__ xq) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= K * (size_t)nq) return;
+  const size_t k = t / nq; const int q = (int)(t % nq);
+  const uint32_t* cell = cells + k * (DIM + 1);
+  for (int c = 0; c < DIM; ++c) {
+    const double v0 = vertices[(size_t)cell[0] * DIM + c];
+    double acc = v0;
+    for (int m = 0; m < DIM; ++m)
+      acc = __dadd_rn(acc, __dmul_rn(xhat[q * DIM + m], __dsub_rn(vertices[(size_t)cell[m + 1] * DIM + c], v0)));
+    xq[t * DIM + c] = acc;
+  }
+}
+
+int quadrature_size(int quad, int* dim) {
+  const Quadrature Q = make_quadrature(quad);
+  if (dim) *dim = Q.dim;
+  return Q.nq;
+}
+
+void quadrature_points(Ctx* ctx, tfelcu_mesh* mesh, int quad, double* d_xq) {
+  const Quadrature Q = make_quadrature(quad);
+  TFELCU_REQUIRE(Q.dim == mesh->dim, "quadrature formula and mesh have different dimensions");
+  DevBuf<double> xhat(Q.x.size());
+  ctx->upload(xhat.p, Q.x.data(), Q.x.size());
+  const size_t n = mesh->K * (size_t)Q.nq;
+  if (mesh->dim == 2) k_quadrature_points<2><<<grid_for(n, 256), 256, 0, ctx->stream>>>(mesh->vertices.p, mesh->cells.p, mesh->K, xhat.p, Q.nq, d_xq);
+  else k_quadrature_points<3><<<grid_for(n, 256), 256, 0, ctx->stream>>>(mesh->vertices.p, mesh->cells.p, mesh->K, xhat.p, Q.nq, d_xq);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  ctx->sync();
+}
+
 double integrate_scalar(Ctx* ctx, tfelcu_mesh* mesh, int quad, const tfelcu_factor* factors, int n_factors,
                         const tfelcu_term* terms, int n_terms) {
   FormBuild fb;

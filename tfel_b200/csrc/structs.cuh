@@ -193,5 +193,7 @@ void assemble_linear(tfelcu_vector* v, int quad, const tfelcu_factor* factors, i
                      const tfelcu_term* terms, int n_terms);
 double integrate_scalar(Ctx* ctx, tfelcu_mesh* mesh, int quad, const tfelcu_factor* factors, int n_factors,
                         const tfelcu_term* terms, int n_terms);
+int quadrature_size(int quad, int* dim);
+void quadrature_points(Ctx* ctx, tfelcu_mesh* mesh, int quad, double* d_xq);
 
 }  // namespace tfelcu
