@@ -320,7 +320,8 @@ def run_own(args):
                 "config": {"workload": "configs[1]: 2D Poisson P1 on %dx%d square mesh, qf5pT, f=1, CG + Jacobi to rtol 1e-8"
                                        % (n, n), "n": n, "cells": cells, "dofs": a.n_rows, "rows_rank0": N, "nnz_rank0": nnz,
                            "l2": "inputs larger than L2 (CSR 1.5 GB, mesh 0.67 GB per pass vs 126 MB)",
-                           "parallelism": ("%d horizontal strips of rows (reference numbering), NCCL halo exchange + allreduce" % world)
+                           "parallelism": ("%d horizontal strips of rows (reference numbering); halo exchange + reductions over %s"
+                                           % (world, "peer-mapped memory (CUDA IPC, NVLink)" if ctx.p2p else "NCCL send/recv + allreduce"))
                            if world > 1 else "single GPU",
                            "structure_build_s": t_structure},
                 "assembly": assembly, "solve": solve, "roofline": roofline, "clocks": clocks,

@@ -124,6 +124,7 @@ int tfelcu_ctx_create_distributed(int device, int rank, int n_ranks, const void*
     ncclUniqueId id;
     std::memcpy(&id, nccl_unique_id128, sizeof(id));
     TFELCU_NCCL(ncclCommInitRank(&c->comm, n_ranks, id, rank));
+    tfelcu::p2p_setup(c.get());   // peer arenas over CUDA IPC; stays on NCCL when IPC is not available
     *ctx = c.release();
   });
 }
@@ -133,6 +134,7 @@ int tfelcu_ctx_destroy(tfelcu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    tfelcu::p2p_teardown(ctx);
     if (ctx->comm) ncclCommDestroy(ctx->comm);
     ctx->table_scratch.release();
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -165,6 +167,8 @@ int tfelcu_ctx_rank(const tfelcu_ctx* ctx, int* rank, int* n_ranks) {
 }
 
 uint64_t tfelcu_ctx_launch_count(const tfelcu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int tfelcu_ctx_p2p_enabled(const tfelcu_ctx* ctx) { return ctx && ctx->p2p ? 1 : 0; }
 
 // ---- mesh --------------------------------------------------------------------------------------
 

@@ -84,6 +84,12 @@ struct Ctx {
   ncclComm_t comm = nullptr;
   int sm_count = 148;
   uint64_t launches = 0;
+  // peer-to-peer arena (dist.cu): a small device buffer of every rank mapped into every other rank through CUDA IPC;
+  // reductions and halo exchanges of the distributed Krylov loop are remote stores + flags over NVLink
+  bool p2p = false;
+  void* arena = nullptr;
+  void* peer_arena[16] = {nullptr};
+  unsigned long long red_seq = 0, halo_seq = 0;
   DevBuf<double> table_scratch;   // reference-element tables of the form being assembled (stream ordered reuse)
 
   void count(uint64_t n = 1) { launches += n; }

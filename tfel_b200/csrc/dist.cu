@@ -13,6 +13,7 @@
 #include "sortutil.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <utility>
 
 namespace tfelcu {
@@ -86,6 +87,162 @@ __global__ void k_reduce_many(ReduceArgs A, double* __restrict__ out) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
   if (threadIdx.x == 0) out[blockIdx.x] = t;
+}
+
+// ------------------------------------------------------------------------------------------
+// peer-to-peer arena: remote stores + sequence flags over NVLink (one process per GPU, CUDA IPC)
+// ------------------------------------------------------------------------------------------
+
+constexpr size_t kArenaHaloCap = (size_t)1 << 20;   // doubles per parity
+constexpr long long kSpinLimit = 20000000000ll;     // clock64 ticks (~10 s): a lost peer must not hang the GPU
+
+struct Arena {
+  unsigned long long red_flag[2][16];   // [parity][source rank]: sequence number of the last complete contribution
+  double red_val[2][16][4];
+  unsigned long long halo_flag[16];     // [source rank]
+  unsigned long long pad[16];
+  double halo[2][kArenaHaloCap];        // landing zone of halo values, [parity]
+};
+
+struct Peers { Arena* a[16]; };
+
+__device__ __forceinline__ bool spin_until(const volatile unsigned long long* flag, unsigned long long seq) {
+  const long long t0 = clock64();
+  while (*flag < seq) {
+    if (clock64() - t0 > kSpinLimit) return false;
+    __nanosleep(40);
+  }
+  return true;
+}
+
+// warp w: fixed-order local sum of partial array w, contribution written into every rank's arena, flag, wait for
+// everybody's contribution, sum in rank order (every rank adds the same numbers in the same order)
+__global__ void k_p2p_allreduce(ReduceArgs A, int k, Peers peers, int me, int P, unsigned long long seq,
+                                double* __restrict__ out, KrylovScalars* __restrict__ S) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int par = (int)(seq & 1ull);
+  {
+    const double* p = A.p[w];
+    const int n = A.n[w];
+    double t = 0.0;
+    for (int i = lane; i < n; i += 32) t += p[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane < P) {
+      *reinterpret_cast<volatile double*>(&peers.a[lane]->red_val[par][me][w]) = t;
+      __threadfence_system();
+    }
+  }
+  __syncthreads();
+  if (w == 0 && lane < P) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&peers.a[lane]->red_flag[par][me]) = seq;
+  }
+  Arena* mine = peers.a[me];
+  double v = 0.0;
+  bool ok = true;
+  if (lane < P) {
+    ok = spin_until(&mine->red_flag[par][lane], seq);
+    __threadfence_system();
+    v = *reinterpret_cast<volatile double*>(&mine->red_val[par][lane][w]);
+  }
+  double t = 0.0;
+  for (int q = 0; q < P; ++q) t += __shfl_sync(0xffffffffu, v, q);
+  if (lane == 0) out[w] = t;
+  if (!__all_sync(0xffffffffu, ok) && lane == 0 && S) S->done = -3;
+}
+
+struct HaloArgs {
+  unsigned long long send_off[17], recv_off[17], land_off[16];
+};
+
+// CTA q: my boundary values -> landing zone of rank q (+ flag); values of rank q -> halo entries of v
+__global__ void __launch_bounds__(256)
+k_p2p_halo(double* __restrict__ v, size_t n_local, const uint32_t* __restrict__ send_idx, HaloArgs H, Peers peers,
+           int me, unsigned long long seq, KrylovScalars* __restrict__ S) {
+  if (S && S->done) return;
+  const int q = blockIdx.x;
+  if (q == me) return;
+  const int par = (int)(seq & 1ull);
+  const size_t sc = H.send_off[q + 1] - H.send_off[q], rc = H.recv_off[q + 1] - H.recv_off[q];
+  if (sc) {
+    double* dst = peers.a[q]->halo[par] + H.land_off[q];
+    const uint32_t* idx = send_idx + H.send_off[q];
+    for (size_t i = threadIdx.x; i < sc; i += blockDim.x) dst[i] = v[idx[i]];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long*>(&peers.a[q]->halo_flag[me]) = seq;
+    }
+  }
+  if (rc) {
+    __shared__ int ok_s;
+    Arena* mine = peers.a[me];
+    if (threadIdx.x == 0) ok_s = spin_until(&mine->halo_flag[q], seq) ? 1 : 0;
+    __syncthreads();
+    __threadfence_system();
+    if (!ok_s) { if (threadIdx.x == 0 && S) S->done = -3; return; }
+    const volatile double* src = mine->halo[par] + H.recv_off[q];
+    double* dst = v + n_local + H.recv_off[q];
+    for (size_t i = threadIdx.x; i < rc; i += blockDim.x) dst[i] = src[i];
+  }
+}
+
+void p2p_teardown(Ctx* ctx) {
+  for (int q = 0; q < 16; ++q)
+    if (ctx->peer_arena[q] && q != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_arena[q]);
+  if (ctx->arena) cudaFree(ctx->arena);
+  ctx->arena = nullptr; ctx->p2p = false;
+  for (int q = 0; q < 16; ++q) ctx->peer_arena[q] = nullptr;
+  cudaGetLastError();
+}
+
+void p2p_setup(Ctx* ctx) {
+  const int P = ctx->n_ranks, me = ctx->rank;
+  if (P < 2 || P > 16 || std::getenv("TFELCU_NO_P2P")) return;
+  int ok = 1;
+  cudaIpcMemHandle_t mine_h;
+  std::memset(&mine_h, 0, sizeof(mine_h));
+  if (cudaMalloc(&ctx->arena, sizeof(Arena)) != cudaSuccess) { ok = 0; ctx->arena = nullptr; cudaGetLastError(); }
+  if (ok) {
+    TFELCU_CK(cudaMemsetAsync(ctx->arena, 0, sizeof(Arena), ctx->stream));
+    ctx->sync();
+    if (cudaIpcGetMemHandle(&mine_h, ctx->arena) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  DevBuf<char> d_mine(64), d_all((size_t)P * 64);
+  ctx->upload(d_mine.p, reinterpret_cast<const char*>(&mine_h), 64);
+  TFELCU_NCCL(ncclAllGather(d_mine.p, d_all.p, 64, ncclChar, ctx->comm, ctx->stream));
+  std::vector<char> h_all((size_t)P * 64);
+  ctx->download(h_all.data(), d_all.p, h_all.size());
+  auto agree = [&](int flag) {   // 1 only when every rank says 1
+    DevBuf<int> f(1);
+    ctx->upload(f.p, &flag, 1);
+    TFELCU_NCCL(ncclAllReduce(f.p, f.p, 1, ncclInt, ncclMin, ctx->comm, ctx->stream));
+    int out = 0; ctx->download(&out, f.p, 1);
+    return out;
+  };
+  ok = agree(ok);
+  if (ok) {
+    for (int q = 0; q < P; ++q) {
+      if (q == me) { ctx->peer_arena[q] = ctx->arena; continue; }
+      cudaIpcMemHandle_t hq;
+      std::memcpy(&hq, &h_all[(size_t)q * 64], 64);
+      if (cudaIpcOpenMemHandle(&ctx->peer_arena[q], hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        ok = 0; ctx->peer_arena[q] = nullptr; cudaGetLastError();
+      }
+    }
+    ok = agree(ok);
+  }
+  if (!ok) { p2p_teardown(ctx); return; }
+  ctx->p2p = true;
+}
+
+static Peers peers_of(Ctx* ctx) {
+  Peers p;
+  for (int q = 0; q < 16; ++q) p.a[q] = static_cast<Arena*>(ctx->peer_arena[q]);
+  return p;
 }
 
 void dist_setup(tfelcu_solver* s) {
@@ -167,6 +324,18 @@ void dist_setup(tfelcu_solver* s) {
   ctx->download(h_cnt_all.data(), cnt_all.p, h_cnt_all.size());
   D.send_off.assign((size_t)P + 1, 0);
   for (int q = 0; q < P; ++q) D.send_off[q + 1] = D.send_off[q] + (size_t)h_cnt_all[(size_t)q * P + me];
+  // where my values land at rank q (its receive offset for me) and whether every rank's halo fits the arena
+  D.land_off.assign((size_t)P, 0);
+  D.p2p_halo = ctx->p2p;
+  for (int q = 0; q < P; ++q) {
+    size_t off = 0, total = 0;
+    for (int r = 0; r < P; ++r) {
+      if (r == me) off = total;
+      total += (size_t)h_cnt_all[(size_t)q * P + r];
+    }
+    D.land_off[q] = off;
+    if (total > kArenaHaloCap) D.p2p_halo = false;
+  }
   const size_t n_send = D.send_off[P];
   // 4. tell the owners which of their rows we need
   DevBuf<uint64_t> req(n_send);
@@ -198,6 +367,15 @@ void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S) {
   DistPlan& D = *s->dist;
   const int P = ctx->n_ranks, me = ctx->rank;
   const size_t n_send = D.send_off[P];
+  if (D.p2p_halo) {
+    HaloArgs H;
+    for (int q = 0; q <= P; ++q) { H.send_off[q] = D.send_off[q]; H.recv_off[q] = D.recv_off[q]; }
+    for (int q = 0; q < P; ++q) H.land_off[q] = D.land_off[q];
+    k_p2p_halo<<<P, 256, 0, ctx->stream>>>(v, D.rows.n_local(), D.send_idx.p, H, peers_of(ctx), me, ++ctx->halo_seq,
+                                          const_cast<KrylovScalars*>(S));
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+    return;
+  }
   if (n_send) {
     k_pack<<<grid_for(n_send, 256), 256, 0, ctx->stream>>>(v, D.send_idx.p, n_send, D.send_buf.p, S);
     ctx->count(); TFELCU_LAUNCH_CHECK();
@@ -220,6 +398,12 @@ const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const 
   ReduceArgs A;
   for (int i = 0; i < 4; ++i) { A.p[i] = i < k ? partial[i] : nullptr; A.n[i] = i < k ? n[i] : 0; }
   double* out = D.red.p + out_slot;
+  if (ctx->p2p) {
+    k_p2p_allreduce<<<1, 32 * k, 0, ctx->stream>>>(A, k, peers_of(ctx), ctx->rank, ctx->n_ranks, ++ctx->red_seq, out,
+                                                  s->scal.p);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+    return out;
+  }
   k_reduce_many<<<k, 32, 0, ctx->stream>>>(A, out);
   ctx->count(); TFELCU_LAUNCH_CHECK();
   TFELCU_NCCL(ncclAllReduce(out, out, (size_t)k, ncclDouble, ncclSum, ctx->comm, ctx->stream));

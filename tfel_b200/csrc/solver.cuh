@@ -49,6 +49,8 @@ struct DistPlan {
   DevBuf<double> send_buf;
   std::vector<size_t> send_off, recv_off;   // [n_ranks + 1]
   DevBuf<double> red;                    // reduction scalars (ncclAllReduce in place)
+  bool p2p_halo = false;                 // halo values travel through the peer arenas
+  std::vector<size_t> land_off;          // [n_ranks]: where this rank's values land in the arena of rank q
 };
 
 }  // namespace tfelcu
@@ -96,5 +98,7 @@ void dist_setup(tfelcu_solver* s);
 void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S);
 const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const int* n, int k, int out_slot);
 void dist_gather(tfelcu_solver* s, const double* x_local, double* x_global);
+void p2p_setup(Ctx* ctx);      // collective over the communicator of ctx
+void p2p_teardown(Ctx* ctx);
 
 }  // namespace tfelcu
