@@ -10,7 +10,7 @@ b += integrate<qf5pT>(f*v, m); u = a.solve(b, s).  `value` = cells / step time w
 resident in HBM; `e2e` = the same through the C ABI from HOST mesh arrays (upload, DOF numbering, Dirichlet set,
 pattern, assembly, solve, solution copied back to the host), everything inside the timed region.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--n 4096] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mesh-n 4096] [--impl reference]
 """
 import argparse
 import json
@@ -340,7 +340,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--mesh-n", dest="n", type=int, default=4096)
     ap.add_argument("--ref-n", type=int, default=REF_SAMPLE_N)
     ap.add_argument("--maxits", type=int, default=20000)
     ap.add_argument("--check-every", type=int, default=100)

@@ -89,7 +89,8 @@ struct Ctx {
   bool p2p = false;
   void* arena = nullptr;
   void* peer_arena[16] = {nullptr};
-  unsigned long long red_seq = 0, halo_seq = 0;
+  unsigned long long* seq_dev = nullptr;   // [0]: reductions done, [1 + q]: halo exchanges done with rank q (device counters,
+                                           // advanced by the kernels themselves so that the loop can live in a CUDA graph)
   DevBuf<double> table_scratch;   // reference-element tables of the form being assembled (stream ordered reuse)
 
   void count(uint64_t n = 1) { launches += n; }

@@ -117,9 +117,11 @@ __device__ __forceinline__ bool spin_until(const volatile unsigned long long* fl
 
 // warp w: fixed-order local sum of partial array w, contribution written into every rank's arena, flag, wait for
 // everybody's contribution, sum in rank order (every rank adds the same numbers in the same order)
-__global__ void k_p2p_allreduce(ReduceArgs A, int k, Peers peers, int me, int P, unsigned long long seq,
+__global__ void k_p2p_allreduce(ReduceArgs A, int k, Peers peers, int me, int P, unsigned long long* __restrict__ seq_dev,
                                 double* __restrict__ out, KrylovScalars* __restrict__ S) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned long long seq = seq_dev[0] + 1;   // every thread reads the counter before thread 0 advances it
+  __syncthreads();
   const int par = (int)(seq & 1ull);
   {
     const double* p = A.p[w];
@@ -150,6 +152,7 @@ __global__ void k_p2p_allreduce(ReduceArgs A, int k, Peers peers, int me, int P,
   for (int q = 0; q < P; ++q) t += __shfl_sync(0xffffffffu, v, q);
   if (lane == 0) out[w] = t;
   if (!__all_sync(0xffffffffu, ok) && lane == 0 && S) S->done = -3;
+  if (threadIdx.x == 0) seq_dev[0] = seq;
 }
 
 struct HaloArgs {
@@ -159,10 +162,13 @@ struct HaloArgs {
 // CTA q: my boundary values -> landing zone of rank q (+ flag); values of rank q -> halo entries of v
 __global__ void __launch_bounds__(256)
 k_p2p_halo(double* __restrict__ v, size_t n_local, const uint32_t* __restrict__ send_idx, HaloArgs H, Peers peers,
-           int me, unsigned long long seq, KrylovScalars* __restrict__ S) {
+           int me, unsigned long long* __restrict__ seq_dev, KrylovScalars* __restrict__ S) {
   if (S && S->done) return;
   const int q = blockIdx.x;
   if (q == me) return;
+  const unsigned long long seq = seq_dev[1 + q] + 1;
+  __syncthreads();
+  if (threadIdx.x == 0) seq_dev[1 + q] = seq;
   const int par = (int)(seq & 1ull);
   const size_t sc = H.send_off[q + 1] - H.send_off[q], rc = H.recv_off[q + 1] - H.recv_off[q];
   if (sc) {
@@ -193,7 +199,8 @@ void p2p_teardown(Ctx* ctx) {
   for (int q = 0; q < 16; ++q)
     if (ctx->peer_arena[q] && q != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_arena[q]);
   if (ctx->arena) cudaFree(ctx->arena);
-  ctx->arena = nullptr; ctx->p2p = false;
+  if (ctx->seq_dev) cudaFree(ctx->seq_dev);
+  ctx->arena = nullptr; ctx->seq_dev = nullptr; ctx->p2p = false;
   for (int q = 0; q < 16; ++q) ctx->peer_arena[q] = nullptr;
   cudaGetLastError();
 }
@@ -205,8 +212,10 @@ void p2p_setup(Ctx* ctx) {
   cudaIpcMemHandle_t mine_h;
   std::memset(&mine_h, 0, sizeof(mine_h));
   if (cudaMalloc(&ctx->arena, sizeof(Arena)) != cudaSuccess) { ok = 0; ctx->arena = nullptr; cudaGetLastError(); }
+  if (ok && cudaMalloc(&ctx->seq_dev, 32 * sizeof(unsigned long long)) != cudaSuccess) { ok = 0; ctx->seq_dev = nullptr; cudaGetLastError(); }
   if (ok) {
     TFELCU_CK(cudaMemsetAsync(ctx->arena, 0, sizeof(Arena), ctx->stream));
+    TFELCU_CK(cudaMemsetAsync(ctx->seq_dev, 0, 32 * sizeof(unsigned long long), ctx->stream));
     ctx->sync();
     if (cudaIpcGetMemHandle(&mine_h, ctx->arena) != cudaSuccess) { ok = 0; cudaGetLastError(); }
   }
@@ -371,7 +380,7 @@ void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S) {
     HaloArgs H;
     for (int q = 0; q <= P; ++q) { H.send_off[q] = D.send_off[q]; H.recv_off[q] = D.recv_off[q]; }
     for (int q = 0; q < P; ++q) H.land_off[q] = D.land_off[q];
-    k_p2p_halo<<<P, 256, 0, ctx->stream>>>(v, D.rows.n_local(), D.send_idx.p, H, peers_of(ctx), me, ++ctx->halo_seq,
+    k_p2p_halo<<<P, 256, 0, ctx->stream>>>(v, D.rows.n_local(), D.send_idx.p, H, peers_of(ctx), me, ctx->seq_dev,
                                           const_cast<KrylovScalars*>(S));
     ctx->count(); TFELCU_LAUNCH_CHECK();
     return;
@@ -399,7 +408,7 @@ const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const 
   for (int i = 0; i < 4; ++i) { A.p[i] = i < k ? partial[i] : nullptr; A.n[i] = i < k ? n[i] : 0; }
   double* out = D.red.p + out_slot;
   if (ctx->p2p) {
-    k_p2p_allreduce<<<1, 32 * k, 0, ctx->stream>>>(A, k, peers_of(ctx), ctx->rank, ctx->n_ranks, ++ctx->red_seq, out,
+    k_p2p_allreduce<<<1, 32 * k, 0, ctx->stream>>>(A, k, peers_of(ctx), ctx->rank, ctx->n_ranks, ctx->seq_dev, out,
                                                   s->scal.p);
     ctx->count(); TFELCU_LAUNCH_CHECK();
     return out;

@@ -11,6 +11,8 @@
 // solver.hpp:125-133). All reductions are per-CTA partial sums combined in a fixed order: bitwise reproducible.
 #include "solver.cuh"
 
+#include <cstdlib>
+
 namespace tfelcu {
 
 constexpr int kVecThreads = 256;
@@ -401,8 +403,11 @@ void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep) {
   // optional SpMV sampling for the roofline report: events around every profile_every-th launch
   const int prof_every = s->params.profile_every;
   std::vector<cudaEvent_t> prof;
+  std::vector<uint32_t> prof_it;
+  uint32_t last_sample = 0;
   auto sample_begin = [&](uint32_t it) -> bool {
-    if (prof_every <= 0 || it % (uint32_t)prof_every || prof.size() >= 1024) return false;
+    if (prof_every <= 0 || (it != 0 && it < last_sample + (uint32_t)prof_every) || prof.size() >= 1024) return false;
+    last_sample = it; prof_it.push_back(it);
     cudaEvent_t a, b;
     TFELCU_CK(cudaEventCreate(&a)); TFELCU_CK(cudaEventCreate(&b));
     prof.push_back(a); prof.push_back(b);
@@ -414,41 +419,70 @@ void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep) {
   ctx->download(&h, S, 1);
   uint32_t issued = 0;
   const uint32_t maxits = s->params.maxits;
+
+  // one CG iteration, enqueued on the context stream; every kernel returns at once when S->done is set
+  auto iteration = [&](uint32_t it, bool may_sample) {
+    if (dist) dist_halo_exchange(s, s->p.p, S);
+    const bool sampled = may_sample && sample_begin(it);
+    const int n_pq = spmv_launch(s, s->p.p, s->q.p, P_pq, S); ++n_spmv;
+    if (sampled) TFELCU_CK(cudaEventRecord(prof.back(), ctx->stream));
+    Sum pq[1];
+    global_sums({Sum{P_pq, n_pq}}, 0, pq);
+    k_cg_update<<<vg, kVecThreads, 0, ctx->stream>>>(s->q.p, dinv, fused ? 1 : 0, n, pq[0].p, pq[0].n, s->r.p, P_rz, P_rr, S);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+    if (!fused) {
+      apply_precond(s, s->r.p, s->z.p);
+      k_dot_partial<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, s->z.p, n, P_rz, S);
+      ctx->count(); TFELCU_LAUNCH_CHECK();
+    }
+    Sum g[2];
+    global_sums({Sum{P_rz, vg}, Sum{P_rr, vg}}, 1, g);
+    k_cg_direction<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, dinv, fused ? nullptr : s->z.p, n, g[0].p, g[0].n, s->p.p,
+                                                       s->x.p, S);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+    k_cg_commit<<<1, 32, 0, ctx->stream>>>(g[1].p, g[1].n, S);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+  };
+
+  // The loop is launch-bound once a rank's share of the matrix is small (8 GPUs: ~60 us of HBM work per iteration):
+  // `check - 1` iterations are captured once in a CUDA graph and replayed; one eager iteration per chunk carries the
+  // optional SpMV timing events. NCCL fallbacks and ILU(0) level launches stay eager.
+  const bool graph_ok = !std::getenv("TFELCU_NO_GRAPH") && pc != TFELCU_PC_ILU0 && (!dist || ctx->p2p) && check >= 8 &&
+                        maxits >= (uint32_t)(2 * check);
+  cudaGraphExec_t graph_exec = nullptr;
+  uint64_t graph_launches = 0, graph_spmv = 0;
+  if (graph_ok && !h.done) {
+    cudaGraph_t graph = nullptr;
+    const uint64_t l0 = ctx->launches, s0 = n_spmv;
+    TFELCU_CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    for (int it = 0; it < check - 1; ++it) iteration(0, false);
+    TFELCU_CK(cudaStreamEndCapture(ctx->stream, &graph));
+    graph_launches = ctx->launches - l0; graph_spmv = n_spmv - s0;
+    ctx->launches = l0; n_spmv = s0;   // captured, not launched yet
+    TFELCU_CK(cudaGraphInstantiate(&graph_exec, graph, 0));
+    TFELCU_CK(cudaGraphDestroy(graph));
+  }
   while (!h.done && issued < maxits) {
     uint32_t chunk = (uint32_t)check;
     if (issued + chunk > maxits) chunk = maxits - issued;
-    for (uint32_t it = 0; it < chunk; ++it) {
-      if (dist) dist_halo_exchange(s, s->p.p, S);
-      const bool sampled = sample_begin(issued + it);
-      const int n_pq = spmv_launch(s, s->p.p, s->q.p, P_pq, S); ++n_spmv;
-      if (sampled) TFELCU_CK(cudaEventRecord(prof.back(), ctx->stream));
-      Sum pq[1];
-      global_sums({Sum{P_pq, n_pq}}, 0, pq);
-      k_cg_update<<<vg, kVecThreads, 0, ctx->stream>>>(s->q.p, dinv, fused ? 1 : 0, n, pq[0].p, pq[0].n, s->r.p, P_rz, P_rr, S);
-      ctx->count(); TFELCU_LAUNCH_CHECK();
-      if (!fused) {
-        apply_precond(s, s->r.p, s->z.p);
-        k_dot_partial<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, s->z.p, n, P_rz, S);
-        ctx->count(); TFELCU_LAUNCH_CHECK();
-      }
-      Sum g[2];
-      global_sums({Sum{P_rz, vg}, Sum{P_rr, vg}}, 1, g);
-      k_cg_direction<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, dinv, fused ? nullptr : s->z.p, n, g[0].p, g[0].n, s->p.p,
-                                                         s->x.p, S);
-      ctx->count(); TFELCU_LAUNCH_CHECK();
-      k_cg_commit<<<1, 32, 0, ctx->stream>>>(g[1].p, g[1].n, S);
-      ctx->count(); TFELCU_LAUNCH_CHECK();
+    if (graph_exec && chunk == (uint32_t)check) {
+      TFELCU_CK(cudaGraphLaunch(graph_exec, ctx->stream));
+      ctx->count(graph_launches); n_spmv += graph_spmv;
+      iteration(issued + chunk - 1, true);
+    } else {
+      for (uint32_t it = 0; it < chunk; ++it) iteration(issued + it, true);
     }
     issued += chunk;
     ctx->download(&h, S, 1);
   }
+  if (graph_exec) TFELCU_CK(cudaGraphExecDestroy(graph_exec));
   if (!prof.empty()) {
     // samples taken after convergence (the kernels return at once) are discarded
     double total = 0.0; uint32_t cnt = 0;
     for (size_t e = 0; e + 1 < prof.size(); e += 2) {
       float ms = 0.f;
       TFELCU_CK(cudaEventElapsedTime(&ms, prof[e], prof[e + 1]));
-      if ((e / 2) * (size_t)prof_every < (size_t)h.its) { total += ms; ++cnt; }
+      if (prof_it[e / 2] < (uint32_t)h.its) { total += ms; ++cnt; }
       cudaEventDestroy(prof[e]); cudaEventDestroy(prof[e + 1]);
     }
     rep->spmv_avg_ms = cnt ? total / cnt : 0.0;

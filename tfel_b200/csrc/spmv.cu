@@ -105,6 +105,9 @@ static const StreamCfg kCfgs[] = {
 };
 constexpr int kNumCfgs = (int)(sizeof(kCfgs) / sizeof(kCfgs[0]));
 
+void spmv_configure(tfelcu_solver* s);
+int spmv_launch_vector(tfelcu_solver* s, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal);
+
 void spmv_plan(tfelcu_solver* s) {
   Ctx* ctx = s->ctx;
   SpmvPlan& P = s->plan;
@@ -146,6 +149,7 @@ void spmv_plan(tfelcu_solver* s) {
                                                                           P.n_blocks, reinterpret_cast<int4*>(P.desc.p));
   ctx->count(); TFELCU_LAUNCH_CHECK();
   ctx->sync();
+  spmv_configure(s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -318,15 +322,15 @@ int spmv_partial_count(tfelcu_solver* s) {
   return (int)grid_for(s->n * (size_t)s->plan.lanes, 256);
 }
 
+// grid < 0: only opt the kernel in to its dynamic shared memory size (done at plan time, outside any graph capture)
 template <bool DOT, int LANES, int TILE_NNZ, int CONSUMERS, int STAGES, int CTAS>
 static void launch_stream(tfelcu_solver* s, int grid, const double* d_x, double* d_y, double* dot_partial,
                           const KrylovScalars* scal) {
   auto kern = k_spmv_stream<DOT, LANES, TILE_NNZ, CONSUMERS, STAGES, CTAS>;
   const size_t smem = sizeof(StreamSmem<TILE_NNZ, CONSUMERS, STAGES>);
-  static bool configured = false;   // one flag per instantiation
-  if (!configured) {
+  if (grid < 0) {
     TFELCU_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    return;
   }
   kern<<<grid, CONSUMERS + 32, smem, s->ctx->stream>>>(s->rowptr, s->colind, s->val, reinterpret_cast<const int4*>(s->plan.desc.p),
                                                       s->plan.n_blocks, d_x, d_y, dot_partial, scal);
@@ -335,6 +339,13 @@ static void launch_stream(tfelcu_solver* s, int grid, const double* d_x, double*
 template <int TILE_NNZ, int CONSUMERS, int STAGES, int CTAS>
 static void launch_stream_cfg(tfelcu_solver* s, int grid, const double* d_x, double* d_y, double* dot_partial,
                               const KrylovScalars* scal) {
+  if (grid < 0) {
+    launch_stream<true, 4, TILE_NNZ, CONSUMERS, STAGES, CTAS>(s, grid, d_x, d_y, dot_partial, scal);
+    launch_stream<false, 4, TILE_NNZ, CONSUMERS, STAGES, CTAS>(s, grid, d_x, d_y, dot_partial, scal);
+    launch_stream<true, 1, TILE_NNZ, CONSUMERS, STAGES, CTAS>(s, grid, d_x, d_y, dot_partial, scal);
+    launch_stream<false, 1, TILE_NNZ, CONSUMERS, STAGES, CTAS>(s, grid, d_x, d_y, dot_partial, scal);
+    return;
+  }
   if (s->plan.row_lanes == 4) {
     if (dot_partial) launch_stream<true, 4, TILE_NNZ, CONSUMERS, STAGES, CTAS>(s, grid, d_x, d_y, dot_partial, scal);
     else launch_stream<false, 4, TILE_NNZ, CONSUMERS, STAGES, CTAS>(s, grid, d_x, d_y, dot_partial, scal);
@@ -344,10 +355,22 @@ static void launch_stream_cfg(tfelcu_solver* s, int grid, const double* d_x, dou
   }
 }
 
+static void stream_dispatch(tfelcu_solver* s, int grid, const double* d_x, double* d_y, double* dot_partial,
+                            const KrylovScalars* scal);
+
 int spmv_launch(tfelcu_solver* s, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal) {
   Ctx* ctx = s->ctx;
   if (s->plan.kernel == TFELCU_SPMV_TMA_STREAM) {
     const int grid = stream_grid(s);
+    stream_dispatch(s, grid, d_x, d_y, dot_partial, scal);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+    return grid;
+  }
+  return spmv_launch_vector(s, d_x, d_y, dot_partial, scal);
+}
+
+static void stream_dispatch(tfelcu_solver* s, int grid, const double* d_x, double* d_y, double* dot_partial,
+                            const KrylovScalars* scal) {
     switch (s->plan.cfg) {
       case 1: launch_stream_cfg<2048, 256, 4, 2>(s, grid, d_x, d_y, dot_partial, scal); break;
       case 2: launch_stream_cfg<1024, 128, 4, 4>(s, grid, d_x, d_y, dot_partial, scal); break;
@@ -355,9 +378,14 @@ int spmv_launch(tfelcu_solver* s, const double* d_x, double* d_y, double* dot_pa
       case 4: launch_stream_cfg<512, 64, 4, 8>(s, grid, d_x, d_y, dot_partial, scal); break;
       default: launch_stream_cfg<1024, 128, 3, 5>(s, grid, d_x, d_y, dot_partial, scal); break;
     }
-    ctx->count(); TFELCU_LAUNCH_CHECK();
-    return grid;
-  }
+}
+
+void spmv_configure(tfelcu_solver* s) {
+  if (s->plan.kernel == TFELCU_SPMV_TMA_STREAM) stream_dispatch(s, -1, nullptr, nullptr, nullptr, nullptr);
+}
+
+int spmv_launch_vector(tfelcu_solver* s, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal) {
+  Ctx* ctx = s->ctx;
   const unsigned grid = grid_for(s->n * (size_t)s->plan.lanes, 256);
 #define TFELCU_VEC(L)                                                                                             \
   do {                                                                                                            \
