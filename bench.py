@@ -28,6 +28,15 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "tfel_ref")
 REF_SAMPLE_N = 512
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -138,7 +147,7 @@ def run_reference(args):
                              "sample": "n=%d per step, %d steps; %s" % (n, args.steps, json.dumps(detail))},
             "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -328,13 +337,18 @@ def run_own(args):
                 "e2e": e2e, "gpu_launches": int(launches)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.ref_n)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
 def main():
+    # libraries (NCCL prints its version) must not pollute stdout: everything but the final JSON line goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

@@ -64,7 +64,7 @@ class SolverReport(C.Structure):
 SYMBOLS = [
     "tfelcu_last_error", "tfelcu_version", "tfelcu_ctx_create", "tfelcu_nccl_unique_id",
     "tfelcu_ctx_create_distributed", "tfelcu_ctx_destroy", "tfelcu_ctx_set_stream", "tfelcu_ctx_stream",
-    "tfelcu_ctx_synchronize", "tfelcu_ctx_rank", "tfelcu_ctx_launch_count", "tfelcu_ctx_p2p_enabled",
+    "tfelcu_ctx_synchronize", "tfelcu_ctx_rank", "tfelcu_ctx_launch_count", "tfelcu_ctx_p2p_enabled", "tfelcu_ctx_p2p_bench",
     "tfelcu_mesh_create", "tfelcu_mesh_gen_square", "tfelcu_mesh_gen_cube", "tfelcu_mesh_destroy",
     "tfelcu_mesh_info", "tfelcu_mesh_download", "tfelcu_mesh_geometry", "tfelcu_mesh_boundary",
     "tfelcu_mesh_boundary_download",
@@ -165,6 +165,11 @@ class Context:
     @property
     def p2p(self):
         return bool(lib().tfelcu_ctx_p2p_enabled(self.h))
+
+    def p2p_bench(self, reps=1000):
+        us = C.c_double()
+        _ck(lib().tfelcu_ctx_p2p_bench(self.h, int(reps), C.byref(us)))
+        return us.value
 
 
 class Mesh:

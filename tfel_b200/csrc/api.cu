@@ -170,6 +170,14 @@ uint64_t tfelcu_ctx_launch_count(const tfelcu_ctx* ctx) { return ctx ? ctx->laun
 
 int tfelcu_ctx_p2p_enabled(const tfelcu_ctx* ctx) { return ctx && ctx->p2p ? 1 : 0; }
 
+int tfelcu_ctx_p2p_bench(tfelcu_ctx* ctx, int reps, double* allreduce_us) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx && allreduce_us && reps > 0, "bad arguments");
+    use_device(ctx);
+    *allreduce_us = tfelcu::p2p_bench_allreduce(ctx, reps);
+  });
+}
+
 // ---- mesh --------------------------------------------------------------------------------------
 
 int tfelcu_mesh_create(tfelcu_ctx* ctx, int dim, const double* vertices, size_t n_vertices, const uint32_t* cells,

@@ -248,6 +248,29 @@ void p2p_setup(Ctx* ctx) {
   ctx->p2p = true;
 }
 
+static Peers peers_of(Ctx* ctx);
+
+// diagnostic: average time of one arena allreduce of 2 values (CUDA events, `reps` back-to-back launches)
+double p2p_bench_allreduce(Ctx* ctx, int reps) {
+  TFELCU_REQUIRE(ctx->p2p, "peer-to-peer arena is not enabled");
+  DevBuf<double> part(64), out(4);
+  ctx->zero(part.p, 64);
+  ReduceArgs A;
+  for (int i = 0; i < 4; ++i) { A.p[i] = part.p; A.n[i] = 32; }
+  cudaEvent_t e0, e1;
+  TFELCU_CK(cudaEventCreate(&e0)); TFELCU_CK(cudaEventCreate(&e1));
+  for (int r = 0; r < 10; ++r)
+    k_p2p_allreduce<<<1, 64, 0, ctx->stream>>>(A, 2, peers_of(ctx), ctx->rank, ctx->n_ranks, ctx->seq_dev, out.p, nullptr);
+  TFELCU_CK(cudaEventRecord(e0, ctx->stream));
+  for (int r = 0; r < reps; ++r)
+    k_p2p_allreduce<<<1, 64, 0, ctx->stream>>>(A, 2, peers_of(ctx), ctx->rank, ctx->n_ranks, ctx->seq_dev, out.p, nullptr);
+  TFELCU_CK(cudaEventRecord(e1, ctx->stream));
+  TFELCU_CK(cudaEventSynchronize(e1));
+  float ms = 0.f; TFELCU_CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return (double)ms * 1e3 / reps;
+}
+
 static Peers peers_of(Ctx* ctx) {
   Peers p;
   for (int q = 0; q < 16; ++q) p.a[q] = static_cast<Arena*>(ctx->peer_arena[q]);

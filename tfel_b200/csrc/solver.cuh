@@ -100,5 +100,6 @@ const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const 
 void dist_gather(tfelcu_solver* s, const double* x_local, double* x_global);
 void p2p_setup(Ctx* ctx);      // collective over the communicator of ctx
 void p2p_teardown(Ctx* ctx);
+double p2p_bench_allreduce(Ctx* ctx, int reps);
 
 }  // namespace tfelcu
