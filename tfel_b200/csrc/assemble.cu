@@ -15,6 +15,8 @@
 #include "structs.cuh"
 #include "geometry.cuh"
 
+#include <cstdlib>
+
 namespace tfelcu {
 
 constexpr int kMaxTerms = 16;
@@ -39,6 +41,10 @@ struct DevTerm {
 struct FormDev {
   int nq, n_terms, n_factors, pad;
   int off_w, off_xhat, off_hat_te, off_hat_tr, off_ref, n_stage;
+  // constant-coefficient forms: sum_t c_t D^{a_t} psi D^{b_t} phi collapses to the W x W tensor
+  //   G = [ c00 , c0r^T Jmt ; Jmt^T cr0 , Jmt^T C Jmt ]   contracted with the pre-integrated reference tensor
+  int has00, has0r, hasr0, hasrr;
+  double c00, c0r[kMaxDim], cr0[kMaxDim], C[kMaxDim][kMaxDim];
   const double* tables;
   DevTerm terms[kMaxTerms];
   DevFactor factors[kMaxFactors];
@@ -145,32 +151,59 @@ __device__ __forceinline__ void element_row(const FormDev& F, const double* sm, 
 #pragma unroll
   for (int j = 0; j < ND_TR; ++j) acc[j] = 0.0;
   if constexpr (CONST_COEF) {
-    // sum_t c_t (T_t (x) R_t) : Mhat, Mhat[a][b][i][j] = sum_q w_q hat_te[q][i][a] hat_tr[q][j][b]
-    double G[W][W];
-#pragma unroll
-    for (int a = 0; a < W; ++a)
-#pragma unroll
-      for (int b = 0; b < W; ++b) G[a][b] = 0.0;
-    for (int t = 0; t < F.n_terms; ++t) {
-      double T[W], R[W];
-      pullback<DIM>(F.terms[t].test_d, g, T);
-      pullback<DIM>(F.terms[t].trial_d, g, R);
-      const double c = F.terms[t].c;
-#pragma unroll
-      for (int a = 0; a < W; ++a)
-#pragma unroll
-        for (int b = 0; b < W; ++b) G[a][b] += c * T[a] * R[b];
-    }
+    // G : Mhat with Mhat[a][b][i][j] = sum_q w_q hat_te[q][i][a] hat_tr[q][j][b] staged in shared memory
     const double* ref = sm + F.off_ref;
+    if (F.has00) {
+      const double* mrow = ref + (0 * ND_TE + i) * ND_TR;
 #pragma unroll
-    for (int a = 0; a < W; ++a)
+      for (int j = 0; j < ND_TR; ++j) acc[j] += F.c00 * mrow[j];
+    }
+    if (F.has0r) {
 #pragma unroll
-      for (int b = 0; b < W; ++b) {
-        const double gab = G[a][b];
-        const double* mrow = ref + ((a * W + b) * ND_TE + i) * ND_TR;
+      for (int u = 0; u < DIM; ++u) {
+        double gv = 0.0;
 #pragma unroll
-        for (int j = 0; j < ND_TR; ++j) acc[j] += gab * mrow[j];
+        for (int d = 0; d < DIM; ++d) gv += F.c0r[d] * g.jmt[d][u];
+        const double* mrow = ref + ((0 * W + 1 + u) * ND_TE + i) * ND_TR;
+#pragma unroll
+        for (int j = 0; j < ND_TR; ++j) acc[j] += gv * mrow[j];
       }
+    }
+    if (F.hasr0) {
+#pragma unroll
+      for (int s2 = 0; s2 < DIM; ++s2) {
+        double gv = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) gv += F.cr0[d] * g.jmt[d][s2];
+        const double* mrow = ref + (((1 + s2) * W + 0) * ND_TE + i) * ND_TR;
+#pragma unroll
+        for (int j = 0; j < ND_TR; ++j) acc[j] += gv * mrow[j];
+      }
+    }
+    if (F.hasrr) {
+      // Jmt^T C Jmt
+      double CJ[DIM][DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d)
+#pragma unroll
+        for (int u = 0; u < DIM; ++u) {
+          double v = 0.0;
+#pragma unroll
+          for (int e = 0; e < DIM; ++e) v += F.C[d][e] * g.jmt[e][u];
+          CJ[d][u] = v;
+        }
+#pragma unroll
+      for (int s2 = 0; s2 < DIM; ++s2)
+#pragma unroll
+        for (int u = 0; u < DIM; ++u) {
+          double gv = 0.0;
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) gv += g.jmt[d][s2] * CJ[d][u];
+          const double* mrow = ref + (((1 + s2) * W + 1 + u) * ND_TE + i) * ND_TR;
+#pragma unroll
+          for (int j = 0; j < ND_TR; ++j) acc[j] += gv * mrow[j];
+        }
+    }
   } else {
     const double* wq = sm + F.off_w;
     const double* hat_te = sm + F.off_hat_te;
@@ -285,7 +318,11 @@ struct RowBlock {
   const uint32_t* adj_ptr; const uint32_t* adj;
   const uint8_t* dir_row; const int32_t* rowptr; const int32_t* colind; double* val;
   int init_mode;   // STAGED only: 1 = values are uninitialised (pending clear()): write them fresh
+  const uint32_t* slots; size_t a_begin;   // slot map of this (segment, trial component), or nullptr: search colind
 };
+
+// slots of one entry of the transposed dof map: nd_tr bytes padded to whole 32-bit words
+__host__ __device__ constexpr int slot_words(int nd_tr) { return (nd_tr + 3) / 4; }
 
 template <int DIM, int ND_TE, int ND_TR, bool CONST_COEF, bool STAGED>
 __global__ void __launch_bounds__(kRowsPerCta) k_assemble_rows(const __grid_constant__ FormDev F, const RowBlock B) {
@@ -315,12 +352,26 @@ __global__ void __launch_bounds__(kRowsPerCta) k_assemble_rows(const __grid_cons
         load_cell_geometry<DIM>(B.vertices, B.cells + k * (DIM + 1), g);
         double acc[ND_TR];
         element_row<DIM, ND_TE, ND_TR, CONST_COEF>(F, sm, k, i, g, acc);
+        if (B.slots) {
+          constexpr int SW = slot_words(ND_TR);
+          const uint32_t* sl = B.slots + (size_t)(a - B.a_begin) * SW;
+          uint32_t w[SW];
 #pragma unroll
-        for (int j = 0; j < ND_TR; ++j) {
-          const int32_t col = (int32_t)(B.off_tr + B.map_tr[k * ND_TR + j]);
-          const int pos = find_in_row(B.colind, rs, re, col);
-          if constexpr (STAGED) stage[pos - seg0] += acc[j] * g.vol;
-          else B.val[pos] += acc[j] * g.vol;
+          for (int t = 0; t < SW; ++t) w[t] = __ldg(sl + t);
+#pragma unroll
+          for (int j = 0; j < ND_TR; ++j) {
+            const int pos = rs + (int)((w[j >> 2] >> (8 * (j & 3))) & 0xffu);
+            if constexpr (STAGED) stage[pos - seg0] += acc[j] * g.vol;
+            else B.val[pos] += acc[j] * g.vol;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < ND_TR; ++j) {
+            const int32_t col = (int32_t)(B.off_tr + B.map_tr[k * ND_TR + j]);
+            const int pos = find_in_row(B.colind, rs, re, col);
+            if constexpr (STAGED) stage[pos - seg0] += acc[j] * g.vol;
+            else B.val[pos] += acc[j] * g.vol;
+          }
         }
       }
     } else if (STAGED && B.init_mode) {
@@ -486,6 +537,15 @@ static void build_form(Ctx* ctx, tfelcu_mesh* mesh, int quad, const tfelcu_facto
       out.const_coef = false;
     }
   }
+  if (out.const_coef) {
+    for (int t = 0; t < F.n_terms; ++t) {
+      const DevTerm& d = F.terms[t];
+      if (d.test_d == 0 && d.trial_d == 0) { F.has00 = 1; F.c00 += d.c; }
+      else if (d.test_d == 0) { F.has0r = 1; F.c0r[d.trial_d - 1] += d.c; }
+      else if (d.trial_d == 0) { F.hasr0 = 1; F.cr0[d.test_d - 1] += d.c; }
+      else { F.hasrr = 1; F.C[d.test_d - 1][d.trial_d - 1] += d.c; }
+    }
+  }
   // tables staged in shared memory
   std::vector<double>& T = out.tables;
   F.off_w = (int)T.size(); T.insert(T.end(), Q.w.begin(), Q.w.end());
@@ -649,6 +709,9 @@ static void assemble_bilinear_dim(tfelcu_matrix* m, int quad, const tfelcu_facto
   const bool single_block = (m->test.n == 1 && m->trial.n == 1);
   const bool colored = (m->scatter == TFELCU_SCATTER_COLORED);
   if (colored) matrix_build_colors(m);
+  else if (!m->has_slots && !m->slots_failed && !std::getenv("TFELCU_NO_SLOTS")) {
+    try { matrix_build_slots(m); } catch (const Error&) { m->has_slots = false; m->slots_failed = true; }   // rows > 256 entries: search
+  }
   for (int a = 0; a < m->test.n; ++a)
     for (int b = 0; b < m->trial.n; ++b) {
       tfelcu_fes* te = m->test.fes[a]; tfelcu_fes* tr = m->trial.fes[b];
@@ -672,6 +735,8 @@ static void assemble_bilinear_dim(tfelcu_matrix* m, int quad, const tfelcu_facto
           if (m->rows.comp[sg] != a) continue;
           B.row_begin = m->rows.g_begin[sg] - m->test.offset[a]; B.row_end = m->rows.g_end[sg] - m->test.offset[a];
           B.local_off = m->rows.local_off[sg];
+          B.slots = m->has_slots ? m->slots[(size_t)sg * m->trial.n + b].p : nullptr;
+          B.a_begin = m->a_begin[sg];
           TFELCU_DISPATCH_ND(DIM, nd_te, NTE,
             TFELCU_DISPATCH_ND(DIM, nd_tr, NTR,
               if (staged) { if constexpr (NTE == NTR) launch_rows<DIM, NTE, NTR>(ctx, fb, B, true, m->max_block_nnz); }

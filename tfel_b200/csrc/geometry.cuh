@@ -54,15 +54,28 @@ __device__ __forceinline__ void load_cell_geometry(const double* __restrict__ ve
                                                    const uint32_t* __restrict__ cell,
                                                    CellGeom<DIM>& g) {
   uint32_t id[DIM + 1];
+  if constexpr (DIM == 3) {   // four ids = one 16-byte load (cells are [K][4], 16-byte aligned)
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(cell));
+    id[0] = q.x; id[1] = q.y; id[2] = q.z; id[3] = q.w;
+  } else {
 #pragma unroll
-  for (int v = 0; v <= DIM; ++v) id[v] = cell[v];
+    for (int v = 0; v <= DIM; ++v) id[v] = __ldg(cell + v);
+  }
+  if constexpr (DIM == 2) {   // a vertex = one 16-byte load
+    const double2* v2 = reinterpret_cast<const double2*>(vertices);
+    const double2 p0 = __ldg(v2 + id[0]), p1 = __ldg(v2 + id[1]), p2 = __ldg(v2 + id[2]);
+    g.v0[0] = p0.x; g.v0[1] = p0.y;
+    g.J[0][0] = p1.x - p0.x; g.J[1][0] = p1.y - p0.y;
+    g.J[0][1] = p2.x - p0.x; g.J[1][1] = p2.y - p0.y;
+  } else {
 #pragma unroll
-  for (int r = 0; r < DIM; ++r) g.v0[r] = __ldg(vertices + (size_t)id[0] * DIM + r);
+    for (int r = 0; r < DIM; ++r) g.v0[r] = __ldg(vertices + (size_t)id[0] * DIM + r);
 #pragma unroll
-  for (int c = 0; c < DIM; ++c)
+    for (int c = 0; c < DIM; ++c)
 #pragma unroll
-    for (int r = 0; r < DIM; ++r)
-      g.J[r][c] = __ldg(vertices + (size_t)id[c + 1] * DIM + r) - g.v0[r];
+      for (int r = 0; r < DIM; ++r)
+        g.J[r][c] = __ldg(vertices + (size_t)id[c + 1] * DIM + r) - g.v0[r];
+  }
   finish_cell_geometry<DIM>(g);
 }
 

@@ -92,7 +92,7 @@ void matrix_build_pattern(tfelcu_matrix* m) {
   const size_t n_local = R.n_local();
   TFELCU_REQUIRE(m->n_rows < 0xfffffffeull && m->n_cols < 0xfffffffeull, "matrix too large for 32-bit indices");
   // owned slices of the transposed test dof maps, one per row segment
-  size_t a_begin[kMaxSeg], a_count[kMaxSeg];
+  size_t* a_begin = m->a_begin; size_t* a_count = m->a_count;
   for (int sg = 0; sg < R.n; ++sg) {
     const int a = R.comp[sg];
     tfelcu_fes* te = m->test.fes[a];
@@ -151,6 +151,65 @@ void matrix_build_pattern(tfelcu_matrix* m) {
   m->max_block_nnz = (size_t)h;
   m->has_colors = false;
   m->val_valid = false;
+  m->has_slots = false; m->slots_failed = false;
+  m->slots.clear();
+}
+
+// one thread per entry a of the owned slice of the transposed test dof map: positions of its nd_tr columns in the row
+__global__ void k_build_slots(const uint32_t* __restrict__ adj, size_t a_begin, size_t n_adj,
+                              const uint32_t* __restrict__ map_te, int nd_te, uint32_t off_te,
+                              unsigned long long row_begin, unsigned long long local_off,
+                              const uint32_t* __restrict__ map_tr, int nd_tr, uint32_t off_tr,
+                              const uint8_t* __restrict__ dir_row, const int32_t* __restrict__ rowptr,
+                              const int32_t* __restrict__ colind, int words, uint32_t* __restrict__ slots, int* __restrict__ bad) {
+  const size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= n_adj) return;
+  const uint32_t code = adj[a_begin + p];
+  const size_t k = code / nd_te;
+  const uint32_t r = map_te[code];
+  uint32_t* out = slots + p * words;
+  for (int t = 0; t < words; ++t) out[t] = 0u;
+  if (dir_row[off_te + r]) return;
+  const size_t lrow = local_off + (r - row_begin);
+  const int rs = rowptr[lrow], re = rowptr[lrow + 1];
+  for (int j = 0; j < nd_tr; ++j) {
+    const int32_t col = (int32_t)(off_tr + map_tr[k * nd_tr + j]);
+    int lo = rs, hi = re;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (colind[mid] < col) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= re || colind[lo] != col || lo - rs > 255) { atomicExch(bad, 1); return; }
+    out[j >> 2] |= (uint32_t)(lo - rs) << (8 * (j & 3));
+  }
+}
+
+void matrix_build_slots(tfelcu_matrix* m) {
+  if (m->has_slots) return;
+  Ctx* ctx = m->ctx;
+  const RowMap& R = m->rows;
+  m->slots.clear();
+  m->slots.resize((size_t)R.n * m->trial.n);
+  DevBuf<int> bad(1);
+  ctx->zero(bad.p, 1);
+  for (int sg = 0; sg < R.n; ++sg)
+    for (int b = 0; b < m->trial.n; ++b) {
+      const int a = R.comp[sg];
+      tfelcu_fes* te = m->test.fes[a]; tfelcu_fes* tr = m->trial.fes[b];
+      const int words = (tr->nd + 3) / 4;
+      const size_t n = m->a_count[sg];
+      DevBuf<uint32_t>& S = m->slots[(size_t)sg * m->trial.n + b];
+      S.alloc(n * words);
+      if (!n) continue;
+      k_build_slots<<<grid_for(n, 256), 256, 0, ctx->stream>>>(te->adj.p, m->a_begin[sg], n, te->dof_map, te->nd,
+                                                             (uint32_t)m->test.offset[a], R.g_begin[sg] - m->test.offset[a],
+                                                             R.local_off[sg], tr->dof_map, tr->nd, (uint32_t)m->trial.offset[b],
+                                                             m->dir_row.p, m->rowptr.p, m->colind.p, words, S.p, bad.p);
+      ctx->count(); TFELCU_LAUNCH_CHECK();
+    }
+  int h = 0; ctx->download(&h, bad.p, 1);
+  if (h) { m->slots.clear(); fail("slot map: a row has more than 256 stored entries or the pattern is inconsistent"); }
+  m->has_slots = true;
 }
 
 // clear(): zero everything, identity on the Dirichlet rows (bilinear_form.hpp:159-165)

@@ -150,6 +150,12 @@ struct tfelcu_matrix {
   int scatter = TFELCU_SCATTER_ROW_GATHER;
   bool val_valid = false;                // false: clear() is pending (performed lazily by the first user)
   size_t max_block_nnz = 0;             // max nnz over blocks of kRowsPerCta consecutive rows
+  // slot map: for entry a of the owned slice of the transposed test dof map (cell k, local dof i of row r) and local
+  // trial dof j, the position of column dof_tr(k, j) inside row r -- so that the assembly never searches colind.
+  // One byte per (a, j), padded to whole 32-bit words per entry.
+  size_t a_begin[tfelcu::kMaxSeg] = {0}, a_count[tfelcu::kMaxSeg] = {0};
+  bool has_slots = false, slots_failed = false;
+  std::vector<tfelcu::DevBuf<uint32_t>> slots;   // [segment * n_trial + trial component][a_count * slot_words(nd_tr)]
   // cell colouring (TFELCU_SCATTER_COLORED): cells sorted by colour
   bool has_colors = false;
   int n_colors = 0;
@@ -182,6 +188,7 @@ void matrix_snapshot_dirichlet(tfelcu_matrix* m);
 void matrix_build_pattern(tfelcu_matrix* m);
 void matrix_build_colors(tfelcu_matrix* m);
 void matrix_ensure_cleared(tfelcu_matrix* m);
+void matrix_build_slots(tfelcu_matrix* m);
 void fes_transpose(tfelcu_fes* f);
 void build_transpose(Ctx* ctx, const uint32_t* dof_map, size_t K, int nd, size_t n_dof,
                      DevBuf<uint32_t>& ptr, DevBuf<uint32_t>& adj);
