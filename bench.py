@@ -45,6 +45,18 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel, n, n_gpus):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/), or None
+    when no capture exists for this configuration"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["per_launch_bytes"][kernel]
+        if d["n"] == n and d["n_gpus"] == n_gpus:
+            return d["dram_read"] + d["dram_write"]
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -263,7 +275,7 @@ def run_own(args):
     roofline = {"kernel": "k_spmv_stream<true> (CSR fp64 SpMV + fused p.Ap partials, inside CG)", "bound": "hbm",
                 "achieved": (spmv_bytes / (spmv_avg_ms * 1e-3) / 1e9) if spmv_avg_ms else None, "peak": peak,
                 "unit": "GB/s", "frac": (spmv_bytes / (spmv_avg_ms * 1e-3) / 1e9 / peak) if spmv_avg_ms else None,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
+                "traffic": ncu_traffic("k_spmv_stream<true,1,1024,128,3,5>", n, world), "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
                 "avg_launch_ms": spmv_avg_ms, "samples_per_solve": int(args.maxits // max(args.profile_every, 1)),
                 "frac_of_nominal_8TBs": (spmv_bytes / (spmv_avg_ms * 1e-3) / 1e9 / 8000.0) if spmv_avg_ms else None}
     assembly = {"cells_per_s": cells / (asm_avg_ms * 1e-3), "ms": asm_avg_ms,
