@@ -118,7 +118,7 @@ __device__ __forceinline__ bool spin_until(const volatile unsigned long long* fl
 // warp w: fixed-order local sum of partial array w, contribution written into every rank's arena, flag, wait for
 // everybody's contribution, sum in rank order (every rank adds the same numbers in the same order)
 __global__ void k_p2p_allreduce(ReduceArgs A, int k, Peers peers, int me, int P, unsigned long long* __restrict__ seq_dev,
-                                double* __restrict__ out, KrylovScalars* __restrict__ S) {
+                                double* __restrict__ out, KrylovScalars* __restrict__ S, int epilogue) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned long long seq = seq_dev[0] + 1;   // every thread reads the counter before thread 0 advances it
   __syncthreads();
@@ -153,6 +153,10 @@ __global__ void k_p2p_allreduce(ReduceArgs A, int k, Peers peers, int me, int P,
   if (lane == 0) out[w] = t;
   if (!__all_sync(0xffffffffu, ok) && lane == 0 && S) S->done = -3;
   if (threadIdx.x == 0) seq_dev[0] = seq;
+  if (epilogue == 1) {   // single-reduction CG: (gamma, rr, delta) -> alpha, beta, stopping test, in the same launch
+    __syncthreads();
+    if (threadIdx.x == 0) cgs_scalar_step(S, out[0], out[1], out[2]);
+  }
 }
 
 struct HaloArgs {
@@ -260,10 +264,10 @@ double p2p_bench_allreduce(Ctx* ctx, int reps) {
   cudaEvent_t e0, e1;
   TFELCU_CK(cudaEventCreate(&e0)); TFELCU_CK(cudaEventCreate(&e1));
   for (int r = 0; r < 10; ++r)
-    k_p2p_allreduce<<<1, 64, 0, ctx->stream>>>(A, 2, peers_of(ctx), ctx->rank, ctx->n_ranks, ctx->seq_dev, out.p, nullptr);
+    k_p2p_allreduce<<<1, 64, 0, ctx->stream>>>(A, 2, peers_of(ctx), ctx->rank, ctx->n_ranks, ctx->seq_dev, out.p, nullptr, 0);
   TFELCU_CK(cudaEventRecord(e0, ctx->stream));
   for (int r = 0; r < reps; ++r)
-    k_p2p_allreduce<<<1, 64, 0, ctx->stream>>>(A, 2, peers_of(ctx), ctx->rank, ctx->n_ranks, ctx->seq_dev, out.p, nullptr);
+    k_p2p_allreduce<<<1, 64, 0, ctx->stream>>>(A, 2, peers_of(ctx), ctx->rank, ctx->n_ranks, ctx->seq_dev, out.p, nullptr, 0);
   TFELCU_CK(cudaEventRecord(e1, ctx->stream));
   TFELCU_CK(cudaEventSynchronize(e1));
   float ms = 0.f; TFELCU_CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -424,7 +428,11 @@ void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S) {
 }
 
 // out_slot .. out_slot + k - 1 of the reduction buffer <- global sums of k partial arrays; returns the device address
-const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const int* n, int k, int out_slot) {
+__global__ void k_cgs_scalars_from(const double* __restrict__ v, KrylovScalars* __restrict__ S) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) cgs_scalar_step(S, v[0], v[1], v[2]);
+}
+
+const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const int* n, int k, int out_slot, int epilogue) {
   Ctx* ctx = s->ctx;
   DistPlan& D = *s->dist;
   ReduceArgs A;
@@ -432,13 +440,17 @@ const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const 
   double* out = D.red.p + out_slot;
   if (ctx->p2p) {
     k_p2p_allreduce<<<1, 32 * k, 0, ctx->stream>>>(A, k, peers_of(ctx), ctx->rank, ctx->n_ranks, ctx->seq_dev, out,
-                                                  s->scal.p);
+                                                  s->scal.p, epilogue);
     ctx->count(); TFELCU_LAUNCH_CHECK();
     return out;
   }
   k_reduce_many<<<k, 32, 0, ctx->stream>>>(A, out);
   ctx->count(); TFELCU_LAUNCH_CHECK();
   TFELCU_NCCL(ncclAllReduce(out, out, (size_t)k, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+  if (epilogue == 1) {
+    k_cgs_scalars_from<<<1, 32, 0, ctx->stream>>>(out, s->scal.p);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+  }
   return out;
 }
 

@@ -356,6 +356,218 @@ static void apply_precond(tfelcu_solver* s, const double* d_in, double* d_out) {
   else fail("preconditioner has no stand-alone apply");
 }
 
+// ------------------------------------------------------------------------------------------
+// Single-reduction CG (Chronopoulos & Gear): the same Krylov iterates as the standard method in exact arithmetic with
+// ONE global reduction per iteration (gamma = r.u, r.r, delta = u.Au together) and one fused vector kernel, for the
+// row-distributed solve where every synchronisation point costs more than the extra two vector passes:
+//     w = A u ; (gamma, rr, delta) ; beta = gamma / gamma_old ; alpha = gamma / (delta - beta gamma / alpha_old)
+//     p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = M^-1 r          (M = diag(A) or I)
+// Per iteration: halo exchange of u, SpMV (+ partials of u.Au), reduction (+ scalar step), fused update = 4 launches.
+// ------------------------------------------------------------------------------------------
+
+// u = M^-1 r, p = s = 0, partial sums of r.u and r.r
+__global__ void __launch_bounds__(kVecThreads)
+k_cgs_start(const double* __restrict__ r, const double* __restrict__ dinv, size_t n, double* __restrict__ u,
+            double* __restrict__ p, double* __restrict__ sd, double* __restrict__ partial_g, double* __restrict__ partial_rr) {
+  __shared__ double red[kVecThreads / 32];
+  double g = 0.0, rr = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double ri = r[i];
+    const double ui = dinv ? dinv[i] * ri : ri;
+    u[i] = ui; p[i] = 0.0; sd[i] = 0.0;
+    g += ri * ui; rr += ri * ri;
+  }
+  const double t0 = block_sum(g, red);
+  const double t1 = block_sum(rr, red);
+  if (threadIdx.x == 0) { partial_g[blockIdx.x] = t0; partial_rr[blockIdx.x] = t1; }
+}
+
+__global__ void k_cgs_init_scalars(const double* __restrict__ partial_bb, int n_partial, double rtol, double atol, double dtol,
+                                   double maxits, KrylovScalars* __restrict__ S) {
+  if (threadIdx.x || blockIdx.x) return;
+  const double bb = sum_partials(partial_bb, n_partial);
+  const double target = fmax(rtol * sqrt(bb), atol);
+  S->bnorm2 = bb; S->target2 = target * target; S->dtol2 = dtol * dtol * bb;
+  S->spare1 = maxits;
+  S->its = 0; S->done = 0;
+}
+
+// single process: the three sums come as per-CTA partials
+__global__ void k_cgs_scalars(const double* __restrict__ pg, int ng, const double* __restrict__ prr, int nrr,
+                              const double* __restrict__ pd, int nd, KrylovScalars* __restrict__ S) {
+  if (blockIdx.x || threadIdx.x >= 32) return;
+  double v[3];
+  const double* p[3] = {pg, prr, pd};
+  const int n[3] = {ng, nrr, nd};
+  for (int k = 0; k < 3; ++k) {
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n[k]; i += 32) t += p[k][i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    v[k] = t;
+  }
+  if (threadIdx.x == 0) cgs_scalar_step(S, v[0], v[1], v[2]);
+}
+
+__global__ void __launch_bounds__(kVecThreads)
+k_cgs_fused(const double* __restrict__ w, const double* __restrict__ dinv, size_t n, double* __restrict__ u,
+            double* __restrict__ p, double* __restrict__ sd, double* __restrict__ x, double* __restrict__ r,
+            double* __restrict__ partial_g, double* __restrict__ partial_rr, const KrylovScalars* __restrict__ S) {
+  __shared__ double red[kVecThreads / 32];
+  if (S->done) return;
+  const double alpha = S->alpha, beta = S->beta;
+  double g = 0.0, rr = 0.0;
+  const size_t n2 = n / 2;
+  const double2* w2 = reinterpret_cast<const double2*>(w);
+  const double2* d2 = reinterpret_cast<const double2*>(dinv);
+  double2* u2 = reinterpret_cast<double2*>(u);
+  double2* p2 = reinterpret_cast<double2*>(p);
+  double2* s2 = reinterpret_cast<double2*>(sd);
+  double2* x2 = reinterpret_cast<double2*>(x);
+  double2* r2 = reinterpret_cast<double2*>(r);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    double2 uv = u2[i], pv = p2[i], sv = s2[i], xv = x2[i], rv = r2[i];
+    const double2 wv = w2[i];
+    pv.x = uv.x + beta * pv.x; pv.y = uv.y + beta * pv.y;
+    sv.x = wv.x + beta * sv.x; sv.y = wv.y + beta * sv.y;
+    xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+    rv.x -= alpha * sv.x; rv.y -= alpha * sv.y;
+    if (dinv) { const double2 dv = d2[i]; uv.x = dv.x * rv.x; uv.y = dv.y * rv.y; } else uv = rv;
+    p2[i] = pv; s2[i] = sv; x2[i] = xv; r2[i] = rv; u2[i] = uv;
+    g += rv.x * uv.x; g += rv.y * uv.y;
+    rr += rv.x * rv.x; rr += rv.y * rv.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const size_t i = n - 1;
+    const double pi = u[i] + beta * p[i], si = w[i] + beta * sd[i];
+    p[i] = pi; sd[i] = si; x[i] += alpha * pi;
+    const double ri = r[i] - alpha * si;
+    r[i] = ri;
+    const double ui = dinv ? dinv[i] * ri : ri;
+    u[i] = ui;
+    g += ri * ui; rr += ri * ri;
+  }
+  const double t0 = block_sum(g, red);
+  const double t1 = block_sum(rr, red);
+  if (threadIdx.x == 0) { partial_g[blockIdx.x] = t0; partial_rr[blockIdx.x] = t1; }
+}
+
+void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep) {
+  Ctx* ctx = s->ctx;
+  const size_t n = s->n;
+  const int vg = vec_grid(s);
+  const int pc = s->params.precond;
+  const double* dinv = pc == TFELCU_PC_JACOBI ? s->dinv.p : nullptr;
+  const bool dist = (bool)s->dist;
+  const size_t n_halo = dist ? s->dist->n_halo : 0;
+  if (s->z.n < n + n_halo) s->z.alloc(n + n_halo);
+  if (s->sdir.n < n) s->sdir.alloc(n);
+  double* u = s->z.p; double* w = s->q.p; double* sd = s->sdir.p;
+  ctx->zero(u, n + n_halo);
+  double* P_d = s->partial.p;
+  double* P_g = s->partial.p + s->n_partial;
+  double* P_rr = s->partial.p + 2 * (size_t)s->n_partial;
+  double* P_bb = s->partial.p + 3 * (size_t)s->n_partial;
+  KrylovScalars* S = s->scal.p;
+  uint64_t n_spmv = 0;
+  const uint64_t launches0 = ctx->launches;
+
+  ctx->zero(S, 1);
+  k_initial_guess<<<grid_for(n, 256), 256, 0, ctx->stream>>>(s->rowptr, s->colind, s->val, s->b.p, n, s->x.p);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  if (dist) dist_halo_exchange(s, s->x.p, nullptr);
+  spmv_launch(s, s->x.p, w, nullptr, nullptr); ++n_spmv;
+  k_residual<<<vg, kVecThreads, 0, ctx->stream>>>(s->b.p, w, n, s->r.p, P_bb);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  {
+    const double* bbp = P_bb; int nbb = vg;
+    if (dist) { const double* ptrs[1] = {P_bb}; const int ns[1] = {vg}; bbp = dist_reduce(s, ptrs, ns, 1, 4); nbb = 1; }
+    k_cgs_init_scalars<<<1, 32, 0, ctx->stream>>>(bbp, nbb, s->params.rtol, s->params.atol, s->params.dtol,
+                                                  (double)s->params.maxits, S);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+  }
+  k_cgs_start<<<vg, kVecThreads, 0, ctx->stream>>>(s->r.p, dinv, n, u, s->p.p, sd, P_g, P_rr);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+
+  const int prof_every = s->params.profile_every;
+  std::vector<cudaEvent_t> prof;
+  std::vector<uint32_t> prof_it;
+  uint32_t last_sample = 0;
+  auto iteration = [&](uint32_t it, bool may_sample) {
+    if (dist) dist_halo_exchange(s, u, S);
+    const bool sampled = may_sample && prof_every > 0 && (it == 0 || it >= last_sample + (uint32_t)prof_every) && prof.size() < 1024;
+    if (sampled) {
+      cudaEvent_t a, b;
+      TFELCU_CK(cudaEventCreate(&a)); TFELCU_CK(cudaEventCreate(&b));
+      prof.push_back(a); prof.push_back(b); prof_it.push_back(it); last_sample = it;
+      TFELCU_CK(cudaEventRecord(a, ctx->stream));
+    }
+    const int n_d = spmv_launch(s, u, w, P_d, S); ++n_spmv;
+    if (sampled) TFELCU_CK(cudaEventRecord(prof.back(), ctx->stream));
+    if (dist) {
+      const double* ptrs[3] = {P_g, P_rr, P_d}; const int ns[3] = {vg, vg, n_d};
+      dist_reduce(s, ptrs, ns, 3, 0, 1);
+    } else {
+      k_cgs_scalars<<<1, 32, 0, ctx->stream>>>(P_g, vg, P_rr, vg, P_d, n_d, S);
+      ctx->count(); TFELCU_LAUNCH_CHECK();
+    }
+    k_cgs_fused<<<vg, kVecThreads, 0, ctx->stream>>>(w, dinv, n, u, s->p.p, sd, s->x.p, s->r.p, P_g, P_rr, S);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+  };
+
+  int check = s->params.check_every > 0 ? s->params.check_every : 50;
+  KrylovScalars h;
+  ctx->download(&h, S, 1);
+  uint32_t issued = 0;
+  const uint32_t maxits = s->params.maxits;
+  const bool graph_ok = !std::getenv("TFELCU_NO_GRAPH") && (!dist || ctx->p2p) && check >= 8 && maxits >= (uint32_t)(2 * check);
+  cudaGraphExec_t graph_exec = nullptr;
+  uint64_t graph_launches = 0, graph_spmv = 0;
+  if (graph_ok) {
+    cudaGraph_t graph = nullptr;
+    const uint64_t l0 = ctx->launches, s0 = n_spmv;
+    TFELCU_CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    for (int it = 0; it < check - 1; ++it) iteration(0, false);
+    TFELCU_CK(cudaStreamEndCapture(ctx->stream, &graph));
+    graph_launches = ctx->launches - l0; graph_spmv = n_spmv - s0;
+    ctx->launches = l0; n_spmv = s0;
+    TFELCU_CK(cudaGraphInstantiate(&graph_exec, graph, 0));
+    TFELCU_CK(cudaGraphDestroy(graph));
+  }
+  // one extra pass detects convergence of the last update (the test runs at the start of an iteration)
+  while (!h.done && issued < maxits + 1) {
+    uint32_t chunk = (uint32_t)check;
+    if (issued + chunk > maxits + 1) chunk = maxits + 1 - issued;
+    if (graph_exec && chunk == (uint32_t)check) {
+      TFELCU_CK(cudaGraphLaunch(graph_exec, ctx->stream));
+      ctx->count(graph_launches); n_spmv += graph_spmv;
+      iteration(issued + chunk - 1, true);
+    } else {
+      for (uint32_t it = 0; it < chunk; ++it) iteration(issued + it, true);
+    }
+    issued += chunk;
+    ctx->download(&h, S, 1);
+  }
+  if (graph_exec) TFELCU_CK(cudaGraphExecDestroy(graph_exec));
+  if (!prof.empty()) {
+    double total = 0.0; uint32_t cnt = 0;
+    for (size_t e = 0; e + 1 < prof.size(); e += 2) {
+      float ms = 0.f;
+      TFELCU_CK(cudaEventElapsedTime(&ms, prof[e], prof[e + 1]));
+      if (prof_it[e / 2] < (uint32_t)h.its) { total += ms; ++cnt; }
+      cudaEventDestroy(prof[e]); cudaEventDestroy(prof[e + 1]);
+    }
+    rep->spmv_avg_ms = cnt ? total / cnt : 0.0;
+    rep->spmv_samples = cnt;
+  }
+  rep->its = (uint32_t)h.its;
+  rep->converged = h.done == 1 ? 1 : ((h.done == 0 || h.done == 2) ? 0 : h.done);
+  rep->rnorm = sqrt(h.rr);
+  rep->bnorm = sqrt(h.bnorm2);
+  rep->n_spmv = n_spmv;
+  rep->n_launches = ctx->launches - launches0;
+}
+
 void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep) {
   Ctx* ctx = s->ctx;
   const size_t n = s->n;
@@ -504,7 +716,13 @@ void solver_solve(tfelcu_solver* s, const double* d_rhs, double* d_x, tfelcu_sol
   TFELCU_CK(cudaEventCreate(&e0)); TFELCU_CK(cudaEventCreate(&e1));
   TFELCU_CK(cudaEventRecord(e0, ctx->stream));
   TFELCU_CK(cudaMemcpyAsync(s->b.p, d_rhs, s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  if (s->params.method == TFELCU_METHOD_CG) solve_cg(s, rep);
+  // row-distributed solves with a pointwise preconditioner use the single-reduction recurrences (fewer launches and
+  // reductions per iteration); TFELCU_CG=standard / single forces either
+  const char* cg_env = std::getenv("TFELCU_CG");
+  const bool pointwise = s->params.precond == TFELCU_PC_JACOBI || s->params.precond == TFELCU_PC_NONE;
+  const bool single = pointwise && (cg_env ? std::string(cg_env) == "single" : (bool)s->dist);
+  if (s->params.method == TFELCU_METHOD_CG && single) solve_cg_single_reduction(s, rep);
+  else if (s->params.method == TFELCU_METHOD_CG) solve_cg(s, rep);
   else if (s->params.method == TFELCU_METHOD_GMRES) solve_gmres(s, rep);
   else fail("unknown Krylov method");
   TFELCU_CK(cudaMemcpyAsync(d_x, s->x.p, s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));

@@ -6,6 +6,9 @@
 
 namespace tfelcu {
 
+// scalar step of the single-reduction (Chronopoulos-Gear) CG from gamma = r.u, rr = r.r, delta = u.Au
+__device__ __forceinline__ void cgs_scalar_step(struct KrylovScalars* S, double gamma, double rr, double delta);
+
 // device-side scalars of a Krylov iteration (one cache line, read by every kernel)
 struct KrylovScalars {
   double rz, pq, alpha, beta, rr, bnorm2, target2, dtol2;
@@ -14,6 +17,21 @@ struct KrylovScalars {
   int its;
   int pad0, pad1;
 };
+
+__device__ __forceinline__ void cgs_scalar_step(KrylovScalars* S, double gamma, double rr, double delta) {
+  if (S->done) return;
+  S->rr = rr;
+  if (!(rr == rr) || !(delta == delta)) { S->done = -2; return; }
+  if (rr <= S->target2) { S->done = 1; return; }
+  if (rr > S->dtol2) { S->done = -1; return; }
+  if ((double)S->its >= S->spare1) { S->done = 2; return; }   // maxits updates done
+  double beta = 0.0, alpha;
+  if (S->its == 0) alpha = gamma / delta;
+  else { beta = gamma / S->rz; alpha = gamma / (delta - beta * gamma / S->alpha); }
+  if (!(alpha == alpha) || delta == 0.0) { S->done = -2; return; }
+  S->alpha = alpha; S->beta = beta; S->rz = gamma; S->pq = delta;
+  S->its += 1;
+}
 
 struct SpmvPlan {
   int kernel = TFELCU_SPMV_VECTOR;
@@ -67,6 +85,7 @@ struct tfelcu_solver {
   tfelcu::SpmvPlan plan;
   // work space
   tfelcu::DevBuf<double> x, b, r, p, q, z, dinv, partial;
+  tfelcu::DevBuf<double> sdir;             // s = A p of the single-reduction CG
   tfelcu::DevBuf<tfelcu::KrylovScalars> scal;
   tfelcu::DevBuf<double> block_inv;        // block Jacobi: [n_blocks][bs][bs]
   tfelcu::DevBuf<double> basis, hess;      // GMRES
@@ -96,7 +115,9 @@ void block_jacobi_apply(tfelcu_solver* s, const double* d_in, double* d_out);
 // ---- dist.cu
 void dist_setup(tfelcu_solver* s);
 void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S);
-const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const int* n, int k, int out_slot);
+// epilogue == 1: the reducing kernel also performs the scalar step of the single-reduction CG (k_cgs_scalars)
+const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const int* n, int k, int out_slot, int epilogue = 0);
+void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep);
 void dist_gather(tfelcu_solver* s, const double* x_local, double* x_global);
 void p2p_setup(Ctx* ctx);      // collective over the communicator of ctx
 void p2p_teardown(Ctx* ctx);
