@@ -493,8 +493,18 @@ void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep) {
   std::vector<cudaEvent_t> prof;
   std::vector<uint32_t> prof_it;
   uint32_t last_sample = 0;
+  // TFELCU_TRACE=1: time every launch of the eager iteration of each chunk (diagnostic, printed by rank 0)
+  const bool trace = std::getenv("TFELCU_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tr;
+  auto mark = [&](bool on) {
+    if (!on) return;
+    cudaEvent_t e; TFELCU_CK(cudaEventCreate(&e)); TFELCU_CK(cudaEventRecord(e, ctx->stream)); tr.push_back(e);
+  };
   auto iteration = [&](uint32_t it, bool may_sample) {
+    const bool t_on = trace && may_sample && tr.size() < 5000;
+    mark(t_on);
     if (dist) dist_halo_exchange(s, u, S);
+    mark(t_on);
     const bool sampled = may_sample && prof_every > 0 && (it == 0 || it >= last_sample + (uint32_t)prof_every) && prof.size() < 1024;
     if (sampled) {
       cudaEvent_t a, b;
@@ -504,6 +514,7 @@ void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep) {
     }
     const int n_d = spmv_launch(s, u, w, P_d, S); ++n_spmv;
     if (sampled) TFELCU_CK(cudaEventRecord(prof.back(), ctx->stream));
+    mark(t_on);
     if (dist) {
       const double* ptrs[3] = {P_g, P_rr, P_d}; const int ns[3] = {vg, vg, n_d};
       dist_reduce(s, ptrs, ns, 3, 0, 1);
@@ -511,8 +522,10 @@ void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep) {
       k_cgs_scalars<<<1, 32, 0, ctx->stream>>>(P_g, vg, P_rr, vg, P_d, n_d, S);
       ctx->count(); TFELCU_LAUNCH_CHECK();
     }
+    mark(t_on);
     k_cgs_fused<<<vg, kVecThreads, 0, ctx->stream>>>(w, dinv, n, u, s->p.p, sd, s->x.p, s->r.p, P_g, P_rr, S);
     ctx->count(); TFELCU_LAUNCH_CHECK();
+    mark(t_on);
   };
 
   int check = s->params.check_every > 0 ? s->params.check_every : 50;
@@ -549,6 +562,15 @@ void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep) {
     ctx->download(&h, S, 1);
   }
   if (graph_exec) TFELCU_CK(cudaGraphExecDestroy(graph_exec));
+  if (!tr.empty()) {
+    double acc[4] = {0, 0, 0, 0}; int cnt = 0;
+    for (size_t e = 0; e + 4 < tr.size(); e += 5, ++cnt)
+      for (int k = 0; k < 4; ++k) { float ms = 0.f; cudaEventElapsedTime(&ms, tr[e + k], tr[e + k + 1]); acc[k] += ms; }
+    if (ctx->rank == 0 && cnt)
+      std::fprintf(stderr, "[tfelcu trace] eager iteration, avg of %d: halo %.1f us, spmv %.1f us, reduce %.1f us, fused %.1f us\n",
+                   cnt, 1e3 * acc[0] / cnt, 1e3 * acc[1] / cnt, 1e3 * acc[2] / cnt, 1e3 * acc[3] / cnt);
+    for (cudaEvent_t e : tr) cudaEventDestroy(e);
+  }
   if (!prof.empty()) {
     double total = 0.0; uint32_t cnt = 0;
     for (size_t e = 0; e + 1 < prof.size(); e += 2) {

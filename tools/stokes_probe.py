@@ -1,0 +1,31 @@
+"""configs[3] probe (tools only): Stokes P2-P2-P1 on gen_square_mesh(n), assembly time and GMRES + ILU(0) behaviour."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import cuda_runner  # noqa: E402
+import problems  # noqa: E402
+from tfel_b200 import capi  # noqa: E402
+
+ctx = capi.Context(0)
+for n in [int(v) for v in sys.argv[1:]] or [64, 128]:
+    p = problems.stokes(n)
+    t0 = time.perf_counter()
+    B = cuda_runner.build(ctx, p)
+    ctx.synchronize(); t_struct = time.perf_counter() - t0
+    for rep in range(2):
+        B.matrix.clear(); B.vector.clear()
+        t0 = time.perf_counter()
+        cuda_runner.assemble(B)
+        ctx.synchronize(); t_asm = time.perf_counter() - t0
+    s = capi.Solver(ctx, method="gmres", precond="ilu0", maxits=3000, restart=300, rtol=1e-8)
+    t0 = time.perf_counter()
+    x, rep = B.matrix.solve(B.vector, s)
+    t_solve = time.perf_counter() - t0
+    print("stokes n=%d: cells %d dofs %d nnz %d | structure %.3f s, assembly %.4f s (%.3g cells/s) | gmres+ilu0: its %d converged %d "
+          "setup %.3f s solve %.3f s launches %d" % (n, B.mesh.n_cells, B.matrix.n_rows, B.matrix.nnz, t_struct, t_asm,
+                                                      B.mesh.n_cells / t_asm, rep["its"], rep["converged"], rep["t_setup_s"],
+                                                      rep["t_solve_s"], rep["n_launches"]), flush=True)
+    s.close(); cuda_runner.close(B)
