@@ -222,7 +222,7 @@ def run_own(args):
     x_dev = torch.empty(a.n_cols, dtype=torch.float64, device="cuda")
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    asm_ms, solve_ms, spmv_ms, its_seen = [], [], [], []
+    asm_ms, solve_ms, spmv_ms, its_seen, spmv_samples = [], [], [], [], []
 
     def step(timed):
         e0, e1, e2 = ev(), ev(), ev()
@@ -239,7 +239,7 @@ def run_own(args):
         if timed:
             e2.synchronize()
             asm_ms.append(e0.elapsed_time(e1)); solve_ms.append(e1.elapsed_time(e2))
-            spmv_ms.append(rep["spmv_avg_ms"]); its_seen.append(rep["its"])
+            spmv_ms.append(rep["spmv_avg_ms"]); its_seen.append(rep["its"]); spmv_samples.append(rep["spmv_samples"])
         return rep
 
     for _ in range(args.warmup):
@@ -276,7 +276,7 @@ def run_own(args):
                 "achieved": (spmv_bytes / (spmv_avg_ms * 1e-3) / 1e9) if spmv_avg_ms else None, "peak": peak,
                 "unit": "GB/s", "frac": (spmv_bytes / (spmv_avg_ms * 1e-3) / 1e9 / peak) if spmv_avg_ms else None,
                 "traffic": ncu_traffic("k_spmv_stream<true,1,1024,128,3,5>", n, world), "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
-                "avg_launch_ms": spmv_avg_ms, "samples_per_solve": int(args.maxits // max(args.profile_every, 1)),
+                "avg_launch_ms": spmv_avg_ms, "samples_per_solve": int(np.mean(spmv_samples)) if spmv_samples else 0,
                 "frac_of_nominal_8TBs": (spmv_bytes / (spmv_avg_ms * 1e-3) / 1e9 / 8000.0) if spmv_avg_ms else None}
     assembly = {"cells_per_s": cells / (asm_avg_ms * 1e-3), "ms": asm_avg_ms,
                 "algorithmic_bytes": asm_bytes, "achieved_gbs": asm_bytes / (asm_avg_ms * 1e-3) / 1e9,

@@ -44,7 +44,7 @@ __global__ void k_diag_pos(const int32_t* __restrict__ rowptr, const int32_t* __
 template <bool LOWER>
 __global__ void __launch_bounds__(128)
 k_levels(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind, const int32_t* __restrict__ diag,
-         size_t n, unsigned int* __restrict__ ticket, volatile int* __restrict__ level) {
+         size_t n, unsigned int* __restrict__ ticket, volatile int* __restrict__ level, int* __restrict__ stuck) {
   __shared__ unsigned int blk;
   if (threadIdx.x == 0) blk = atomicAdd(ticket, 1u);
   __syncthreads();
@@ -57,7 +57,11 @@ k_levels(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
   for (int e = e0; e < e1; ++e) {
     const int c = colind[e];
     int l;
-    while ((l = level[c]) < 0) { __nanosleep(20); }
+    const long long t0 = clock64();
+    while ((l = level[c]) < 0) {
+      if (clock64() - t0 > 40000000000ll) { atomicExch(stuck, 1); l = 0; break; }   // never expected: do not hang the GPU
+      __nanosleep(20);
+    }
     lv = l + 1 > lv ? l + 1 : lv;
   }
   __threadfence();
@@ -224,9 +228,11 @@ void ilu0_setup(tfelcu_solver* s) {
   for (int pass = 0; pass < 2; ++pass) {
     TFELCU_CK(cudaMemsetAsync(level.p, 0xff, n * sizeof(int), ctx->stream));
     ctx->zero(ticket.p, 1);
-    if (pass == 0) k_levels<true><<<grid_for(n, 128), 128, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, n, ticket.p, level.p);
-    else k_levels<false><<<grid_for(n, 128), 128, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, n, ticket.p, level.p);
+    if (pass == 0) k_levels<true><<<grid_for(n, 128), 128, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, n, ticket.p, level.p, missing.p);
+    else k_levels<false><<<grid_for(n, 128), 128, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, n, ticket.p, level.p, missing.p);
     ctx->count(); TFELCU_LAUNCH_CHECK();
+    ctx->download(&h_missing, missing.p, 1);
+    TFELCU_REQUIRE(!h_missing, "ILU(0): level analysis did not terminate");
     if (pass == 0) schedule(ctx, level.p, n, I.order_l, I.level_ptr_l);
     else schedule(ctx, level.p, n, I.order_u, I.level_ptr_u);
   }
