@@ -30,6 +30,7 @@
 #include <memory>
 #include <string>
 #include <tuple>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -354,6 +355,13 @@ public:
   class element {   // composite_fes.hpp:152-300
   public:
     element(const composite_finite_element_space& f, array<double> c) : fes(&f), coefficients(std::move(c)) {}
+    // from one element per component (composite_fes.hpp:160-175)
+    template <typename first_t, typename... rest_t,
+              typename = typename std::enable_if<!std::is_same<typename std::decay<first_t>::type, array<double>>::value>::type>
+    element(const composite_finite_element_space& f, const first_t& c0, const rest_t&... cs) : fes(&f), coefficients{f.get_total_dof_number()} {
+      std::size_t at(0);
+      append(at, c0, cs...);
+    }
     const array<double>& get_coefficients() const { return coefficients; }
     template <std::size_t n>
     typename component_space<n>::element get_component() const {
@@ -364,6 +372,14 @@ public:
       return typename component_space<n>::element(sp, std::move(c));
     }
   private:
+    void append(std::size_t&) {}
+    template <typename first_t, typename... rest_t>
+    void append(std::size_t& at, const first_t& c0, const rest_t&... cs) {
+      const array<double>& c(c0.get_coefficients());
+      for (std::size_t i(0); i < c.get_size(0); ++i) coefficients.at(at + i) = c.at(i);
+      at += c.get_size(0);
+      append(at, cs...);
+    }
     const composite_finite_element_space* fes;
     array<double> coefficients;
   };
@@ -377,6 +393,8 @@ public:
   void add_dirichlet_boundary(const sm_t& dm, rest... value) { std::get<n>(spaces)->add_dirichlet_boundary(dm, value...); }
 
   std::size_t get_total_dof_number() const { return get_component_offset(n_component); }
+  template <std::size_t n>
+  std::size_t get_dof_number() const { return std::get<n>(spaces)->get_dof_number(); }
   std::size_t get_component_offset(std::size_t c) const {   // blocks concatenated: [u0 | u1 | p] (composite_bilinear_form.hpp:41-62)
     std::vector<std::size_t> n;
     dof_numbers(n, std::make_index_sequence<n_component>());
@@ -601,9 +619,30 @@ public:
     std::vector<double> xq;
     int nq(0), dim(0);
     std::size_t K(0);
-    factors.resize(e.factors.size());
+    // the same coefficient (same field + derivative, same callback, same program) appears once in the C arrays
+    std::vector<int> remap(e.factors.size(), -1);
+    std::vector<std::size_t> kept;
     for (std::size_t i(0); i < e.factors.size(); ++i) {
       const factor_desc& f(e.factors[i]);
+      for (std::size_t k(0); k < kept.size() and remap[i] < 0; ++k) {
+        const factor_desc& g(e.factors[kept[k]]);
+        bool same(f.kind == g.kind and f.d == g.d);
+        if (same and f.kind == TFELCU_FACTOR_FIELD) same = f.fes == g.fes and f.data.get() == g.data.get();
+        else if (same and f.kind == TFELCU_FACTOR_PROGRAM) {
+          same = f.prog.size() == g.prog.size();
+          for (std::size_t t(0); same and t < f.prog.size(); ++t) same = f.prog[t].op == g.prog[t].op and f.prog[t].imm == g.prog[t].imm;
+        } else if (same) {
+          typedef double (*fn_t)(const double*);
+          const fn_t* pf(f.fn.template target<fn_t>()); const fn_t* pg(g.fn.template target<fn_t>());
+          same = pf and pg and *pf == *pg;
+        }
+        if (same) remap[i] = static_cast<int>(k);
+      }
+      if (remap[i] < 0) { remap[i] = static_cast<int>(kept.size()); kept.push_back(i); }
+    }
+    factors.resize(kept.size());
+    for (std::size_t i(0); i < kept.size(); ++i) {
+      const factor_desc& f(e.factors[kept[i]]);
       tfelcu_factor& o(factors[i]);
       o.kind = f.kind; o.d = f.d; o.fes = f.fes; o.data = nullptr; o.ops = nullptr; o.n_ops = 0; o.pad = 0;
       if (f.kind == TFELCU_FACTOR_FIELD) o.data = f.data->data();
@@ -627,7 +666,7 @@ public:
       tfelcu_term t;
       t.test_comp = m.test_comp; t.test_d = m.test_d; t.trial_comp = m.trial_comp; t.trial_d = m.trial_d;
       t.c = m.c; t.n_factors = static_cast<int>(m.factors.size());
-      for (int k(0); k < 5; ++k) t.factor[k] = k < t.n_factors ? m.factors[k] : 0;
+      for (int k(0); k < 5; ++k) t.factor[k] = k < t.n_factors ? remap[m.factors[k]] : 0;
       terms.push_back(t);
     }
   }

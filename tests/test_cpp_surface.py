@@ -72,3 +72,19 @@ def test_user_plugin_fields_and_integrals():
     r = subprocess.run([os.path.join(BIN, "plugin_and_forms")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "plugin_and_forms: ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_reference_navier_stokes_program():
+    """test/navier_stokes_2d_p2_p1.cpp:236-448 on the CUDA path: Newton iterations converge (relative velocity step
+    below 1e-8) within the reference's 10 steps for the first time steps; per-step reassembly with coefficient fields."""
+    build()
+    r = subprocess.run([os.path.join(BIN, "navier_stokes_2d_p2_p1"), "12", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr
+    assert "warning" not in r.stdout
+    steps = [line for line in r.stdout.splitlines() if line.startswith("newton step #")]
+    assert len(steps) >= 4
+    # quadratic convergence: the last Newton step of each time step is below the tolerance
+    last = [float(line.split("(")[1].split(",")[0]) for line in steps]
+    assert min(last) < 1e-8
+    assert "summary:" in r.stdout

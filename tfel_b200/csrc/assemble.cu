@@ -19,8 +19,8 @@
 
 namespace tfelcu {
 
-constexpr int kMaxTerms = 16;
-constexpr int kMaxFactors = 8;
+constexpr int kMaxTerms = 24;
+constexpr int kMaxFactors = 12;
 constexpr int kMaxProgOps = 48;
 
 struct DevFactor {
