@@ -464,9 +464,31 @@ inline int import_factors(const expression<a>& src, std::vector<factor_desc>& ds
   return base;
 }
 
+// c * (one finite element field, possibly differentiated) and nothing else
+template <bool a>
+inline bool is_plain_field(const expression<a>& x) {
+  return x.terms.size() == 1 and x.terms[0].test_comp < 0 and x.terms[0].trial_comp < 0 and x.terms[0].factors.size() == 1 and
+         x.factors[x.terms[0].factors[0]].kind == TFELCU_FACTOR_FIELD;
+}
+
 template <bool r, bool a, bool b>
 inline expression<r> add(const expression<a>& x, const expression<b>& y, double sign) {
   expression<r> out;
+  if (is_plain_field(x) and is_plain_field(y)) {
+    // fields of one space are a vector space: u_h +- v_h is the field of the summed coefficients, evaluated pointwise
+    // like the reference does (no cancellation between expanded products in (u_h - v_h) * (u_h - v_h))
+    const factor_desc& fx(x.factors[x.terms[0].factors[0]]);
+    const factor_desc& fy(y.factors[y.terms[0].factors[0]]);
+    if (fx.fes == fy.fes and fx.d == fy.d and fx.data->size() == fy.data->size()) {
+      factor_desc f(fx);
+      f.data = std::make_shared<std::vector<double>>(fx.data->size());
+      const double cx(x.terms[0].c), cy(sign * y.terms[0].c);
+      for (std::size_t i(0); i < f.data->size(); ++i) (*f.data)[i] = cx * (*fx.data)[i] + cy * (*fy.data)[i];
+      out.factors.push_back(f);
+      monomial m; m.factors.push_back(0); out.terms.push_back(m);
+      return out;
+    }
+  }
   out.factors = x.factors; out.terms = x.terms;
   const int base(import_factors(y, out.factors));
   for (monomial m : y.terms) { m.c *= sign; for (auto& f : m.factors) f += base; out.terms.push_back(m); }
