@@ -350,3 +350,22 @@ def test_full_size_fingerprints_match_the_reference(ctx, name, problem, golden_d
         assert n >= 8, n
     finally:
         cuda_runner.close(got["_built"])
+
+
+def test_quadrature_points_and_kind_offsets(ctx):
+    """tfelcu_mesh_quadrature_points (cell.hpp:456-468) against the oracle; entity-kind offsets of fes.hpp:33-72."""
+    from tfel_b200 import capi
+    m = capi.Mesh.square(ctx, 1.0, 1.0, 7, 7)
+    v, c = m.download()
+    assert np.array_equal(m.quadrature_points("qf5pT"), orc.quadrature_points(v, c, "qf5pT"))
+    p2 = capi.Space(m, "p2"); p1 = capi.Space(m, "p1"); p1b = capi.Space(m, "p1b")
+    assert p1.kind_offsets() == [0, 64, 64, 64, 64]
+    assert p2.kind_offsets() == [0, 64, 64 + 161, 64 + 161, 64 + 161][:2] + [225, 225, 225]
+    assert p1b.kind_offsets() == [0, 64, 64, 64 + 98, 64 + 98]
+    for s in (p1, p2, p1b):
+        s.close()
+    m.close()
+    m = capi.Mesh.cube(ctx, 1.0, 1.0, 1.0, 3, 3, 3)
+    v, c = m.download()
+    assert np.array_equal(m.quadrature_points("qfSym10pTet"), orc.quadrature_points(v, c, "qfSym10pTet"))
+    m.close()
