@@ -329,8 +329,8 @@ __global__ void __launch_bounds__(kRowsPerCta) k_assemble_rows(const __grid_cons
   extern __shared__ double sm[];
   for (int idx = threadIdx.x; idx < F.n_stage; idx += blockDim.x) sm[idx] = __ldg(F.tables + idx);
   double* stage = sm + F.n_stage;
-  const size_t r0 = B.row_begin + (size_t)blockIdx.x * kRowsPerCta;
-  size_t r1 = r0 + kRowsPerCta; if (r1 > B.row_end) r1 = B.row_end;
+  const size_t r0 = B.row_begin + (size_t)blockIdx.x * blockDim.x;   // one thread per row; blockDim.x = rows per CTA
+  size_t r1 = r0 + blockDim.x; if (r1 > B.row_end) r1 = B.row_end;
   const size_t to_local = B.local_off - B.row_begin;   // local row = dof + to_local (mod 2^64)
   int seg0 = 0, seg_len = 0;
   if constexpr (STAGED) {
@@ -642,15 +642,15 @@ static void ensure_smem(Kern kern, size_t bytes) {
 }
 
 template <int DIM, int ND_TE, int ND_TR>
-static void launch_rows(Ctx* ctx, const FormBuild& fb, const RowBlock& B, bool staged, size_t stage_doubles) {
+static void launch_rows(Ctx* ctx, const FormBuild& fb, const RowBlock& B, bool staged, size_t stage_doubles, int rows_per_cta) {
   if (B.row_end <= B.row_begin) return;
-  const unsigned grid = grid_for(B.row_end - B.row_begin, kRowsPerCta);
+  const unsigned grid = grid_for(B.row_end - B.row_begin, (unsigned)rows_per_cta);
   const size_t smem = ((size_t)fb.F.n_stage + (staged ? stage_doubles : 0)) * sizeof(double);
 #define TFELCU_ROWS(CC, ST)                                                                      \
   do {                                                                                           \
     auto kern = k_assemble_rows<DIM, ND_TE, ND_TR, CC, ST>;                                      \
     ensure_smem(kern, smem);                                                                     \
-    kern<<<grid, kRowsPerCta, smem, ctx->stream>>>(fb.F, B);                                     \
+    kern<<<grid, rows_per_cta, smem, ctx->stream>>>(fb.F, B);                                    \
   } while (0)
   if (fb.const_coef) { if (staged) TFELCU_ROWS(true, true); else TFELCU_ROWS(true, false); }
   else { if (staged) TFELCU_ROWS(false, true); else TFELCU_ROWS(false, false); }
@@ -739,8 +739,8 @@ static void assemble_bilinear_dim(tfelcu_matrix* m, int quad, const tfelcu_facto
           B.a_begin = m->a_begin[sg];
           TFELCU_DISPATCH_ND(DIM, nd_te, NTE,
             TFELCU_DISPATCH_ND(DIM, nd_tr, NTR,
-              if (staged) { if constexpr (NTE == NTR) launch_rows<DIM, NTE, NTR>(ctx, fb, B, true, m->max_block_nnz); }
-              else launch_rows<DIM, NTE, NTR>(ctx, fb, B, false, 0);))
+              if (staged) { if constexpr (NTE == NTR) launch_rows<DIM, NTE, NTR>(ctx, fb, B, true, m->max_block_nnz, m->rows_per_cta); }
+              else launch_rows<DIM, NTE, NTR>(ctx, fb, B, false, 0, m->rows_per_cta);))
         }
         if (staged) m->val_valid = true;
       } else {

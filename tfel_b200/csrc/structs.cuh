@@ -149,7 +149,8 @@ struct tfelcu_matrix {
   bool pristine = true;                 // no += since clear()
   int scatter = TFELCU_SCATTER_ROW_GATHER;
   bool val_valid = false;                // false: clear() is pending (performed lazily by the first user)
-  size_t max_block_nnz = 0;             // max nnz over blocks of kRowsPerCta consecutive rows
+  int rows_per_cta = 128;               // rows (= threads) of one CTA of the owner-computes assembly
+  size_t max_block_nnz = 0;             // max nnz over blocks of rows_per_cta consecutive rows
   // slot map: for entry a of the owned slice of the transposed test dof map (cell k, local dof i of row r) and local
   // trial dof j, the position of column dof_tr(k, j) inside row r -- so that the assembly never searches colind.
   // One byte per (a, j), padded to whole 32-bit words per entry.
