@@ -327,7 +327,8 @@ __host__ __device__ constexpr int slot_words(int nd_tr) { return (nd_tr + 3) / 4
 template <int DIM, int ND_TE, int ND_TR, bool CONST_COEF, bool STAGED>
 __global__ void __launch_bounds__(kRowsPerCta) k_assemble_rows(const __grid_constant__ FormDev F, const RowBlock B) {
   extern __shared__ double sm[];
-  for (int idx = threadIdx.x; idx < F.n_stage; idx += blockDim.x) sm[idx] = __ldg(F.tables + idx);
+  // constant-coefficient forms only read the pre-integrated reference tensor (the last table)
+  for (int idx = (CONST_COEF ? F.off_ref : 0) + threadIdx.x; idx < F.n_stage; idx += blockDim.x) sm[idx] = __ldg(F.tables + idx);
   double* stage = sm + F.n_stage;
   const size_t r0 = B.row_begin + (size_t)blockIdx.x * blockDim.x;   // one thread per row; blockDim.x = rows per CTA
   size_t r1 = r0 + blockDim.x; if (r1 > B.row_end) r1 = B.row_end;
