@@ -135,6 +135,9 @@ int tfelcu_ctx_destroy(tfelcu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     tfelcu::p2p_teardown(ctx);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->comm) ncclCommDestroy(ctx->comm);
     ctx->table_scratch.release();
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);

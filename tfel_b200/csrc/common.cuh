@@ -89,6 +89,8 @@ struct Ctx {
   bool p2p = false;
   void* arena = nullptr;
   void* peer_arena[16] = {nullptr};
+  cudaStream_t side_stream = nullptr;      // halo exchange overlapped with the interior SpMV
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   unsigned long long* seq_dev = nullptr;   // [0]: reductions done, [1 + q]: halo exchanges done with rank q (device counters,
                                            // advanced by the kernels themselves so that the loop can live in a CUDA graph)
   DevBuf<double> table_scratch;   // reference-element tables of the form being assembled (stream ordered reuse)

@@ -155,7 +155,7 @@ __global__ void k_p2p_allreduce(ReduceArgs A, int k, Peers peers, int me, int P,
   if (threadIdx.x == 0) seq_dev[0] = seq;
   if (epilogue == 1) {   // single-reduction CG: (gamma, rr, delta) -> alpha, beta, stopping test, in the same launch
     __syncthreads();
-    if (threadIdx.x == 0) cgs_scalar_step(S, out[0], out[1], out[2]);
+    if (threadIdx.x == 0) cgs_scalar_step(S, out[0], out[1], k == 4 ? out[2] + out[3] : out[2]);
   }
 }
 
@@ -398,22 +398,23 @@ void dist_setup(tfelcu_solver* s) {
 }
 
 // owned entries of v (length n_local + n_halo) -> halo entries of the neighbours' copies
-void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S) {
+void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S, cudaStream_t stream) {
   Ctx* ctx = s->ctx;
   DistPlan& D = *s->dist;
   const int P = ctx->n_ranks, me = ctx->rank;
   const size_t n_send = D.send_off[P];
+  if (!stream) stream = ctx->stream;
   if (D.p2p_halo) {
     HaloArgs H;
     for (int q = 0; q <= P; ++q) { H.send_off[q] = D.send_off[q]; H.recv_off[q] = D.recv_off[q]; }
     for (int q = 0; q < P; ++q) H.land_off[q] = D.land_off[q];
-    k_p2p_halo<<<P, 256, 0, ctx->stream>>>(v, D.rows.n_local(), D.send_idx.p, H, peers_of(ctx), me, ctx->seq_dev,
-                                          const_cast<KrylovScalars*>(S));
+    k_p2p_halo<<<P, 256, 0, stream>>>(v, D.rows.n_local(), D.send_idx.p, H, peers_of(ctx), me, ctx->seq_dev,
+                                     const_cast<KrylovScalars*>(S));
     ctx->count(); TFELCU_LAUNCH_CHECK();
     return;
   }
   if (n_send) {
-    k_pack<<<grid_for(n_send, 256), 256, 0, ctx->stream>>>(v, D.send_idx.p, n_send, D.send_buf.p, S);
+    k_pack<<<grid_for(n_send, 256), 256, 0, stream>>>(v, D.send_idx.p, n_send, D.send_buf.p, S);
     ctx->count(); TFELCU_LAUNCH_CHECK();
   }
   const size_t n_local = D.rows.n_local();
@@ -421,15 +422,15 @@ void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S) {
   for (int q = 0; q < P; ++q) {
     if (q == me) continue;
     const size_t rc = D.recv_off[q + 1] - D.recv_off[q], sc = D.send_off[q + 1] - D.send_off[q];
-    if (sc) TFELCU_NCCL(ncclSend(D.send_buf.p + D.send_off[q], sc, ncclDouble, q, ctx->comm, ctx->stream));
-    if (rc) TFELCU_NCCL(ncclRecv(v + n_local + D.recv_off[q], rc, ncclDouble, q, ctx->comm, ctx->stream));
+    if (sc) TFELCU_NCCL(ncclSend(D.send_buf.p + D.send_off[q], sc, ncclDouble, q, ctx->comm, stream));
+    if (rc) TFELCU_NCCL(ncclRecv(v + n_local + D.recv_off[q], rc, ncclDouble, q, ctx->comm, stream));
   }
   TFELCU_NCCL(ncclGroupEnd());
 }
 
 // out_slot .. out_slot + k - 1 of the reduction buffer <- global sums of k partial arrays; returns the device address
-__global__ void k_cgs_scalars_from(const double* __restrict__ v, KrylovScalars* __restrict__ S) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) cgs_scalar_step(S, v[0], v[1], v[2]);
+__global__ void k_cgs_scalars_from(const double* __restrict__ v, int k, KrylovScalars* __restrict__ S) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) cgs_scalar_step(S, v[0], v[1], k == 4 ? v[2] + v[3] : v[2]);
 }
 
 const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const int* n, int k, int out_slot, int epilogue) {
@@ -448,7 +449,7 @@ const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const 
   ctx->count(); TFELCU_LAUNCH_CHECK();
   TFELCU_NCCL(ncclAllReduce(out, out, (size_t)k, ncclDouble, ncclSum, ctx->comm, ctx->stream));
   if (epilogue == 1) {
-    k_cgs_scalars_from<<<1, 32, 0, ctx->stream>>>(out, s->scal.p);
+    k_cgs_scalars_from<<<1, 32, 0, ctx->stream>>>(out, k, s->scal.p);
     ctx->count(); TFELCU_LAUNCH_CHECK();
   }
   return out;

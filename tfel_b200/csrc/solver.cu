@@ -325,6 +325,7 @@ void solver_setup(tfelcu_solver* s) {
   s->scal.alloc(1);
   ctx->zero(s->scal.p, 1);
   spmv_plan(s);
+  if (s->dist) spmv_split_boundary(s, n);   // interior slabs first: they overlap the halo exchange
   int np = spmv_partial_count(s);
   const int vg = vec_grid(s);
   if (vg > np) np = vg;
@@ -500,10 +501,26 @@ void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep) {
     if (!on) return;
     cudaEvent_t e; TFELCU_CK(cudaEventCreate(&e)); TFELCU_CK(cudaEventRecord(e, ctx->stream)); tr.push_back(e);
   };
+  // distributed, optional (TFELCU_OVERLAP=1): the halo exchange runs on a side stream while the interior slabs (owned
+  // columns only) are multiplied; the boundary slabs follow once the halo has landed. Measured at n = 4096: 8 GPUs
+  // 0.122 vs 0.129 ms per iteration, 2 GPUs 0.362 vs 0.313 ms (the extra launch and the cross-stream joins cost more
+  // than the hidden latency), so it is off by default.
+  const bool overlap = dist && s->plan.n_interior > 0 && s->plan.n_interior < s->plan.n_blocks && std::getenv("TFELCU_OVERLAP");
+  if (overlap && !ctx->side_stream) {
+    TFELCU_CK(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    TFELCU_CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    TFELCU_CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  }
+  double* P_d2 = s->partial.p + 3 * (size_t)s->n_partial;   // partials of the boundary slabs (P_bb is free by then)
   auto iteration = [&](uint32_t it, bool may_sample) {
     const bool t_on = trace && may_sample && tr.size() < 5000;
     mark(t_on);
-    if (dist) dist_halo_exchange(s, u, S);
+    if (overlap) {
+      TFELCU_CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+      TFELCU_CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+      dist_halo_exchange(s, u, S, ctx->side_stream);
+      TFELCU_CK(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+    } else if (dist) dist_halo_exchange(s, u, S);
     mark(t_on);
     const bool sampled = may_sample && prof_every > 0 && (it == 0 || it >= last_sample + (uint32_t)prof_every) && prof.size() < 1024;
     if (sampled) {
@@ -512,10 +529,19 @@ void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep) {
       prof.push_back(a); prof.push_back(b); prof_it.push_back(it); last_sample = it;
       TFELCU_CK(cudaEventRecord(a, ctx->stream));
     }
-    const int n_d = spmv_launch(s, u, w, P_d, S); ++n_spmv;
+    int n_d, n_d2 = 0;
+    if (overlap) {
+      n_d = spmv_launch_part(s, 1, u, w, P_d, S);
+      TFELCU_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+      n_d2 = spmv_launch_part(s, 2, u, w, P_d2, S);
+    } else n_d = spmv_launch(s, u, w, P_d, S);
+    ++n_spmv;
     if (sampled) TFELCU_CK(cudaEventRecord(prof.back(), ctx->stream));
     mark(t_on);
-    if (dist) {
+    if (dist && n_d2 > 0) {
+      const double* ptrs[4] = {P_g, P_rr, P_d, P_d2}; const int ns[4] = {vg, vg, n_d, n_d2};
+      dist_reduce(s, ptrs, ns, 4, 0, 1);
+    } else if (dist) {
       const double* ptrs[3] = {P_g, P_rr, P_d}; const int ns[3] = {vg, vg, n_d};
       dist_reduce(s, ptrs, ns, 3, 0, 1);
     } else {

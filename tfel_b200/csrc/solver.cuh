@@ -41,6 +41,8 @@ struct SpmvPlan {
   int n_blocks = 0;
   int row_lanes = 1;                     // threads per row of the in-slab row reduction
   int cfg = 0;                           // tile shape (spmv.cu: kCfgs)
+  int part_begin = 0, part_count = 0;    // slab range of the launch being issued
+  int n_interior = -1;                   // distributed operators: slabs [0, n_interior) reference owned columns only
   int tile_nnz = 0, tile_rows = 0;
 };
 
@@ -108,13 +110,15 @@ void spmv_plan(tfelcu_solver* s);
 // y = A x; when dot_partial != nullptr also writes per-CTA partial sums of x . y and returns their number
 int spmv_launch(tfelcu_solver* s, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal);
 int spmv_partial_count(tfelcu_solver* s);
+int spmv_launch_part(tfelcu_solver* s, int part, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal);
+void spmv_split_boundary(tfelcu_solver* s, size_t n_local);
 void ilu0_setup(tfelcu_solver* s);
 void ilu0_apply(tfelcu_solver* s, const double* d_in, double* d_out);
 void block_jacobi_setup(tfelcu_solver* s);
 void block_jacobi_apply(tfelcu_solver* s, const double* d_in, double* d_out);
 // ---- dist.cu
 void dist_setup(tfelcu_solver* s);
-void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S);
+void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S, cudaStream_t stream = nullptr);
 // epilogue == 1: the reducing kernel also performs the scalar step of the single-reduction CG (k_cgs_scalars)
 const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const int* n, int k, int out_slot, int epilogue = 0);
 void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep);

@@ -311,11 +311,12 @@ k_spmv_vector(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
   }
 }
 
-static int stream_grid(tfelcu_solver* s) {
+static int stream_grid(tfelcu_solver* s, int n_slabs) {
   int g = s->ctx->sm_count * kCfgs[s->plan.cfg].ctas_per_sm;
-  if (g > s->plan.n_blocks) g = s->plan.n_blocks;
+  if (g > n_slabs) g = n_slabs;
   return g < 1 ? 1 : g;
 }
+static int stream_grid(tfelcu_solver* s) { return stream_grid(s, s->plan.n_blocks); }
 
 int spmv_partial_count(tfelcu_solver* s) {
   if (s->plan.kernel == TFELCU_SPMV_TMA_STREAM) return stream_grid(s);
@@ -332,8 +333,9 @@ static void launch_stream(tfelcu_solver* s, int grid, const double* d_x, double*
     TFELCU_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return;
   }
-  kern<<<grid, CONSUMERS + 32, smem, s->ctx->stream>>>(s->rowptr, s->colind, s->val, reinterpret_cast<const int4*>(s->plan.desc.p),
-                                                      s->plan.n_blocks, d_x, d_y, dot_partial, scal);
+  kern<<<grid, CONSUMERS + 32, smem, s->ctx->stream>>>(s->rowptr, s->colind, s->val,
+                                                      reinterpret_cast<const int4*>(s->plan.desc.p) + s->plan.part_begin,
+                                                      s->plan.part_count, d_x, d_y, dot_partial, scal);
 }
 
 template <int TILE_NNZ, int CONSUMERS, int STAGES, int CTAS>
@@ -362,11 +364,62 @@ int spmv_launch(tfelcu_solver* s, const double* d_x, double* d_y, double* dot_pa
   Ctx* ctx = s->ctx;
   if (s->plan.kernel == TFELCU_SPMV_TMA_STREAM) {
     const int grid = stream_grid(s);
+    s->plan.part_begin = 0; s->plan.part_count = s->plan.n_blocks;
     stream_dispatch(s, grid, d_x, d_y, dot_partial, scal);
     ctx->count(); TFELCU_LAUNCH_CHECK();
     return grid;
   }
   return spmv_launch_vector(s, d_x, d_y, dot_partial, scal);
+}
+
+// part 1: the slabs whose rows reference owned columns only (can run while the halo travels); part 2: the others.
+// Returns the number of dot partials written (0 when the part is empty and nothing was launched).
+int spmv_launch_part(tfelcu_solver* s, int part, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal) {
+  Ctx* ctx = s->ctx;
+  TFELCU_REQUIRE(s->plan.kernel == TFELCU_SPMV_TMA_STREAM && s->plan.n_interior >= 0, "SpMV plan has no interior / boundary split");
+  const int begin = part == 1 ? 0 : s->plan.n_interior;
+  const int count = part == 1 ? s->plan.n_interior : s->plan.n_blocks - s->plan.n_interior;
+  if (count <= 0) return 0;
+  const int grid = stream_grid(s, count);
+  s->plan.part_begin = begin; s->plan.part_count = count;
+  stream_dispatch(s, grid, d_x, d_y, dot_partial, scal);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  return grid;
+}
+
+// slab b references a column another rank owns
+__global__ void k_slab_is_boundary(const int4* __restrict__ desc, int n_blocks, const int32_t* __restrict__ colind, int n_local,
+                                   int* __restrict__ flag) {
+  const int b = blockIdx.x;
+  if (b >= n_blocks) return;
+  const int4 d = desc[b];
+  int any = 0;
+  for (int e = d.z + threadIdx.x; e < d.w; e += blockDim.x) any |= (colind[e] >= n_local) ? 1 : 0;
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) flag[b] = any;
+}
+
+// reorder the slab descriptors: interior slabs first, boundary slabs last (stable); sets plan.n_interior
+void spmv_split_boundary(tfelcu_solver* s, size_t n_local) {
+  Ctx* ctx = s->ctx;
+  SpmvPlan& P = s->plan;
+  P.n_interior = -1;
+  if (P.kernel != TFELCU_SPMV_TMA_STREAM || P.n_blocks <= 0) return;
+  DevBuf<int> flag((size_t)P.n_blocks);
+  k_slab_is_boundary<<<P.n_blocks, 128, 0, ctx->stream>>>(reinterpret_cast<const int4*>(P.desc.p), P.n_blocks, s->colind, (int)n_local, flag.p);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  std::vector<int> h_flag((size_t)P.n_blocks);
+  std::vector<int32_t> h_desc((size_t)P.n_blocks * 4), out((size_t)P.n_blocks * 4);
+  ctx->download(h_flag.data(), flag.p, h_flag.size());
+  ctx->download(h_desc.data(), P.desc.p, h_desc.size());
+  size_t at = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int b = 0; b < P.n_blocks; ++b)
+      if ((h_flag[b] != 0) == (pass == 1)) { for (int k = 0; k < 4; ++k) out[at * 4 + k] = h_desc[(size_t)b * 4 + k]; ++at; }
+    if (pass == 0) P.n_interior = (int)at;
+  }
+  ctx->upload(P.desc.p, out.data(), out.size());
+  ctx->sync();
 }
 
 static void stream_dispatch(tfelcu_solver* s, int grid, const double* d_x, double* d_y, double* dot_partial,
