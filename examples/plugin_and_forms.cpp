@@ -4,6 +4,7 @@
 // test/quadrature_2d.cpp:10-18) and the error convention (std::string thrown by value).
 #include <tfel/tfel.hpp>
 
+#include <algorithm>
 #include <cassert>
 
 // Jacobi-preconditioned CG written against the plugin interface only
@@ -104,6 +105,19 @@ int main() {
     const double j2(integrate<quad_type>(d<2>(make_expr<p2_type>(w)), m4));
     std::cout << "int 0.5 y^2 = " << j1 << " (1/6), int d_y = " << j2 << " (1/2)" << std::endl;
     if (std::fabs(j1 - 1.0 / 6.0) > 1e-13 or std::fabs(j2 - 0.5) > 1e-13) throw std::string("fe_derivative_form known answer missed");
+
+    // projectors (projector.hpp:12-97, test/l2_projection.cpp): 0.5 y^2 is in P2, so both projections reproduce it
+    {
+      const p2_fes_type::element wl(projector::lagrange<p2_type>(half_y2, fes2));
+      const p2_fes_type::element w2(projector::l2<p2_type, quad_type>(half_y2, fes2));
+      double e1(0.0), e2(0.0);
+      for (std::size_t i(0); i < nd; ++i) {
+        e1 = std::max(e1, std::fabs(wl.get_coefficients().at(i) - coef.at(i)));
+        e2 = std::max(e2, std::fabs(w2.get_coefficients().at(i) - coef.at(i)));
+      }
+      std::cout << "projector::lagrange max diff " << e1 << ", projector::l2 max diff " << e2 << std::endl;
+      if (e1 > 0.0 or e2 > 1e-8) throw std::string("projectors do not reproduce a P2 function");
+    }
 
     // error convention: missing dictionary key -> std::string (solver.hpp:132)
     bool thrown(false);

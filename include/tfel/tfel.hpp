@@ -904,4 +904,55 @@ private:
   tfelcu_matrix* h = nullptr;
 };
 
+// ---- projectors (projector.hpp:12-97): callers on either side of the path (initial conditions, coefficient fields) ------
+namespace projector {
+
+// L2 projection: the mass-matrix solve through the assembly + solve path (projector.hpp:12-46), CG + Jacobi on device
+template <typename fe_type, typename quadrature_type>
+typename finite_element_space<fe_type>::element
+l2(const expression<false>& expr, const finite_element_space<fe_type>& fes) {
+  typedef finite_element_space<fe_type> fes_type;
+  bilinear_form<fes_type, fes_type> a(fes, fes); {
+    auto u(a.get_trial_function());
+    auto v(a.get_test_function());
+    a += integrate<quadrature_type>(u * v, fes.get_mesh());
+  }
+  linear_form<fes_type> f(fes); {
+    auto v(f.get_test_function());
+    f += integrate<quadrature_type>(expr * v, fes.get_mesh());
+  }
+  dictionary p(dictionary()
+               .set("maxits",  2000u)
+               .set("restart", 1000u)
+               .set("rtol",    1.e-8)
+               .set("atol",    1.e-50)
+               .set("dtol",    1.e20)
+               .set("ilufill", 2u));
+  solver::cuda::cg_jacobi s(p);
+  return a.solve(f, s);
+}
+
+template <typename fe_type, typename quadrature_type>
+typename finite_element_space<fe_type>::element
+l2(const std::function<double(const double*)>& fun, const finite_element_space<fe_type>& fes) {
+  return l2<fe_type, quadrature_type>(make_expr(fun), fes);
+}
+
+// nodal interpolation (projector.hpp:48-63): the function at the space coordinate of every dof (fes.hpp:190-202)
+template <typename fe_type>
+typename finite_element_space<fe_type>::element
+lagrange(const std::function<double(const double*)>& fun, const finite_element_space<fe_type>& fes) {
+  const std::size_t n(fes.get_dof_number());
+  const std::size_t dim(fe_type::cell_type::dim);
+  std::vector<unsigned int> dofs(n);
+  for (std::size_t i(0); i < n; ++i) dofs[i] = static_cast<unsigned int>(i);
+  std::vector<double> x(n * dim);
+  tfel_cuda::ck(tfelcu_fes_dof_coordinates(fes.handle(), dofs.data(), n, x.data()));
+  array<double> coefficients{n};
+  for (std::size_t i(0); i < n; ++i) coefficients.at(i) = fun(&x[i * dim]);
+  return typename finite_element_space<fe_type>::element(fes, coefficients);
+}
+
+}  // namespace projector
+
 #endif  // TFEL_TFEL_HPP
