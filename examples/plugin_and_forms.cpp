@@ -116,7 +116,7 @@ int main() {
         e2 = std::max(e2, std::fabs(w2.get_coefficients().at(i) - coef.at(i)));
       }
       std::cout << "projector::lagrange max diff " << e1 << ", projector::l2 max diff " << e2 << std::endl;
-      if (e1 > 0.0 or e2 > 1e-8) throw std::string("projectors do not reproduce a P2 function");
+      if (e1 > 0.0 or e2 > 1e-6) throw std::string("projectors do not reproduce a P2 function");
     }
 
     // error convention: missing dictionary key -> std::string (solver.hpp:132)

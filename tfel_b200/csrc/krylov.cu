@@ -173,19 +173,71 @@ __global__ void k_tri_level(const int32_t* __restrict__ rowptr, const int32_t* _
   if (t < end) tri_row<LOWER>(rowptr, colind, diag, lu, in, out, order[t]);
 }
 
+// Several consecutive small levels in one CTA, software pipelined: the metadata of a thread's row in the NEXT level
+// (meta[t] = row, first entry, end entry, in schedule order) is requested before the current level is computed and its
+// first entries before the barrier, so that after the barrier only the gathers of the solution are on the critical path.
 template <bool LOWER>
 __global__ void __launch_bounds__(1024)
-k_tri_levels_cta(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind, const int32_t* __restrict__ diag,
-                 const double* __restrict__ lu, const int32_t* __restrict__ order, const int32_t* __restrict__ level_ptr,
-                 int l0, int l1, const double* in, double* out,
-                 const KrylovScalars* __restrict__ S) {
+k_tri_levels_cta(const int32_t* __restrict__ colind, const int32_t* __restrict__ diag, const double* __restrict__ lu,
+                 const int4* __restrict__ meta, const int32_t* __restrict__ level_ptr,
+                 int l0, int l1, const double* in, double* out, const KrylovScalars* __restrict__ S) {
   if (S && S->done) return;
+  constexpr int PF = 4;   // entries kept in registers ahead of the barrier
+  int lp_cur = level_ptr[l0], lp_next = level_ptr[l0 + 1];
+  int4 m = make_int4(-1, 0, 0, 0);
+  double acc = 0.0, ud = 1.0;
+  int c[PF]; double v[PF];
+  auto fetch_meta = [&](int first, int end) {
+    const int t = first + (int)threadIdx.x;
+    m = t < end ? __ldg(meta + t) : make_int4(-1, 0, 0, 0);
+  };
+  auto fetch_entries = [&]() {
+    if (m.x < 0) return;
+    acc = in[m.x];
+    if (!LOWER) ud = lu[diag[m.x]];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const bool ok = m.y + u < m.z;
+      c[u] = ok ? __ldg(colind + m.y + u) : -1;
+      v[u] = ok ? lu[m.y + u] : 0.0;
+    }
+  };
+  fetch_meta(lp_cur, lp_next);
+  fetch_entries();
   for (int l = l0; l < l1; ++l) {
-    const int t = level_ptr[l] + threadIdx.x;
-    if (t < level_ptr[l + 1]) tri_row<LOWER>(rowptr, colind, diag, lu, in, out, order[t]);
+    // current level, from registers
+    const int4 cur = m;
+    const double cur_acc = acc, cur_ud = ud;
+    int cc[PF]; double cv[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) { cc[u] = c[u]; cv[u] = v[u]; }
+    // request the metadata of the next level now: it does not depend on the solution
+    const int nf = lp_next;
+    int ne = nf;
+    if (l + 1 < l1) { ne = level_ptr[l + 2]; fetch_meta(nf, ne); }
+    if (cur.x >= 0) {
+      double a = cur_acc;
+      double xv[PF];
+#pragma unroll
+      for (int u = 0; u < PF; ++u) xv[u] = cc[u] >= 0 ? __ldcg(out + cc[u]) : 0.0;
+#pragma unroll
+      for (int u = 0; u < PF; ++u) a -= cv[u] * xv[u];
+      for (int e = cur.y + PF; e < cur.z; ++e) a -= lu[e] * __ldcg(out + colind[e]);
+      out[cur.x] = LOWER ? a : a / cur_ud;
+    }
+    if (l + 1 < l1) fetch_entries();
+    lp_cur = nf; lp_next = ne;
     __threadfence_block();
     __syncthreads();
   }
+}
+
+__global__ void k_sched_meta(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ diag, const int32_t* __restrict__ order,
+                             size_t n, int lower, int4* __restrict__ meta) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int i = order[t];
+  meta[t] = lower ? make_int4(i, rowptr[i], diag[i], 0) : make_int4(i, diag[i] + 1, rowptr[i + 1], 0);
 }
 
 // launch plan of a level schedule: runs of consecutive levels of at most 1024 rows each go to one CTA
@@ -236,6 +288,10 @@ void ilu0_setup(tfelcu_solver* s) {
     if (pass == 0) schedule(ctx, level.p, n, I.order_l, I.level_ptr_l);
     else schedule(ctx, level.p, n, I.order_u, I.level_ptr_u);
   }
+  I.meta_l.alloc(4 * n); I.meta_u.alloc(4 * n);
+  k_sched_meta<<<grid_for(n, 256), 256, 0, ctx->stream>>>(s->rowptr, I.diag.p, I.order_l.p, n, 1, reinterpret_cast<int4*>(I.meta_l.p));
+  k_sched_meta<<<grid_for(n, 256), 256, 0, ctx->stream>>>(s->rowptr, I.diag.p, I.order_u.p, n, 0, reinterpret_cast<int4*>(I.meta_u.p));
+  ctx->count(2); TFELCU_LAUNCH_CHECK();
   I.d_level_ptr_l.alloc(I.level_ptr_l.size());
   I.d_level_ptr_u.alloc(I.level_ptr_u.size());
   ctx->upload(I.d_level_ptr_l.p, I.level_ptr_l.data(), I.level_ptr_l.size());
@@ -268,8 +324,9 @@ static void tri_launches(tfelcu_solver* s, const double* d_in, double* d_out, bo
   if (runs.empty()) runs = plan_runs(lp);
   for (const LevelRun& r : runs) {
     if (r.cta) {
-      if (lower) k_tri_levels_cta<true><<<1, 1024, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, I.lu.p, order, d_lp, r.l0, r.l1, d_in, d_out, S);
-      else k_tri_levels_cta<false><<<1, 1024, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, I.lu.p, order, d_lp, r.l0, r.l1, d_in, d_out, S);
+      const int4* meta = reinterpret_cast<const int4*>(lower ? I.meta_l.p : I.meta_u.p);
+      if (lower) k_tri_levels_cta<true><<<1, 1024, 0, ctx->stream>>>(s->colind, I.diag.p, I.lu.p, meta, d_lp, r.l0, r.l1, d_in, d_out, S);
+      else k_tri_levels_cta<false><<<1, 1024, 0, ctx->stream>>>(s->colind, I.diag.p, I.lu.p, meta, d_lp, r.l0, r.l1, d_in, d_out, S);
     } else {
       const int b = lp[r.l0], e = lp[r.l1];
       const unsigned g = grid_for((size_t)(e - b), 128);
@@ -508,6 +565,7 @@ void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep) {
   GmresDev h;
   std::memset(&h, 0, sizeof(h));
   bool first_cycle = true;
+  const int poll = s->params.check_every > 0 ? s->params.check_every : 8;
   while (true) {
     // v0 = M^-1 (b - A x)
     if (first_cycle) {
@@ -547,9 +605,14 @@ void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep) {
       ctx->count(); TFELCU_LAUNCH_CHECK();
       k_scale_by_norm<<<vg, kVecT, 0, ctx->stream>>>(w, n, Pn, vg, G);   // skipped on device once done
       ctx->count(); TFELCU_LAUNCH_CHECK();
-      ctx->download(&h, G, 1);
-      if (h.done) { ++k; break; }
+      // the stopping test lives on the device (every kernel returns at once when G->done is set): the host only polls
+      // every few Arnoldi steps, so that launches stay queued ahead of the GPU
+      if ((k + 1) % poll == 0 || k + 1 == M) {
+        ctx->download(&h, G, 1);
+        if (h.done) { ++k; break; }
+      }
     }
+    ctx->download(&h, G, 1);
     const int cols = h.k;
     if (cols > 0) {
       k_gmres_backsolve<<<1, 256, 0, ctx->stream>>>(H, g, cols, M, y);

@@ -56,6 +56,7 @@ struct Ilu0 {
   DevBuf<int32_t> order_l, order_u;      // rows grouped by level
   std::vector<int32_t> level_ptr_l, level_ptr_u;
   DevBuf<int32_t> d_level_ptr_l, d_level_ptr_u;
+  DevBuf<int32_t> meta_l, meta_u;        // [n][4] in schedule order: row, first entry, end entry of its L / U part
   std::vector<LevelRun> runs_l, runs_u;
 };
 
