@@ -59,8 +59,8 @@ struct DevBuf {
   void alloc(size_t count) {
     release();
     n = count;
-    // +4 elements of slack: bulk copies in the SpMV kernel read whole 16-byte chunks
-    if (count) TFELCU_CK(cudaMalloc(&p, (count + 4) * sizeof(T)));
+    // +8 elements of slack: bulk copies in the SpMV kernel read whole 16-byte chunks of 2-, 4- and 8-byte entries
+    if (count) TFELCU_CK(cudaMalloc(&p, (count + 8) * sizeof(T)));
   }
   void release() {
     if (p) cudaFree(p);

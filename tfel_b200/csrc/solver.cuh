@@ -43,6 +43,8 @@ struct SpmvPlan {
   int cfg = 0;                           // tile shape (spmv.cu: kCfgs)
   int part_begin = 0, part_count = 0;    // slab range of the launch being issued
   int n_interior = -1;                   // distributed operators: slabs [0, n_interior) reference owned columns only
+  DevBuf<int16_t> delta16;               // column - row of every stored entry, when all fit 16 bits
+  bool use_delta16 = false;
   int tile_nnz = 0, tile_rows = 0;
 };
 

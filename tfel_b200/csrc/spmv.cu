@@ -20,7 +20,7 @@
 
 namespace tfelcu {
 
-constexpr int kTilePad = 8;             // slack for 16-byte aligned bulk copies
+constexpr int kTilePad = 16;            // slack for 16-byte aligned bulk copies (8 entries of 2 bytes on either side)
 
 // ------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D bulk copy global -> shared (SASS: UBLKCP / SYNCS)
@@ -94,6 +94,17 @@ __global__ void k_max_row_len(const int32_t* __restrict__ rowptr, size_t n, int*
   if (r < n) atomicMax(out, rowptr[r + 1] - rowptr[r]);
 }
 
+__global__ void k_col_delta16(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind, size_t n,
+                              int16_t* __restrict__ delta, int* __restrict__ far) {
+  const size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+    const long long d = (long long)colind[e] - (long long)r;
+    if (d < -32767 || d > 32767) { atomicExch(far, 1); delta[e] = 0; }
+    else delta[e] = (int16_t)d;
+  }
+}
+
 // tile shapes of the streamed kernel: (entries, consumer threads, ring stages, CTAs per SM)
 struct StreamCfg { int tile_nnz, consumers, stages, ctas_per_sm; };
 static const StreamCfg kCfgs[] = {
@@ -148,6 +159,19 @@ void spmv_plan(tfelcu_solver* s) {
   k_slab_desc<<<grid_for((size_t)P.n_blocks, 256), 256, 0, ctx->stream>>>(cum.p, s->rowptr, s->n, (unsigned long long)S,
                                                                           P.n_blocks, reinterpret_cast<int4*>(P.desc.p));
   ctx->count(); TFELCU_LAUNCH_CHECK();
+  // 16-bit column offsets when every entry is close enough to the diagonal (finite element matrices in reference
+  // numbering are banded: +-(n + 2) for the P1 square mesh)
+  P.use_delta16 = false;
+  if (!std::getenv("TFELCU_NO_DELTA16") && s->nnz) {
+    DevBuf<int> far(1);
+    ctx->zero(far.p, 1);
+    P.delta16.alloc(s->nnz + 16);
+    k_col_delta16<<<grid_for(s->n, 256), 256, 0, ctx->stream>>>(s->rowptr, s->colind, s->n, P.delta16.p, far.p);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+    int h_far = 0; ctx->download(&h_far, far.p, 1);
+    P.use_delta16 = (h_far == 0);
+    if (!P.use_delta16) P.delta16.release();
+  }
   ctx->sync();
   spmv_configure(s);
 }
@@ -156,10 +180,12 @@ void spmv_plan(tfelcu_solver* s) {
 // TMA-streamed kernel
 // ------------------------------------------------------------------------------------------
 
-template <int TILE_NNZ, int CONSUMERS, int STAGES>
+// COL_T = int32_t: column indices as stored; int16_t: column - row (solver-internal copy, built when every stored
+// entry of the operator lies within +-32767 of the diagonal -- 2 bytes less per entry to stream)
+template <int TILE_NNZ, int CONSUMERS, int STAGES, typename COL_T>
 struct StreamSmem {
   double val[STAGES][TILE_NNZ + kTilePad];
-  int32_t col[STAGES][TILE_NNZ + kTilePad];
+  COL_T col[STAGES][TILE_NNZ + kTilePad];
   int32_t rp[STAGES][CONSUMERS + 12];
   int32_t meta[STAGES][4];   // r0, r1, first copied entry a0, first copied row r0a
   uint64_t full[STAGES];
@@ -167,13 +193,15 @@ struct StreamSmem {
   double red[CONSUMERS / 32];
 };
 
-template <bool DOT, int LANES, int TILE_NNZ, int CONSUMERS, int STAGES, int CTAS>
+template <bool DOT, int LANES, int TILE_NNZ, int CONSUMERS, int STAGES, int CTAS, typename COL_T>
 __global__ void __launch_bounds__(CONSUMERS + 32, CTAS)
-k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind, const double* __restrict__ val,
+k_spmv_stream(const int32_t* __restrict__ rowptr, const COL_T* __restrict__ colind, const double* __restrict__ val,
               const int4* __restrict__ desc, int n_blocks, const double* __restrict__ x,
               double* __restrict__ y, double* __restrict__ dot_partial, const KrylovScalars* __restrict__ scal) {
   extern __shared__ __align__(128) unsigned char raw[];
-  using Smem = StreamSmem<TILE_NNZ, CONSUMERS, STAGES>;
+  using Smem = StreamSmem<TILE_NNZ, CONSUMERS, STAGES, COL_T>;
+  constexpr bool kDelta = sizeof(COL_T) == 2;
+  constexpr int kAlign = kDelta ? 8 : 4;   // entries per 16 bytes of the column stream
   Smem& S = *reinterpret_cast<Smem*>(raw);
   if (scal && scal->done) {
     if (DOT && threadIdx.x == 0) dot_partial[blockIdx.x] = 0.0;
@@ -198,16 +226,16 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
         if (b + step < n_blocks) d = __ldg(desc + b + step);
         if (it >= STAGES) mbar_wait(&S.empty[stage], (uint32_t)(it / STAGES - 1) & 1u);
         const int r0 = cur.x, r1 = cur.y, e0 = cur.z, e1 = cur.w;
-        const int a0 = e0 & ~3, a1 = (e1 + 3) & ~3;
+        const int a0 = e0 & ~(kAlign - 1), a1 = (e1 + kAlign - 1) & ~(kAlign - 1);
         const int cnt = a1 - a0;
         const int r0a = r0 & ~3;
         const int rcnt = ((r1 + 1 + 3) & ~3) - r0a;
         int32_t* m = S.meta[stage];
         m[0] = r0; m[1] = r1; m[2] = a0; m[3] = r0a;
-        mbar_expect_tx(&S.full[stage], (uint32_t)cnt * 12u + (uint32_t)rcnt * 4u);
+        mbar_expect_tx(&S.full[stage], (uint32_t)cnt * (8u + (uint32_t)sizeof(COL_T)) + (uint32_t)rcnt * 4u);
         if (cnt > 0) {
           bulk_g2s(S.val[stage], val + a0, (uint32_t)cnt * 8u, &S.full[stage]);
-          bulk_g2s(S.col[stage], colind + a0, (uint32_t)cnt * 4u, &S.full[stage]);
+          bulk_g2s(S.col[stage], colind + a0, (uint32_t)cnt * (uint32_t)sizeof(COL_T), &S.full[stage]);
         }
         bulk_g2s(S.rp[stage], rowptr + r0a, (uint32_t)rcnt * 4u, &S.full[stage]);
       }
@@ -225,7 +253,7 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
     const int32_t* m = S.meta[stage];
     const int r0 = m[0], r1 = m[1], a0 = m[2], r0a = m[3];
     const double* vs = S.val[stage];
-    const int32_t* cs = S.col[stage];
+    const COL_T* cs = S.col[stage];
     const int32_t* rp = S.rp[stage];
     const int r = r0 + row_in_slab;
     const bool has = r < r1;
@@ -239,7 +267,7 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
         for (int u = 0; u < U; ++u) {
           const int eu = e + u * LANES;
           const bool ok = eu < re;
-          c[u] = ok ? cs[eu] : -1;
+          c[u] = ok ? (kDelta ? r + (int)cs[eu] : (int)cs[eu]) : -1;
           v[u] = ok ? vs[eu] : 0.0;
         }
 #pragma unroll
@@ -324,18 +352,32 @@ int spmv_partial_count(tfelcu_solver* s) {
 }
 
 // grid < 0: only opt the kernel in to its dynamic shared memory size (done at plan time, outside any graph capture)
-template <bool DOT, int LANES, int TILE_NNZ, int CONSUMERS, int STAGES, int CTAS>
-static void launch_stream(tfelcu_solver* s, int grid, const double* d_x, double* d_y, double* dot_partial,
-                          const KrylovScalars* scal) {
-  auto kern = k_spmv_stream<DOT, LANES, TILE_NNZ, CONSUMERS, STAGES, CTAS>;
-  const size_t smem = sizeof(StreamSmem<TILE_NNZ, CONSUMERS, STAGES>);
+template <bool DOT, int LANES, int TILE_NNZ, int CONSUMERS, int STAGES, int CTAS, typename COL_T>
+static void launch_stream_t(tfelcu_solver* s, int grid, const COL_T* col, const double* d_x, double* d_y, double* dot_partial,
+                            const KrylovScalars* scal) {
+  auto kern = k_spmv_stream<DOT, LANES, TILE_NNZ, CONSUMERS, STAGES, CTAS, COL_T>;
+  const size_t smem = sizeof(StreamSmem<TILE_NNZ, CONSUMERS, STAGES, COL_T>);
   if (grid < 0) {
     TFELCU_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return;
   }
-  kern<<<grid, CONSUMERS + 32, smem, s->ctx->stream>>>(s->rowptr, s->colind, s->val,
+  kern<<<grid, CONSUMERS + 32, smem, s->ctx->stream>>>(s->rowptr, col, s->val,
                                                       reinterpret_cast<const int4*>(s->plan.desc.p) + s->plan.part_begin,
                                                       s->plan.part_count, d_x, d_y, dot_partial, scal);
+}
+
+template <bool DOT, int LANES, int TILE_NNZ, int CONSUMERS, int STAGES, int CTAS>
+static void launch_stream(tfelcu_solver* s, int grid, const double* d_x, double* d_y, double* dot_partial,
+                          const KrylovScalars* scal) {
+  if (grid < 0) {   // configure both column formats
+    launch_stream_t<DOT, LANES, TILE_NNZ, CONSUMERS, STAGES, CTAS, int32_t>(s, grid, nullptr, d_x, d_y, dot_partial, scal);
+    launch_stream_t<DOT, LANES, TILE_NNZ, CONSUMERS, STAGES, CTAS, int16_t>(s, grid, nullptr, d_x, d_y, dot_partial, scal);
+    return;
+  }
+  if (s->plan.use_delta16)
+    launch_stream_t<DOT, LANES, TILE_NNZ, CONSUMERS, STAGES, CTAS, int16_t>(s, grid, s->plan.delta16.p, d_x, d_y, dot_partial, scal);
+  else
+    launch_stream_t<DOT, LANES, TILE_NNZ, CONSUMERS, STAGES, CTAS, int32_t>(s, grid, s->colind, d_x, d_y, dot_partial, scal);
 }
 
 template <int TILE_NNZ, int CONSUMERS, int STAGES, int CTAS>
