@@ -683,7 +683,7 @@ public:
       }
     }
     for (const monomial& m : e.terms) {
-      if (m.c == 0.0 && false) continue;   // zero terms still touch the pattern in the reference: keep them
+      // terms with a zero constant are kept: the reference adds their (zero) contributions too
       if (m.factors.size() > 5) throw std::string("integrand: more than 5 coefficient factors in one product");
       tfelcu_term t;
       t.test_comp = m.test_comp; t.test_d = m.test_d; t.trial_comp = m.trial_comp; t.trial_d = m.trial_d;

@@ -17,8 +17,15 @@ def build():
 
 def test_reference_programs_compile_against_the_cuda_headers():
     build()
-    for name in ("poisson", "stokes_2d_p2_p1", "plugin_and_forms"):
+    for name in ("poisson", "stokes_2d_p2_p1", "navier_stokes_2d_p2_p1", "plugin_and_forms", "expression_algebra"):
         assert os.path.exists(os.path.join(BIN, name))
+
+
+def test_expression_algebra_matches_reference_assertions():
+    """test/expression.cpp:20-50 of the reference (the only assertions in its test tree) on the host-side lowering."""
+    build()
+    r = subprocess.run([os.path.join(BIN, "expression_algebra")], capture_output=True, text=True)
+    assert r.returncode == 0 and "expression_algebra: ok" in r.stdout, r.stdout + r.stderr
 
 
 def test_no_device_is_an_error_not_a_fallback():
