@@ -10,6 +10,9 @@
 #include "solver.cuh"
 #include "sortutil.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace tfelcu {
 
 constexpr int kVecT = 256;
@@ -173,63 +176,83 @@ __global__ void k_tri_level(const int32_t* __restrict__ rowptr, const int32_t* _
   if (t < end) tri_row<LOWER>(rowptr, colind, diag, lu, in, out, order[t]);
 }
 
-// Several consecutive small levels in one CTA, software pipelined: the metadata of a thread's row in the NEXT level
-// (meta[t] = row, first entry, end entry, in schedule order) is requested before the current level is computed and its
-// first entries before the barrier, so that after the barrier only the gathers of the solution are on the critical path.
+// Several consecutive small levels in one CTA. A row is shared by `lpr` lanes (its entries strided over them, partial
+// sums combined with shuffles): a level then costs a few dependent loads instead of one per entry of its longest row.
+// The values of the rows computed inside the run live in SHARED memory (indexed by schedule position), rows computed
+// by earlier launches are read from global memory. Metadata and the first entries of a lane in the next level (row,
+// columns, factors, schedule positions of the columns: nothing that depends on the solution) are requested one level
+// ahead of the barrier.
 template <bool LOWER>
 __global__ void __launch_bounds__(1024)
 k_tri_levels_cta(const int32_t* __restrict__ colind, const int32_t* __restrict__ diag, const double* __restrict__ lu,
-                 const int4* __restrict__ meta, const int32_t* __restrict__ level_ptr,
-                 int l0, int l1, const double* in, double* out, const KrylovScalars* __restrict__ S) {
+                 const int4* __restrict__ meta, const int32_t* __restrict__ sched_pos, const int32_t* __restrict__ level_ptr,
+                 int l0, int l1, int lpr, const double* in, double* out, const KrylovScalars* __restrict__ S) {
+  extern __shared__ double xs[];   // [rows of the run]
   if (S && S->done) return;
-  constexpr int PF = 4;   // entries kept in registers ahead of the barrier
-  int lp_cur = level_ptr[l0], lp_next = level_ptr[l0 + 1];
+  constexpr int PF = 2;            // entries per lane kept in registers ahead of the barrier
+  const int slot = (int)threadIdx.x / lpr, lane = (int)threadIdx.x % lpr;
+  const int base = level_ptr[l0], run_rows = level_ptr[l1] - base;
+  int lp_next = level_ptr[l0 + 1];
   int4 m = make_int4(-1, 0, 0, 0);
+  int t_cur = -1;
   double acc = 0.0, ud = 1.0;
-  int c[PF]; double v[PF];
+  int c[PF], ps[PF]; double v[PF];
   auto fetch_meta = [&](int first, int end) {
-    const int t = first + (int)threadIdx.x;
+    const int t = first + slot;
+    t_cur = t;
     m = t < end ? __ldg(meta + t) : make_int4(-1, 0, 0, 0);
   };
   auto fetch_entries = [&]() {
+#pragma unroll
+    for (int u = 0; u < PF; ++u) { c[u] = -1; v[u] = 0.0; ps[u] = -1; }
     if (m.x < 0) return;
-    acc = in[m.x];
-    if (!LOWER) ud = lu[diag[m.x]];
+    if (lane == 0) { acc = in[m.x]; if (!LOWER) ud = lu[diag[m.x]]; }
 #pragma unroll
     for (int u = 0; u < PF; ++u) {
-      const bool ok = m.y + u < m.z;
-      c[u] = ok ? __ldg(colind + m.y + u) : -1;
-      v[u] = ok ? lu[m.y + u] : 0.0;
+      const int e = m.y + lane + u * lpr;
+      if (e < m.z) { c[u] = __ldg(colind + e); v[u] = lu[e]; ps[u] = __ldg(sched_pos + c[u]) - base; }
     }
   };
-  fetch_meta(lp_cur, lp_next);
+  auto value_of = [&](int col, int p) -> double {   // shared memory when the column's row is computed in this run
+    return (p >= 0 && p < run_rows) ? xs[p] : out[col];
+  };
+  fetch_meta(base, lp_next);
   fetch_entries();
   for (int l = l0; l < l1; ++l) {
-    // current level, from registers
     const int4 cur = m;
+    const int cur_t = t_cur;
     const double cur_acc = acc, cur_ud = ud;
-    int cc[PF]; double cv[PF];
+    int cc[PF], cp[PF]; double cv[PF];
 #pragma unroll
-    for (int u = 0; u < PF; ++u) { cc[u] = c[u]; cv[u] = v[u]; }
-    // request the metadata of the next level now: it does not depend on the solution
+    for (int u = 0; u < PF; ++u) { cc[u] = c[u]; cv[u] = v[u]; cp[u] = ps[u]; }
     const int nf = lp_next;
     int ne = nf;
     if (l + 1 < l1) { ne = level_ptr[l + 2]; fetch_meta(nf, ne); }
+    double part = 0.0;
     if (cur.x >= 0) {
-      double a = cur_acc;
-      double xv[PF];
 #pragma unroll
-      for (int u = 0; u < PF; ++u) xv[u] = cc[u] >= 0 ? __ldcg(out + cc[u]) : 0.0;
-#pragma unroll
-      for (int u = 0; u < PF; ++u) a -= cv[u] * xv[u];
-      for (int e = cur.y + PF; e < cur.z; ++e) a -= lu[e] * __ldcg(out + colind[e]);
-      out[cur.x] = LOWER ? a : a / cur_ud;
+      for (int u = 0; u < PF; ++u) if (cc[u] >= 0) part += cv[u] * value_of(cc[u], cp[u]);
+      for (int e = cur.y + lane + PF * lpr; e < cur.z; e += lpr) {
+        const int col = colind[e];
+        part += lu[e] * value_of(col, sched_pos[col] - base);
+      }
+    }
+    for (int o = lpr >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (cur.x >= 0 && lane == 0) {
+      const double a = cur_acc - part;
+      const double r = LOWER ? a : a / cur_ud;
+      xs[cur_t - base] = r;
+      out[cur.x] = r;
     }
     if (l + 1 < l1) fetch_entries();
-    lp_cur = nf; lp_next = ne;
-    __threadfence_block();
+    lp_next = ne;
     __syncthreads();
   }
+}
+
+__global__ void k_sched_pos(const int32_t* __restrict__ order, size_t n, int32_t* __restrict__ pos) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t < n) pos[order[t]] = (int32_t)t;
 }
 
 __global__ void k_sched_meta(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ diag, const int32_t* __restrict__ order,
@@ -242,15 +265,19 @@ __global__ void k_sched_meta(const int32_t* __restrict__ rowptr, const int32_t* 
 
 // launch plan of a level schedule: runs of consecutive levels of at most 1024 rows each go to one CTA
 
+constexpr int kRunRows = 24 * 1024;   // 192 KB of shared memory
+constexpr int kRunLevelRows = 256;    // levels up to this many rows are walked inside one CTA (>= 4 lanes per row)
+
 static std::vector<LevelRun> plan_runs(const std::vector<int32_t>& level_ptr) {
   std::vector<LevelRun> runs;
   const int nl = (int)level_ptr.size() - 1;
   int l = 0;
   while (l < nl) {
     const int sz = level_ptr[l + 1] - level_ptr[l];
-    if (sz <= 1024) {
+    if (sz <= kRunLevelRows) {
       int e = l + 1;
-      while (e < nl && level_ptr[e + 1] - level_ptr[e] <= 1024) ++e;
+      // the rows of a run live in the shared memory of its CTA: at most kRunRows of them
+      while (e < nl && level_ptr[e + 1] - level_ptr[e] <= kRunLevelRows && level_ptr[e + 1] - level_ptr[l] <= kRunRows) ++e;
       runs.push_back({l, e, true});
       l = e;
     } else {
@@ -289,9 +316,20 @@ void ilu0_setup(tfelcu_solver* s) {
     else schedule(ctx, level.p, n, I.order_u, I.level_ptr_u);
   }
   I.meta_l.alloc(4 * n); I.meta_u.alloc(4 * n);
+  I.pos_l.alloc(n); I.pos_u.alloc(n);
+  k_sched_pos<<<grid_for(n, 256), 256, 0, ctx->stream>>>(I.order_l.p, n, I.pos_l.p);
+  k_sched_pos<<<grid_for(n, 256), 256, 0, ctx->stream>>>(I.order_u.p, n, I.pos_u.p);
+  ctx->count(2);
+  TFELCU_CK(cudaFuncSetAttribute(k_tri_levels_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRunRows * (int)sizeof(double)));
+  TFELCU_CK(cudaFuncSetAttribute(k_tri_levels_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRunRows * (int)sizeof(double)));
   k_sched_meta<<<grid_for(n, 256), 256, 0, ctx->stream>>>(s->rowptr, I.diag.p, I.order_l.p, n, 1, reinterpret_cast<int4*>(I.meta_l.p));
   k_sched_meta<<<grid_for(n, 256), 256, 0, ctx->stream>>>(s->rowptr, I.diag.p, I.order_u.p, n, 0, reinterpret_cast<int4*>(I.meta_u.p));
   ctx->count(2); TFELCU_LAUNCH_CHECK();
+  if (std::getenv("TFELCU_TRACE")) {
+    const auto rl = plan_runs(I.level_ptr_l), ru = plan_runs(I.level_ptr_u);
+    std::fprintf(stderr, "[tfelcu trace] ILU(0): n %zu nnz %zu, L levels %zu (runs %zu), U levels %zu (runs %zu)\n", n, s->nnz,
+                 I.level_ptr_l.size() - 1, rl.size(), I.level_ptr_u.size() - 1, ru.size());
+  }
   I.d_level_ptr_l.alloc(I.level_ptr_l.size());
   I.d_level_ptr_u.alloc(I.level_ptr_u.size());
   ctx->upload(I.d_level_ptr_l.p, I.level_ptr_l.data(), I.level_ptr_l.size());
@@ -325,8 +363,16 @@ static void tri_launches(tfelcu_solver* s, const double* d_in, double* d_out, bo
   for (const LevelRun& r : runs) {
     if (r.cta) {
       const int4* meta = reinterpret_cast<const int4*>(lower ? I.meta_l.p : I.meta_u.p);
-      if (lower) k_tri_levels_cta<true><<<1, 1024, 0, ctx->stream>>>(s->colind, I.diag.p, I.lu.p, meta, d_lp, r.l0, r.l1, d_in, d_out, S);
-      else k_tri_levels_cta<false><<<1, 1024, 0, ctx->stream>>>(s->colind, I.diag.p, I.lu.p, meta, d_lp, r.l0, r.l1, d_in, d_out, S);
+      const int32_t* pos = lower ? I.pos_l.p : I.pos_u.p;
+      const size_t smem = (size_t)(lp[r.l1] - lp[r.l0]) * sizeof(double);
+      int widest = 1;
+      for (int l = r.l0; l < r.l1; ++l) widest = std::max(widest, lp[l + 1] - lp[l]);
+      int lpr = 16;                                  // lanes per row: as many as 1024 threads allow, at most 16
+      while (lpr > 1 && widest * lpr > 1024) lpr >>= 1;
+      int threads = ((widest * lpr + 31) / 32) * 32;
+      if (threads < 32) threads = 32;
+      if (lower) k_tri_levels_cta<true><<<1, threads, smem, ctx->stream>>>(s->colind, I.diag.p, I.lu.p, meta, pos, d_lp, r.l0, r.l1, lpr, d_in, d_out, S);
+      else k_tri_levels_cta<false><<<1, threads, smem, ctx->stream>>>(s->colind, I.diag.p, I.lu.p, meta, pos, d_lp, r.l0, r.l1, lpr, d_in, d_out, S);
     } else {
       const int b = lp[r.l0], e = lp[r.l1];
       const unsigned g = grid_for((size_t)(e - b), 128);

@@ -113,15 +113,26 @@ k_cg_start(const double* __restrict__ r, const double* __restrict__ dinv, const 
   if (threadIdx.x == 0) { partial_rz[blockIdx.x] = t0; partial_rr[blockIdx.x] = t1; }
 }
 
+// one warp: global sums of b.b, r.z, r.r from their per-CTA partials, tolerances and the initial stopping test
 __global__ void k_cg_set_scalars(const double* __restrict__ partial_bb, const double* __restrict__ partial_rz,
                                  const double* __restrict__ partial_rr, int n_partial, double rtol, double atol,
                                  double dtol, KrylovScalars* __restrict__ S) {
-  if (threadIdx.x || blockIdx.x) return;
-  const double bb = sum_partials(partial_bb, n_partial);
+  if (blockIdx.x || threadIdx.x >= 32) return;
+  const double* p[3] = {partial_bb, partial_rz, partial_rr};
+  double v[3];
+  for (int k = 0; k < 3; ++k) {
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n_partial; i += 32) t += p[k][i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    v[k] = t;
+  }
+  if (threadIdx.x) return;
+  const double bb = v[0];
   const double target = fmax(rtol * sqrt(bb), atol);
   S->bnorm2 = bb; S->target2 = target * target; S->dtol2 = dtol * dtol * bb;
-  S->rz = sum_partials(partial_rz, n_partial);
-  S->rr = sum_partials(partial_rr, n_partial);
+  S->rz = v[1];
+  S->rr = v[2];
   S->its = 0;
   S->done = (S->rr <= S->target2) ? 1 : 0;
 }

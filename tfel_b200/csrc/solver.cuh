@@ -59,6 +59,7 @@ struct Ilu0 {
   std::vector<int32_t> level_ptr_l, level_ptr_u;
   DevBuf<int32_t> d_level_ptr_l, d_level_ptr_u;
   DevBuf<int32_t> meta_l, meta_u;        // [n][4] in schedule order: row, first entry, end entry of its L / U part
+  DevBuf<int32_t> pos_l, pos_u;          // [n]: schedule position of every row
   std::vector<LevelRun> runs_l, runs_u;
 };
 
