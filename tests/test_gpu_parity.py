@@ -371,3 +371,60 @@ def test_quadrature_points_and_kind_offsets(ctx):
     # the order of the points inside a symmetry orbit is ours: compare per cell as sets
     assert np.abs(np.sort(a.reshape(a.shape[0], -1), axis=1) - np.sort(b.reshape(b.shape[0], -1), axis=1)).max() <= 1e-15
     m.close()
+
+
+def test_mesh_with_unused_vertices_and_unsorted_cells(ctx):
+    """Edge cases of the mesh / space constructors: vertices no cell uses are skipped by the numbering
+    (get_vertex_list, cell.hpp:393-405: dofs are ranks among the USED vertices); cells whose first nv - 1 ids are not
+    ascending are sorted like mesh.hpp:294-298 does; a cell that is still not ascending is refused
+    (subdomain.hpp:11-13)."""
+    from tfel_b200 import capi
+    v, c = orc.gen_square_mesh(1.0, 1.0, 5, 5)
+    keep = np.ones(c.shape[0], dtype=bool)
+    keep[[0, 1, 2, 3, 10, 11]] = False          # vertex 0 (and 1) lose all / some of their cells
+    c2 = np.ascontiguousarray(c[keep])
+    for fe_name, fe in (("p1", orc.FE_P1), ("p2", orc.FE_P2), ("p1b", orc.FE_P1_BUBBLE)):
+        m = capi.Mesh.create(ctx, v, c2)
+        sp = capi.Space(m, fe_name)
+        dof_map, N, g2l = orc.fes_build(2, fe, c2)
+        assert sp.n_dof == N
+        assert_int_equal(sp.dof_map(), dof_map, fe_name)
+        assert_int_equal(sp.g2l(), g2l, fe_name)
+        bel, bid, bsd = orc.boundary_submesh(2, c2)
+        gel, gid, gsd = m.boundary()
+        assert_int_equal(gel, bel); assert_int_equal(gid, bid); assert_int_equal(gsd, bsd)
+        assert_int_equal(sp.boundary_dofs(), orc.dirichlet_dofs(2, fe, c2, bel))
+        sp.close(); m.close()
+    # first two ids swapped: sorted like the reference; result equals the sorted mesh
+    c3 = c.copy(); c3[7, [0, 1]] = c3[7, [1, 0]]
+    m = capi.Mesh.create(ctx, v, c3)
+    assert np.array_equal(m.download()[1], c)
+    m.close()
+    # last id out of order: the reference only sorts the first nv - 1 ids and then throws
+    c4 = c.copy(); c4[7, [1, 2]] = c4[7, [2, 1]]
+    with pytest.raises(capi.TfelCudaError, match="ordered"):
+        capi.Mesh.create(ctx, v, c4)
+
+
+def test_empty_and_tiny_inputs(ctx):
+    """One-cell meshes, a form with no terms, an integrand that is identically zero, a system of Dirichlet rows only."""
+    from tfel_b200 import capi
+    v = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]]); c = np.array([[0, 1, 2]], dtype=np.uint32)
+    m = capi.Mesh.create(ctx, v, c)
+    sp = capi.Space(m, "p2")
+    assert sp.n_dof == 6
+    sp.add_dirichlet_boundary(1.5)                     # every dof of a single triangle is on the boundary
+    a = capi.Matrix(sp); b = capi.Vector(sp)
+    a.assemble("qf5pT", [dict(test=(0, 1), trial=(0, 1))])
+    a.assemble("qf5pT", [])                            # no terms: nothing happens
+    b.assemble("qf5pT", [dict(test=(0, 0), c=0.0)])
+    rp, ci, val = a.csr()
+    assert np.array_equal(rp, np.arange(7)) and np.array_equal(ci, np.arange(6)) and np.all(val == 1.0)
+    s = capi.Solver(ctx, method="cg", precond="jacobi")
+    x, rep = a.solve(b, s)
+    assert rep["converged"] == 1 and rep["its"] == 0 and np.all(x == 1.5)
+    s2 = capi.Solver(ctx, method="gmres", precond="ilu0", restart=5, maxits=10)
+    x, rep = a.solve(b, s2)
+    assert rep["converged"] == 1 and np.allclose(x, 1.5)
+    assert capi.integrate(m, "qf5pT", [dict(c=2.0)]) == pytest.approx(1.0)   # 2 |K| = 1
+    s.close(); s2.close(); a.close(); b.close(); sp.close(); m.close()
