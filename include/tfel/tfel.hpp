@@ -433,6 +433,8 @@ namespace tfel_cuda {
 struct factor_desc {
   int kind = 0;                                      // TFELCU_FACTOR_* ; 0 = host callback to be tabulated
   int d = 0;
+  std::shared_ptr<void> device_table;                // TABLE: double[K][nq] on the device (tfel_device.cuh functors)
+  int table_quad = 0;                                // TABLE: quadrature formula the table was evaluated for
   const tfelcu_fes* fes = nullptr;                   // FIELD
   std::shared_ptr<std::vector<double>> data;         // FIELD coefficients
   std::function<double(const double*)> fn;           // host callback (free_function / std_function)
@@ -650,6 +652,7 @@ public:
         const factor_desc& g(e.factors[kept[k]]);
         bool same(f.kind == g.kind and f.d == g.d);
         if (same and f.kind == TFELCU_FACTOR_FIELD) same = f.fes == g.fes and f.data.get() == g.data.get();
+        else if (same and f.kind == TFELCU_FACTOR_TABLE) same = f.device_table.get() == g.device_table.get();
         else if (same and f.kind == TFELCU_FACTOR_PROGRAM) {
           same = f.prog.size() == g.prog.size();
           for (std::size_t t(0); same and t < f.prog.size(); ++t) same = f.prog[t].op == g.prog[t].op and f.prog[t].imm == g.prog[t].imm;
@@ -669,6 +672,10 @@ public:
       o.kind = f.kind; o.d = f.d; o.fes = f.fes; o.data = nullptr; o.ops = nullptr; o.n_ops = 0; o.pad = 0;
       if (f.kind == TFELCU_FACTOR_FIELD) o.data = f.data->data();
       else if (f.kind == TFELCU_FACTOR_PROGRAM) { o.ops = f.prog.data(); o.n_ops = static_cast<int>(f.prog.size()); }
+      else if (f.kind == TFELCU_FACTOR_TABLE) {   // evaluated on the device by a user functor (tfel_device.cuh)
+        if (f.table_quad != quad_id) throw std::string("integrate: a device function was tabulated for another quadrature formula");
+        o.data = static_cast<const double*>(f.device_table.get());
+      }
       else {   // free_function (expression.hpp:31-58): f(x_q) for every cell and quadrature point
         if (xq.empty()) {
           ck(tfelcu_quadrature_size(quad_id, &nq, &dim));

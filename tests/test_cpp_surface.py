@@ -17,7 +17,7 @@ def build():
 
 def test_reference_programs_compile_against_the_cuda_headers():
     build()
-    for name in ("poisson", "stokes_2d_p2_p1", "navier_stokes_2d_p2_p1", "plugin_and_forms", "expression_algebra"):
+    for name in ("poisson", "stokes_2d_p2_p1", "navier_stokes_2d_p2_p1", "plugin_and_forms", "expression_algebra", "device_functor"):
         assert os.path.exists(os.path.join(BIN, name))
 
 
@@ -95,3 +95,13 @@ def test_reference_navier_stokes_program():
     last = [float(line.split("(")[1].split(",")[0]) for line in steps]
     assert min(last) < 1e-8
     assert "summary:" in r.stdout
+
+
+@pytest.mark.gpu
+def test_device_functor_coefficients():
+    """include/tfel/tfel_device.cuh: coefficient functions as __device__ functors instantiated in the user's own
+    (nvcc-compiled) translation unit give the same system as the host-callback path."""
+    build()
+    r = subprocess.run([os.path.join(BIN, "device_functor"), "40"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "device_functor: ok" in r.stdout
