@@ -82,7 +82,12 @@ typedef struct {
 
 enum { TFELCU_METHOD_CG = 1, TFELCU_METHOD_GMRES = 2 };
 enum { TFELCU_PC_NONE = 0, TFELCU_PC_JACOBI = 1, TFELCU_PC_BLOCK_JACOBI = 2, TFELCU_PC_ILU0 = 3 };
-enum { TFELCU_SCATTER_ROW_GATHER = 0, TFELCU_SCATTER_COLORED = 1 };
+/* Scatter strategies of the assembly, all free of atomics and bitwise reproducible. ROW_GATHER: one thread per row
+ * recomputes its row of every incident element matrix. COLORED: one launch per colour of the cell conflict graph.
+ * PATCH: rows grouped into compact patches of the mesh (quadtree / octree leaves of the dof coordinates); one CTA
+ * computes every element matrix of its patch once in shared memory, then each row gathers. AUTO (default): the
+ * measured winner, today ROW_GATHER; TFELCU_SCATTER=rows|patch|colored in the environment overrides AUTO. */
+enum { TFELCU_SCATTER_ROW_GATHER = 0, TFELCU_SCATTER_COLORED = 1, TFELCU_SCATTER_PATCH = 2, TFELCU_SCATTER_AUTO = 3 };
 enum { TFELCU_SPMV_AUTO = 0, TFELCU_SPMV_VECTOR = 1, TFELCU_SPMV_TMA_STREAM = 2 };
 
 /* same keys as the dictionary solver::petsc::gmres_ilu requires (solver.hpp:125-133) */
@@ -213,6 +218,8 @@ int tfelcu_vector_clear(tfelcu_vector* v);
 int tfelcu_vector_size(const tfelcu_vector* v, size_t* n);
 int tfelcu_vector_assemble(tfelcu_vector* v, int quad, const tfelcu_factor* factors, int n_factors,
                            const tfelcu_term* terms, int n_terms);
+/* TFELCU_SCATTER_ROW_GATHER, _PATCH or _AUTO (default) for the += of a linear form */
+int tfelcu_vector_set_scatter(tfelcu_vector* v, int scatter);
 int tfelcu_vector_download(const tfelcu_vector* v, double* host);
 int tfelcu_vector_upload(tfelcu_vector* v, const double* host);
 double* tfelcu_vector_device_ptr(tfelcu_vector* v);

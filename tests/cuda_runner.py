@@ -39,7 +39,7 @@ def build(ctx, problem, scatter=None, generator="device"):
     for name, (c, fn) in problem.fields.items():
         B.fields[name] = (B.spaces[c], fn(B.spaces[c].dof_coordinates()))
     B.matrix = capi.Matrix(B.spaces, B.spaces, scatter=scatter)
-    B.vector = capi.Vector(B.spaces)
+    B.vector = capi.Vector(B.spaces, scatter=scatter)
     return B
 
 

@@ -38,7 +38,7 @@ def compare(got, ref, rowptr_key="csr_rowptr"):
             assert_values_close(got[key], r, 1e-12, key)
 
 
-@pytest.mark.parametrize("scatter", ["rows", "colored"])
+@pytest.mark.parametrize("scatter", ["rows", "colored", "patch"])
 @pytest.mark.parametrize("problem", problems.GOLDEN_CASES, ids=lambda p: p.golden)
 def test_cuda_matches_reference_fixture(ctx, problem, scatter, golden_dir):
     gold = dict(np.load(os.path.join(golden_dir, problem.golden + ".npz")))
@@ -60,6 +60,30 @@ def test_cuda_matches_oracle(ctx, problem):
         compare(got, ref)
     finally:
         cuda_runner.close(got["_built"])
+
+
+@pytest.mark.parametrize("problem", [problems.poisson("p1", 57), problems.poisson("p1", 130), problems.poisson("p2", 23),
+                                     problems.poissong("p2", 19), problems.tet("p1", 7), problems.tet("p1b", 5),
+                                     problems.tet("p2", 5), problems.stokes(13), problems.navier_stokes(9),
+                                     problems.laplace2(11)],
+                         ids=lambda p: "%s_n%d" % (p.name, p.mesh[1]))
+def test_patch_strategy_matches_oracle_and_rows(ctx, problem):
+    """TFELCU_SCATTER_PATCH (rows grouped into quadtree / octree leaves, element matrices once per patch in shared
+    memory) on every element and form kind, composite forms included: against the oracle to 1e-12, and against the
+    owner-computes rows -- same cells per row in the same order, so equal to the last bits."""
+    ref = oracle_runner.run(problem)
+    got = cuda_runner.run(ctx, problem, scatter="patch")
+    rows = cuda_runner.run(ctx, problem, scatter="rows")
+    try:
+        compare(got, ref)
+        scale = np.abs(rows["csr_val"]).max()
+        assert np.abs(got["csr_val"] - rows["csr_val"]).max() <= 1e-14 * scale
+        assert np.abs(got["linear_form"] - rows["linear_form"]).max() <= 1e-14 * max(np.abs(rows["linear_form"]).max(), 1e-300)
+        again = cuda_runner.run(ctx, problem, scatter="patch")
+        assert np.array_equal(again["csr_val"], got["csr_val"]) and np.array_equal(again["linear_form"], got["linear_form"])
+        cuda_runner.close(again["_built"])
+    finally:
+        cuda_runner.close(got["_built"]); cuda_runner.close(rows["_built"])
 
 
 def test_host_mesh_upload_equals_device_generator(ctx):
@@ -88,10 +112,11 @@ def test_assembly_is_bitwise_reproducible(ctx):
     assert np.abs(runs[0] - runs[2]).max() <= 1e-13 * np.abs(runs[0]).max()
 
 
-def test_accumulate_twice_and_clear(ctx):
+@pytest.mark.parametrize("scatter", [None, "rows", "patch"])
+def test_accumulate_twice_and_clear(ctx, scatter):
     """a += x; a += x doubles the entries but keeps identity rows; clear() restores them."""
     p = problems.poisson("p1", 12)
-    B = cuda_runner.build(ctx, p)
+    B = cuda_runner.build(ctx, p, scatter=scatter)
     try:
         cuda_runner.assemble(B)
         _, _, v1 = B.matrix.csr()

@@ -20,7 +20,7 @@ QUAD = {"qf1pT": 1, "qf2pT": 2, "qf5pT": 3, "qf1pTlump": 4,
 FACTOR_FIELD, FACTOR_TABLE, FACTOR_PROGRAM = 1, 2, 3
 METHOD = {"cg": 1, "gmres": 2}
 PRECOND = {"none": 0, "jacobi": 1, "block_jacobi": 2, "ilu0": 3}
-SCATTER = {"rows": 0, "colored": 1}
+SCATTER = {"rows": 0, "colored": 1, "patch": 2, "auto": 3}
 SPMV = {"auto": 0, "vector": 1, "stream": 2}
 
 
@@ -76,7 +76,7 @@ SYMBOLS = [
     "tfelcu_matrix_set_scatter", "tfelcu_matrix_assemble", "tfelcu_matrix_download_csr",
     "tfelcu_matrix_color_count",
     "tfelcu_vector_create", "tfelcu_vector_create_rows", "tfelcu_vector_destroy", "tfelcu_vector_clear", "tfelcu_vector_size",
-    "tfelcu_vector_assemble", "tfelcu_vector_download", "tfelcu_vector_upload", "tfelcu_vector_device_ptr",
+    "tfelcu_vector_assemble", "tfelcu_vector_set_scatter", "tfelcu_vector_download", "tfelcu_vector_upload", "tfelcu_vector_device_ptr",
     "tfelcu_integrate", "tfelcu_quadrature_size", "tfelcu_mesh_quadrature_points",
     "tfelcu_solver_create", "tfelcu_solver_destroy", "tfelcu_solver_set_operator",
     "tfelcu_solver_set_operator_csr", "tfelcu_solver_solve", "tfelcu_matrix_solve", "tfelcu_matrix_make_rhs",
@@ -446,7 +446,7 @@ class Matrix:
 class Vector:
     """linear_form<fes> (linear_form.hpp:9-20)."""
 
-    def __init__(self, test, rows=None):
+    def __init__(self, test, rows=None, scatter=None):
         test = list(test) if isinstance(test, (list, tuple)) else [test]
         self.test, self.ctx = test, test[0].ctx
         self.h = C.c_void_p()
@@ -456,6 +456,8 @@ class Vector:
         else:
             rb = (C.c_size_t * len(rows))(*[int(r[0]) for r in rows]); re = (C.c_size_t * len(rows))(*[int(r[1]) for r in rows])
             _ck(lib().tfelcu_vector_create_rows(self.ctx.h, len(test), te, len(rows), rb, re, C.byref(self.h)))
+        if scatter is not None and scatter != "colored":   # a linear form has no colour-by-colour variant
+            _ck(lib().tfelcu_vector_set_scatter(self.h, SCATTER[scatter]))
         n = C.c_size_t()
         _ck(lib().tfelcu_vector_size(self.h, C.byref(n)))
         self.n = n.value

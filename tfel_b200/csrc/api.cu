@@ -483,8 +483,9 @@ int tfelcu_matrix_info(const tfelcu_matrix* m, size_t* n_rows, size_t* n_cols, s
 int tfelcu_matrix_set_scatter(tfelcu_matrix* m, int scatter) {
   return guarded([&] {
     TFELCU_REQUIRE(m != nullptr, "null matrix");
-    TFELCU_REQUIRE(scatter == TFELCU_SCATTER_ROW_GATHER || scatter == TFELCU_SCATTER_COLORED, "unknown scatter strategy");
+    TFELCU_REQUIRE(scatter >= TFELCU_SCATTER_ROW_GATHER && scatter <= TFELCU_SCATTER_AUTO, "unknown scatter strategy");
     m->scatter = scatter;
+    m->patch_refused = false;
   });
 }
 
@@ -554,6 +555,16 @@ int tfelcu_vector_clear(tfelcu_vector* v) {
 
 int tfelcu_vector_size(const tfelcu_vector* v, size_t* n) {
   return guarded([&] { TFELCU_REQUIRE(v && n, "null pointer"); *n = v->data.n; });
+}
+
+int tfelcu_vector_set_scatter(tfelcu_vector* v, int scatter) {
+  return guarded([&] {
+    TFELCU_REQUIRE(v != nullptr, "null vector");
+    TFELCU_REQUIRE(scatter == TFELCU_SCATTER_ROW_GATHER || scatter == TFELCU_SCATTER_PATCH || scatter == TFELCU_SCATTER_AUTO,
+                   "unknown scatter strategy for a linear form");
+    v->scatter = scatter;
+    v->patch_refused = false;
+  });
 }
 
 int tfelcu_vector_assemble(tfelcu_vector* v, int quad, const tfelcu_factor* factors, int n_factors,

@@ -159,6 +159,8 @@ void matrix_build_pattern(tfelcu_matrix* m) {
   m->val_valid = false;
   m->has_slots = false; m->slots_failed = false;
   m->slots.clear();
+  m->has_patches = false;
+  m->patch_stage_off.clear();
 }
 
 // one thread per entry a of the owned slice of the transposed test dof map: positions of its nd_tr columns in the row

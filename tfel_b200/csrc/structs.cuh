@@ -17,6 +17,22 @@ struct EntityIndex {
   DevBuf<uint32_t> first;         // [n_unique]: smallest k * n_local + j among the incident (cell, local) pairs
 };
 
+// Patches of rows for the patch assembly (patch.cu): the dofs of one owned row range sorted along a Morton curve of
+// their space coordinates and cut into groups of rows_per_patch; for each patch the ascending list of the cells
+// incident to its rows, and the transposed dof map re-expressed in patch-local cell indices.
+struct PatchPlan {
+  size_t row_begin = 0, row_end = 0;   // dofs of the component covered by the plan
+  int rows_per_patch = 0;              // capacity of a patch
+  size_t n_patch = 0;
+  size_t a_begin = 0, a_count = 0;     // slice of the transposed dof map of [row_begin, row_end)
+  DevBuf<uint32_t> row_ptr;            // [n_patch + 1]: rows of patch p are rows[row_ptr[p] .. row_ptr[p + 1])
+  DevBuf<uint32_t> rows;               // [row_end - row_begin]: dofs in patch order
+  DevBuf<uint32_t> cell_ptr;           // [n_patch + 1]
+  DevBuf<uint32_t> cells;              // cells of each patch, ascending
+  DevBuf<uint32_t> adj_local;          // [a_count]: (index of the cell in its patch's list) * nd + local dof
+  size_t max_cells = 0;                // largest patch, in cells
+};
+
 }  // namespace tfelcu
 
 struct tfelcu_mesh {
@@ -56,6 +72,7 @@ struct tfelcu_fes {
   // for every (cell k, local dof i) with dof_map[k][i] == r
   bool has_adj = false;
   tfelcu::DevBuf<uint32_t> adj_ptr, adj;
+  std::vector<std::unique_ptr<tfelcu::PatchPlan>> patch_plans;   // built on demand, one per (row range, patch size)
 };
 
 namespace tfelcu {
@@ -133,6 +150,8 @@ struct tfelcu_vector {
   tfelcu::SpaceList space;
   tfelcu::RowMap rows;                  // owned rows; data holds rows.n_local() entries
   tfelcu::DevBuf<double> data;
+  int scatter = TFELCU_SCATTER_AUTO;
+  bool patch_refused = false;
 };
 
 struct tfelcu_matrix {
@@ -147,7 +166,8 @@ struct tfelcu_matrix {
   tfelcu::DevBuf<int32_t> rowptr, colind;
   tfelcu::DevBuf<double> val;
   bool pristine = true;                 // no += since clear()
-  int scatter = TFELCU_SCATTER_ROW_GATHER;
+  int scatter = TFELCU_SCATTER_AUTO;
+  bool patch_refused = false;           // AUTO: the patch strategy did not apply to this form once; stay on rows
   bool val_valid = false;                // false: clear() is pending (performed lazily by the first user)
   int rows_per_cta = 128;               // rows (= threads) of one CTA of the owner-computes assembly
   size_t max_block_nnz = 0;             // max nnz over blocks of rows_per_cta consecutive rows
@@ -157,6 +177,12 @@ struct tfelcu_matrix {
   size_t a_begin[tfelcu::kMaxSeg] = {0}, a_count[tfelcu::kMaxSeg] = {0};
   bool has_slots = false, slots_failed = false;
   std::vector<tfelcu::DevBuf<uint32_t>> slots;   // [segment * n_trial + trial component][a_count * slot_words(nd_tr)]
+  // patch assembly (TFELCU_SCATTER_PATCH): per row segment the plan (owned by the test space) and, per row in patch
+  // order, the offset of the row inside the shared-memory stage of its patch
+  bool has_patches = false;
+  tfelcu::PatchPlan* patch_plan[tfelcu::kMaxSeg] = {nullptr};
+  std::vector<tfelcu::DevBuf<uint32_t>> patch_stage_off;
+  size_t patch_max_stage[tfelcu::kMaxSeg] = {0};
   // cell colouring (TFELCU_SCATTER_COLORED): cells sorted by colour
   bool has_colors = false;
   int n_colors = 0;
@@ -193,6 +219,15 @@ void matrix_build_slots(tfelcu_matrix* m);
 void fes_transpose(tfelcu_fes* f);
 void build_transpose(Ctx* ctx, const uint32_t* dof_map, size_t K, int nd, size_t n_dof,
                      DevBuf<uint32_t>& ptr, DevBuf<uint32_t>& adj);
+
+// ---- patch.cu
+PatchPlan* fes_patch_plan(tfelcu_fes* f, size_t row_begin, size_t row_end, int rows_per_patch);
+void matrix_build_patches(tfelcu_matrix* m);
+int resolve_scatter(int requested, bool single_block, int nd_te, int nd_tr);
+bool assemble_bilinear_patch(tfelcu_matrix* m, int quad, const tfelcu_factor* factors, int n_factors,
+                             const tfelcu_term* terms, int n_terms);
+bool assemble_linear_patch(tfelcu_vector* v, int quad, const tfelcu_factor* factors, int n_factors,
+                           const tfelcu_term* terms, int n_terms);
 
 // ---- assemble.cu
 void assemble_bilinear(tfelcu_matrix* m, int quad, const tfelcu_factor* factors, int n_factors,
