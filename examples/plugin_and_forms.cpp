@@ -58,6 +58,19 @@ int main() {
     const std::size_t n(24);
     fe_mesh<cell_type> m(gen_square_mesh(1.0, 1.0, n, n));
     submesh<cell_type> dm(m.get_boundary_submesh());
+    {
+      // face neighbours (mesh.hpp:301-332): symmetric, and -1 exactly on the 4n boundary edges
+      std::size_t on_boundary(0);
+      for (std::size_t k(0); k < m.get_cell_number(); ++k)
+        for (std::size_t j(0); j < 3; ++j) {
+          const int other(static_cast<int>(m.get_cell_neighbour(k, j)));
+          if (other < 0) { ++on_boundary; continue; }
+          bool back(false);
+          for (std::size_t jj(0); jj < 3; ++jj) back = back or static_cast<std::size_t>(m.get_cell_neighbour(other, jj)) == k;
+          if (not back) throw std::string("cell neighbour table is not symmetric");
+        }
+      if (on_boundary != dm.get_cell_number() or on_boundary != 4 * n) throw std::string("cell neighbour table: wrong boundary count");
+    }
     fes_type fes(m);
     fes.add_dirichlet_boundary(dm);
     bilinear_form<fes_type, fes_type> a(fes, fes); {

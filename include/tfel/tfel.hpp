@@ -197,9 +197,18 @@ public:
     tfel_cuda::ck(tfelcu_mesh_download(h, nullptr, c.get_data()));
     return c;
   }
+  // mesh.hpp:214-216 (the reference returns the int table entry as std::size_t: -1 wraps, kept)
+  std::size_t get_cell_neighbour(std::size_t k, std::size_t face_id) const {
+    if (neighbours.get_rank() == 0) {
+      neighbours = array<int>{get_cell_number(), static_cast<std::size_t>(cell_t::dim + 1)};
+      tfel_cuda::ck(tfelcu_mesh_neighbours(h, neighbours.get_data()));
+    }
+    return neighbours.at(k, face_id);
+  }
   tfelcu_mesh* handle() const { return h; }
 protected:
   tfelcu_mesh* h = nullptr;
+  mutable array<int> neighbours;   // compute_cell_neighbours (mesh.hpp:301-332), fetched from the device on first use
 };
 
 template <typename cell_t>

@@ -155,6 +155,9 @@ int tfelcu_mesh_geometry(const tfelcu_mesh* mesh, double* vol, double* jmt);
 int tfelcu_mesh_boundary(tfelcu_mesh* mesh, size_t* n_faces);
 int tfelcu_mesh_boundary_download(const tfelcu_mesh* mesh, uint32_t* el, uint32_t* parent_cell,
                                   uint32_t* parent_subdomain);
+/* compute_cell_neighbours, mesh.hpp:301-332: nb[K][dim + 1] (host or device buffer), nb[k][j] = the cell across local
+ * face j of cell k, -1 on the boundary */
+int tfelcu_mesh_neighbours(tfelcu_mesh* mesh, int32_t* nb);
 
 /* ---- finite element space: finite_element_space<fe>, src/core/fes.hpp:18-82 ---------------- */
 

@@ -141,6 +141,13 @@ def boundary_submesh(dim, cells):
             _take(sd_id, F, np.uint32))
 
 
+def cell_neighbours(dim, cells):
+    cells = _u32(cells)
+    nb = np.zeros((cells.shape[0], dim + 1), dtype=np.int32)
+    lib().orc_cell_neighbours(dim, _p(cells, C.c_uint), C.c_size_t(cells.shape[0]), _p(nb, C.c_int))
+    return nb
+
+
 def fes_build(dim, fe, cells):
     cells = _u32(cells); K = cells.shape[0]; nd = fe_ndof(dim, fe)
     dof_map = np.zeros((K, nd), dtype=np.uint32)

@@ -124,6 +124,11 @@ namespace {
     }
     dmp.put_f64("cell_volume", vol, {K});
     dmp.put_f64("jmt", jmt, {K, dim, dim});
+    // face-neighbour table of mesh<cell>::compute_cell_neighbours (mesh.hpp:301-332), -1 on the boundary
+    std::vector<int> nb(K * nv);
+    for (std::size_t k(0); k < K; ++k)
+      for (std::size_t j(0); j < nv; ++j) nb[k * nv + j] = static_cast<int>(m.get_cell_neighbour(k, j));
+    dmp.put_i32("cell_neighbours", nb, {K, nv});
   }
 
   template<typename submesh_type>

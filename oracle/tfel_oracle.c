@@ -441,6 +441,33 @@ size_t orc_boundary_submesh(int dim, const unsigned* cells, size_t K,
   return F;
 }
 
+/* Face neighbours: mesh.hpp:301-332. The cell loop runs in ascending k; the first cell that meets a face is
+ * remembered, every later one links itself to the first and the first to itself (the last one wins there). */
+void orc_cell_neighbours(int dim, const unsigned* cells, size_t K, int* nb) {
+  const int sd = dim - 1, ne = n_entities(dim, sd);
+  for (size_t i = 0; i < K * (size_t)(dim + 1); ++i) nb[i] = -1;
+  ent_key* keys = (ent_key*)malloc(sizeof(ent_key) * K * ne + 1);
+  size_t n = 0;
+  for (size_t k = 0; k < K; ++k)
+    for (int j = 0; j < ne; ++j) {
+      int lv[4]; const int m = local_entity(dim, sd, j, lv);
+      make_key(&keys[n], cells + k * (dim + 1), lv, m);
+      keys[n].cell = (unsigned)k; keys[n].local = (unsigned)j;
+      ++n;
+    }
+  qsort(keys, n, sizeof(ent_key), ent_cmp_stable);   /* equal faces stay in ascending (k, j) order */
+  for (size_t i = 0; i < n;) {
+    size_t j = i + 1;
+    while (j < n && ent_cmp(&keys[i], &keys[j]) == 0) ++j;
+    for (size_t t = i + 1; t < j; ++t) {
+      nb[(size_t)keys[t].cell * (dim + 1) + keys[t].local] = (int)keys[i].cell;
+      nb[(size_t)keys[i].cell * (dim + 1) + keys[i].local] = (int)keys[t].cell;
+    }
+    i = j;
+  }
+  free(keys);
+}
+
 /* ------------------------------------------------------------------------- */
 /* Finite element space: fes.hpp:18-82                                        */
 /* ------------------------------------------------------------------------- */

@@ -57,6 +57,9 @@ void orc_geometry(int dim, const double* vertices, const unsigned* cells, size_t
 
 size_t orc_boundary_submesh(int dim, const unsigned* cells, size_t K,
                             unsigned** el, unsigned** el_id, unsigned** sd_id);
+/* face-neighbour table of mesh<cell>::compute_cell_neighbours (mesh.hpp:301-332): nb[k][j] = the cell on the other
+ * side of local face j of cell k, -1 on the boundary */
+void orc_cell_neighbours(int dim, const unsigned* cells, size_t K, int* nb);
 
 size_t orc_fes_build(int dim, int fe, const unsigned* cells, size_t K, unsigned* dof_map);
 void orc_fes_g2l(const unsigned* dof_map, size_t K, int nd, size_t N, unsigned* g2l);

@@ -76,6 +76,7 @@ def run(ctx, problem, scatter=None, generator="device", do_assemble=True):
     out["vertices"], out["cells"] = B.mesh.download()
     out["cell_volume"], out["jmt"] = B.mesh.geometry()
     out["boundary_cells"], out["boundary_parent_cell"], out["boundary_parent_subdomain"] = B.mesh.boundary()
+    out["cell_neighbours"] = B.mesh.neighbours()
     ncomp = len(problem.comps)
     prefix = (lambda c: "") if ncomp == 1 and not problem.composite else (lambda c: "c%d_" % c)
     for c, sp in enumerate(B.spaces):

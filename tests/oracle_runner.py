@@ -32,6 +32,7 @@ def run(problem, assemble=True):
     out["cell_volume"], out["jmt"] = orc.geometry(vertices, cells)
     bel, bid, bsd = orc.boundary_submesh(dim, cells)
     out["boundary_cells"], out["boundary_parent_cell"], out["boundary_parent_subdomain"] = bel, bid, bsd
+    out["cell_neighbours"] = orc.cell_neighbours(dim, cells)
 
     ncomp = len(problem.comps)
     prefix = (lambda c: "") if ncomp == 1 and not problem.composite else (lambda c: "c%d_" % c)

@@ -67,7 +67,7 @@ SYMBOLS = [
     "tfelcu_ctx_synchronize", "tfelcu_ctx_rank", "tfelcu_ctx_launch_count", "tfelcu_ctx_p2p_enabled", "tfelcu_ctx_p2p_bench",
     "tfelcu_mesh_create", "tfelcu_mesh_gen_square", "tfelcu_mesh_gen_cube", "tfelcu_mesh_destroy",
     "tfelcu_mesh_info", "tfelcu_mesh_download", "tfelcu_mesh_geometry", "tfelcu_mesh_boundary",
-    "tfelcu_mesh_boundary_download",
+    "tfelcu_mesh_boundary_download", "tfelcu_mesh_neighbours",
     "tfelcu_fes_create", "tfelcu_fes_destroy", "tfelcu_fes_info", "tfelcu_fes_kind_offsets", "tfelcu_fes_download_dof_map",
     "tfelcu_fes_download_g2l", "tfelcu_fes_dof_coordinates", "tfelcu_fes_boundary_dofs",
     "tfelcu_fes_boundary_dofs_get", "tfelcu_fes_add_dirichlet", "tfelcu_fes_add_dirichlet_const",
@@ -232,6 +232,13 @@ class Mesh:
         pc = np.zeros(F.value, dtype=np.uint32); ps = np.zeros(F.value, dtype=np.uint32)
         _ck(lib().tfelcu_mesh_boundary_download(self.h, _ptr(el), _ptr(pc), _ptr(ps)))
         return el, pc, ps
+
+
+    def neighbours(self):
+        """mesh<cell>::compute_cell_neighbours (mesh.hpp:301-332): [K][dim + 1] int32, -1 on the boundary"""
+        nb = np.zeros((self.n_cells, self.dim + 1), dtype=np.int32)
+        _ck(lib().tfelcu_mesh_neighbours(self.h, _ptr(nb)))
+        return nb
 
 
 class Space:

@@ -276,6 +276,18 @@ int tfelcu_mesh_boundary_download(const tfelcu_mesh* mesh, uint32_t* el, uint32_
   });
 }
 
+int tfelcu_mesh_neighbours(tfelcu_mesh* mesh, int32_t* nb) {
+  return guarded([&] {
+    TFELCU_REQUIRE(mesh && nb, "null pointer");
+    use_device(mesh->ctx);
+    const size_t n = mesh->K * (size_t)(mesh->dim + 1);
+    if (tfelcu::is_device_pointer(nb)) { tfelcu::mesh_neighbours(mesh, nb); return; }
+    tfelcu::DevBuf<int32_t> d(n);
+    tfelcu::mesh_neighbours(mesh, d.p);
+    copy_out(mesh->ctx, nb, d.p, n);
+  });
+}
+
 // ---- finite element space -------------------------------------------------------------------------
 
 int tfelcu_fes_create(tfelcu_ctx* ctx, tfelcu_mesh* mesh, int fe, tfelcu_fes** fes) {

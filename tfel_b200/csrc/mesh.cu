@@ -306,6 +306,42 @@ void mesh_build_boundary(tfelcu_mesh* m) {
 }
 
 // ------------------------------------------------------------------------------------------
+// face-neighbour table: mesh<cell>::compute_cell_neighbours (mesh.hpp:301-332)
+// ------------------------------------------------------------------------------------------
+
+// largest k * n_local + j among the (cell, local face) pairs of every face
+__global__ void k_face_last(const uint32_t* __restrict__ rank, size_t n, uint32_t* __restrict__ last) {
+  const size_t code = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (code < n) atomicMax(last + rank[code], (uint32_t)code);
+}
+
+// The reference walks the cells in ascending order, remembers the first (cell, local face) that meets a face, links every
+// later cell to that first one and the first one to the later cell (so the last one stays): first <-> last, others -> first.
+__global__ void k_neighbours(const uint32_t* __restrict__ rank, const uint32_t* __restrict__ first,
+                             const uint32_t* __restrict__ last, size_t n, int n_local, int32_t* __restrict__ nb) {
+  const size_t code = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (code >= n) return;
+  const uint32_t u = rank[code], f = first[u], l = last[u];
+  nb[code] = (f == l) ? -1 : (int32_t)(((uint32_t)code == f ? l : f) / (uint32_t)n_local);
+}
+
+void mesh_neighbours(tfelcu_mesh* m, int32_t* d_nb) {
+  Ctx* ctx = m->ctx;
+  const int sd = m->dim - 1;
+  EntityIndex* E = mesh_entities(m, sd);
+  const int n_local = n_sub_entities(m->dim, sd);   // == dim + 1 faces per simplex
+  const size_t n = m->K * (size_t)n_local;
+  if (!n) return;
+  DevBuf<uint32_t> last(E->n_unique);
+  ctx->zero(last.p, E->n_unique);
+  k_face_last<<<grid_for(n, 256), 256, 0, ctx->stream>>>(E->rank.p, n, last.p);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  k_neighbours<<<grid_for(n, 256), 256, 0, ctx->stream>>>(E->rank.p, E->first.p, last.p, n, n_local, d_nb);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  ctx->sync();
+}
+
+// ------------------------------------------------------------------------------------------
 // geometry download (parity of a3)
 // ------------------------------------------------------------------------------------------
 

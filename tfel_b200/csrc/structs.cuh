@@ -202,6 +202,7 @@ void mesh_validate_cells(tfelcu_mesh* m);
 void mesh_build_vertex_rank(tfelcu_mesh* m);
 EntityIndex* mesh_entities(tfelcu_mesh* m, int sd);
 void mesh_build_boundary(tfelcu_mesh* m);
+void mesh_neighbours(tfelcu_mesh* m, int32_t* d_nb);
 
 // ---- fes.cu
 void fes_build(tfelcu_fes* f);
