@@ -97,6 +97,31 @@ def main():
         assert err <= 1e-8, err
         if rank == 0:
             print("dist worker: %s n=%d ranks=%d its=%d/%d rel diff %.2e" % (which, n, world, repd["its"], rep1["its"], err))
+    # restarted GMRES on the row-distributed operator (halo exchange before every product, rank-ordered reductions of
+    # every MGS dot product) against the single-GPU GMRES: same Arnoldi process up to the rounding of the partial sums
+    for pc in ("jacobi", "block_jacobi"):
+        if which == "stokes":
+            gkw = dict(method="gmres", precond=pc, maxits=45, restart=20, rtol=1e-30)   # a fixed number of Arnoldi steps
+        else:
+            gkw = dict(method="gmres", precond=pc, maxits=4000, restart=60, rtol=1e-10)
+        if pc == "block_jacobi":
+            gkw["block_size"] = 4
+        g1 = capi.Solver(ctx, **gkw); g1.set_operator(B.matrix)
+        gd = capi.Solver(ctx, **gkw); gd.set_operator(A)
+        xg_full, r1 = B.matrix.solve(B.vector, g1)
+        xg_dist, rd = A.solve(b, gd)
+        if pc == "jacobi":   # the blocks of block-Jacobi are rank-local: another preconditioner when rows are split
+            assert abs(int(r1["its"]) - int(rd["its"])) <= 2, (r1["its"], rd["its"])
+        if which != "stokes":
+            assert r1["converged"] == 1 and rd["converged"] == 1, (r1, rd)
+            gerr = np.linalg.norm(xg_dist - xg_full) / np.linalg.norm(xg_full)
+            assert gerr <= 1e-8, gerr
+        elif pc == "jacobi":
+            gerr = np.linalg.norm(xg_dist - xg_full) / max(np.linalg.norm(xg_full), 1e-300)
+            assert gerr <= 1e-6, gerr
+        if rank == 0:
+            print("dist worker: %s n=%d ranks=%d gmres+%s its=%d/%d" % (which, n, world, pc, rd["its"], r1["its"]))
+        g1.close(); gd.close()
     s1.close(); sd.close(); A.close(); b.close(); cuda_runner.close(B)
     dist.barrier()
     ctx.close()

@@ -562,10 +562,14 @@ static void precond(tfelcu_solver* s, const double* d_in, double* d_out) {
   }
 }
 
+// Row-distributed operators (one process per GPU): every basis vector carries its halo entries behind the owned ones
+// (it is the input of the next product), a halo exchange precedes each product, and every dot product / norm is reduced
+// over the ranks -- in rank order, so that all ranks hold the same bits and take the same branch of every test.
 void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep) {
   Ctx* ctx = s->ctx;
-  TFELCU_REQUIRE(!s->dist, "GMRES on a row-distributed operator is not available yet (use CG, or one rank)");
+  const bool dist = (bool)s->dist;
   const size_t n = s->n;
+  const size_t n_halo = dist ? s->dist->n_halo : 0;
   const int vg = vgrid(s);
   const uint64_t launches0 = ctx->launches;
   uint64_t n_spmv = 0;
@@ -576,10 +580,16 @@ void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep) {
   if (m < 1) m = 1;
   size_t free_b = 0, total_b = 0;
   TFELCU_CK(cudaMemGetInfo(&free_b, &total_b));
-  const size_t ld = (n + 3) & ~(size_t)3;
+  const size_t ld = (n + n_halo + 3) & ~(size_t)3;
   if (!s->basis.n || s->basis.n < (size_t)(m + 1) * ld) {
     const size_t have = s->basis.bytes();
     long long fit = (long long)((free_b + have) * 0.8 / (8.0 * (double)(ld ? ld : 1))) - 1;
+    if (dist) {   // every rank must run the same number of Arnoldi steps per cycle: agree on the smallest fit
+      DevBuf<long long> f(1);
+      ctx->upload(f.p, &fit, 1);
+      TFELCU_NCCL(ncclAllReduce(f.p, f.p, 1, ncclInt64, ncclMin, ctx->comm, ctx->stream));
+      ctx->download(&fit, f.p, 1);
+    }
     if (m > fit) m = fit;
     TFELCU_REQUIRE(m >= 1, "GMRES: not enough device memory for a Krylov basis");
     s->basis.release();
@@ -597,15 +607,28 @@ void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep) {
   GmresDev* G = Gd.p;
   double* V = s->basis.p;
   double* t = s->r.p;          // work vector
-  double* P0 = s->partial.p;   // two alternating partial-sum buffers
-  double* P1 = s->partial.p + s->n_partial;
+  double* P[2] = {s->partial.p, s->partial.p + s->n_partial};   // two alternating partial-sum buffers
+  // what the consumers of a sum read: the per-CTA partials themselves, or the one value reduced over the ranks
+  const double* R[2] = {P[0], P[1]};
+  int RN[2] = {vg, vg};
+  auto reduced = [&](int which) {
+    if (!dist) return;
+    const double* ptrs[1] = {P[which]}; const int ns[1] = {vg};
+    R[which] = dist_reduce(s, ptrs, ns, 1, 5 + which);
+    RN[which] = 1;
+  };
+  auto product = [&](double* v_in, double* out) {   // out = A v_in
+    if (dist) dist_halo_exchange(s, v_in, nullptr);
+    spmv_launch(s, v_in, out, nullptr, nullptr); ++n_spmv;
+  };
 
-  ctx->zero(s->x.p, n);                                      // x0 = 0 (solver.cpp:165-166)
+  ctx->zero(s->x.p, n + n_halo);                             // x0 = 0 (solver.cpp:165-166)
   ctx->zero(s->scal.p, 1);
   precond(s, s->b.p, s->q.p);
-  k_dot<<<vg, kVecT, 0, ctx->stream>>>(s->q.p, s->q.p, n, P0);
+  k_dot<<<vg, kVecT, 0, ctx->stream>>>(s->q.p, s->q.p, n, P[0]);
   ctx->count(); TFELCU_LAUNCH_CHECK();
-  k_gmres_init<<<1, 32, 0, ctx->stream>>>(P0, vg, s->params.rtol, s->params.atol, s->params.dtol, G);
+  reduced(0);
+  k_gmres_init<<<1, 32, 0, ctx->stream>>>(R[0], RN[0], s->params.rtol, s->params.atol, s->params.dtol, G);
   ctx->count(); TFELCU_LAUNCH_CHECK();
 
   GmresDev h;
@@ -617,39 +640,42 @@ void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep) {
     if (first_cycle) {
       TFELCU_CK(cudaMemcpyAsync(V, s->q.p, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
-      spmv_launch(s, s->x.p, s->q.p, nullptr, nullptr); ++n_spmv;
+      product(s->x.p, s->q.p);
       k_sub<<<vg, kVecT, 0, ctx->stream>>>(s->b.p, s->q.p, n, t);
       ctx->count(); TFELCU_LAUNCH_CHECK();
       precond(s, t, V);
     }
     first_cycle = false;
-    k_dot<<<vg, kVecT, 0, ctx->stream>>>(V, V, n, P0);
+    k_dot<<<vg, kVecT, 0, ctx->stream>>>(V, V, n, P[0]);
     ctx->count(); TFELCU_LAUNCH_CHECK();
-    k_gmres_cycle_start<<<1, 32, 0, ctx->stream>>>(P0, vg, G, g, M);
+    reduced(0);
+    k_gmres_cycle_start<<<1, 32, 0, ctx->stream>>>(R[0], RN[0], G, g, M);
     ctx->count(); TFELCU_LAUNCH_CHECK();
     ctx->download(&h, G, 1);
     if (h.done) break;
-    k_scale_by_norm<<<vg, kVecT, 0, ctx->stream>>>(V, n, P0, vg, G);
+    k_scale_by_norm<<<vg, kVecT, 0, ctx->stream>>>(V, n, R[0], RN[0], G);
     ctx->count(); TFELCU_LAUNCH_CHECK();
     int k = 0;
     for (; k < M; ++k) {
       double* w = V + (size_t)(k + 1) * ld;
-      spmv_launch(s, V + (size_t)k * ld, t, nullptr, nullptr); ++n_spmv;
+      product(V + (size_t)k * ld, t);
       precond(s, t, w);
       double* Hk = H + (size_t)k * (M + 1);
       // MGS: k + 2 fused steps; step j projects out v_{j-1} and starts the product with v_j (the last: with w)
       for (int j = 0; j <= k + 1; ++j) {
         const double* v_prev = j > 0 ? V + (size_t)(j - 1) * ld : nullptr;
         const bool last = (j == k + 1);
-        k_mgs_step<<<vg, kVecT, 0, ctx->stream>>>(w, v_prev, (j & 1) ? P0 : P1, vg, j > 0 ? Hk + (j - 1) : nullptr,
-                                                 last ? w : V + (size_t)j * ld, last ? 1 : 0, n, (j & 1) ? P1 : P0, G);
+        const int prev = (j & 1) ? 0 : 1, next = (j & 1) ? 1 : 0;
+        k_mgs_step<<<vg, kVecT, 0, ctx->stream>>>(w, v_prev, R[prev], RN[prev], j > 0 ? Hk + (j - 1) : nullptr,
+                                                 last ? w : V + (size_t)j * ld, last ? 1 : 0, n, P[next], G);
         ctx->count();
+        reduced(next);
       }
       TFELCU_LAUNCH_CHECK();
-      double* Pn = ((k + 1) & 1) ? P1 : P0;
-      k_gmres_givens<<<1, 32, 0, ctx->stream>>>(H, cs, sn, g, Pn, vg, k, M, maxits, G);
+      const int fin = ((k + 1) & 1) ? 1 : 0;
+      k_gmres_givens<<<1, 32, 0, ctx->stream>>>(H, cs, sn, g, R[fin], RN[fin], k, M, maxits, G);
       ctx->count(); TFELCU_LAUNCH_CHECK();
-      k_scale_by_norm<<<vg, kVecT, 0, ctx->stream>>>(w, n, Pn, vg, G);   // skipped on device once done
+      k_scale_by_norm<<<vg, kVecT, 0, ctx->stream>>>(w, n, R[fin], RN[fin], G);   // skipped on device once done
       ctx->count(); TFELCU_LAUNCH_CHECK();
       // the stopping test lives on the device (every kernel returns at once when G->done is set): the host only polls
       // every few Arnoldi steps, so that launches stay queued ahead of the GPU
