@@ -99,7 +99,7 @@ def main():
             print("dist worker: %s n=%d ranks=%d its=%d/%d rel diff %.2e" % (which, n, world, repd["its"], rep1["its"], err))
     # restarted GMRES on the row-distributed operator (halo exchange before every product, rank-ordered reductions of
     # every MGS dot product) against the single-GPU GMRES: same Arnoldi process up to the rounding of the partial sums
-    for pc in ("jacobi", "block_jacobi"):
+    for pc in ("jacobi", "block_jacobi", "ilu0"):   # ilu0: ILU(0) of every rank's diagonal block
         if which == "stokes":
             gkw = dict(method="gmres", precond=pc, maxits=45, restart=20, rtol=1e-30)   # a fixed number of Arnoldi steps
         else:
@@ -110,7 +110,7 @@ def main():
         gd = capi.Solver(ctx, **gkw); gd.set_operator(A)
         xg_full, r1 = B.matrix.solve(B.vector, g1)
         xg_dist, rd = A.solve(b, gd)
-        if pc == "jacobi":   # the blocks of block-Jacobi are rank-local: another preconditioner when rows are split
+        if pc == "jacobi":   # block-Jacobi / ILU(0) factorise rank-local blocks: another preconditioner when rows are split
             assert abs(int(r1["its"]) - int(rd["its"])) <= 2, (r1["its"], rd["its"])
         if which != "stokes":
             assert r1["converged"] == 1 and rd["converged"] == 1, (r1, rd)

@@ -288,16 +288,59 @@ static std::vector<LevelRun> plan_runs(const std::vector<int32_t>& level_ptr) {
   return runs;
 }
 
+// diagonal block of a row-distributed operator: entries whose (local) column is an owned row
+__global__ void k_owned_flag(const int32_t* __restrict__ colind, size_t nnz, int32_t n, uint32_t* __restrict__ keep) {
+  const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (e < nnz) keep[e] = colind[e] < n ? 1u : 0u;
+}
+
+__global__ void k_block_rowptr(const int32_t* __restrict__ rowptr, const uint32_t* __restrict__ pos, size_t n, size_t nnz,
+                               int32_t total, int32_t* __restrict__ out) {
+  const size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r > n) return;
+  out[r] = (r == n || (size_t)rowptr[r] >= nnz) ? total : (int32_t)pos[rowptr[r]];
+}
+
+__global__ void k_block_compact(const int32_t* __restrict__ colind, const double* __restrict__ val, const uint32_t* __restrict__ keep,
+                                const uint32_t* __restrict__ pos, size_t nnz, int32_t* __restrict__ out_col, double* __restrict__ out_val) {
+  const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (e < nnz && keep[e]) { out_col[pos[e]] = colind[e]; out_val[pos[e]] = val[e]; }
+}
+
 void ilu0_setup(tfelcu_solver* s) {
   Ctx* ctx = s->ctx;
   const size_t n = s->n;
   TFELCU_REQUIRE(n < 0x7fffffffull, "ILU(0): too many rows");
   s->ilu.reset(new Ilu0());
   Ilu0& I = *s->ilu;
+  I.rowptr = s->rowptr; I.colind = s->colind; I.val = s->val; I.nnz = s->nnz;
+  if (s->dist) {
+    // row-distributed operator: ILU(0) of the DIAGONAL BLOCK of this rank (block-Jacobi over the ranks with an
+    // incomplete factorisation inside). Owned columns are the local indices < n and keep their ascending order.
+    DevBuf<uint32_t> keep(s->nnz), pos(s->nnz);
+    if (s->nnz) {
+      k_owned_flag<<<grid_for(s->nnz, 256), 256, 0, ctx->stream>>>(s->colind, s->nnz, (int32_t)n, keep.p);
+      ctx->count(); TFELCU_LAUNCH_CHECK();
+      exclusive_sum<uint32_t, uint32_t>(ctx, keep.p, pos.p, s->nnz);
+    }
+    uint32_t last_pos = 0, last_keep = 0;
+    if (s->nnz) { ctx->download(&last_pos, pos.p + (s->nnz - 1), 1); ctx->download(&last_keep, keep.p + (s->nnz - 1), 1); }
+    I.nnz = (size_t)last_pos + last_keep;
+    I.own_rowptr.alloc(n + 1); I.own_colind.alloc(I.nnz); I.own_val.alloc(I.nnz);
+    k_block_rowptr<<<grid_for(n + 1, 256), 256, 0, ctx->stream>>>(s->rowptr, pos.p, n, s->nnz, (int32_t)I.nnz, I.own_rowptr.p);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+    if (s->nnz) {
+      k_block_compact<<<grid_for(s->nnz, 256), 256, 0, ctx->stream>>>(s->colind, s->val, keep.p, pos.p, s->nnz,
+                                                                     I.own_colind.p, I.own_val.p);
+      ctx->count(); TFELCU_LAUNCH_CHECK();
+    }
+    ctx->sync();
+    I.rowptr = I.own_rowptr.p; I.colind = I.own_colind.p; I.val = I.own_val.p;
+  }
   I.diag.alloc(n);
   DevBuf<int> missing(1);
   ctx->zero(missing.p, 1);
-  k_diag_pos<<<grid_for(n, 256), 256, 0, ctx->stream>>>(s->rowptr, s->colind, n, I.diag.p, missing.p);
+  k_diag_pos<<<grid_for(n, 256), 256, 0, ctx->stream>>>(I.rowptr, I.colind, n, I.diag.p, missing.p);
   ctx->count(); TFELCU_LAUNCH_CHECK();
   int h_missing = 0; ctx->download(&h_missing, missing.p, 1);
   TFELCU_REQUIRE(!h_missing, "ILU(0): the matrix has a row without a stored diagonal entry");
@@ -307,8 +350,8 @@ void ilu0_setup(tfelcu_solver* s) {
   for (int pass = 0; pass < 2; ++pass) {
     TFELCU_CK(cudaMemsetAsync(level.p, 0xff, n * sizeof(int), ctx->stream));
     ctx->zero(ticket.p, 1);
-    if (pass == 0) k_levels<true><<<grid_for(n, 128), 128, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, n, ticket.p, level.p, missing.p);
-    else k_levels<false><<<grid_for(n, 128), 128, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, n, ticket.p, level.p, missing.p);
+    if (pass == 0) k_levels<true><<<grid_for(n, 128), 128, 0, ctx->stream>>>(I.rowptr, I.colind, I.diag.p, n, ticket.p, level.p, missing.p);
+    else k_levels<false><<<grid_for(n, 128), 128, 0, ctx->stream>>>(I.rowptr, I.colind, I.diag.p, n, ticket.p, level.p, missing.p);
     ctx->count(); TFELCU_LAUNCH_CHECK();
     ctx->download(&h_missing, missing.p, 1);
     TFELCU_REQUIRE(!h_missing, "ILU(0): level analysis did not terminate");
@@ -322,12 +365,12 @@ void ilu0_setup(tfelcu_solver* s) {
   ctx->count(2);
   TFELCU_CK(cudaFuncSetAttribute(k_tri_levels_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRunRows * (int)sizeof(double)));
   TFELCU_CK(cudaFuncSetAttribute(k_tri_levels_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRunRows * (int)sizeof(double)));
-  k_sched_meta<<<grid_for(n, 256), 256, 0, ctx->stream>>>(s->rowptr, I.diag.p, I.order_l.p, n, 1, reinterpret_cast<int4*>(I.meta_l.p));
-  k_sched_meta<<<grid_for(n, 256), 256, 0, ctx->stream>>>(s->rowptr, I.diag.p, I.order_u.p, n, 0, reinterpret_cast<int4*>(I.meta_u.p));
+  k_sched_meta<<<grid_for(n, 256), 256, 0, ctx->stream>>>(I.rowptr, I.diag.p, I.order_l.p, n, 1, reinterpret_cast<int4*>(I.meta_l.p));
+  k_sched_meta<<<grid_for(n, 256), 256, 0, ctx->stream>>>(I.rowptr, I.diag.p, I.order_u.p, n, 0, reinterpret_cast<int4*>(I.meta_u.p));
   ctx->count(2); TFELCU_LAUNCH_CHECK();
   if (std::getenv("TFELCU_TRACE")) {
     const auto rl = plan_runs(I.level_ptr_l), ru = plan_runs(I.level_ptr_u);
-    std::fprintf(stderr, "[tfelcu trace] ILU(0): n %zu nnz %zu, L levels %zu (runs %zu), U levels %zu (runs %zu)\n", n, s->nnz,
+    std::fprintf(stderr, "[tfelcu trace] ILU(0): n %zu nnz %zu, L levels %zu (runs %zu), U levels %zu (runs %zu)\n", n, I.nnz,
                  I.level_ptr_l.size() - 1, rl.size(), I.level_ptr_u.size() - 1, ru.size());
   }
   I.d_level_ptr_l.alloc(I.level_ptr_l.size());
@@ -336,15 +379,15 @@ void ilu0_setup(tfelcu_solver* s) {
   ctx->upload(I.d_level_ptr_u.p, I.level_ptr_u.data(), I.level_ptr_u.size());
 
   // numeric factorisation on a copy of the values, level by level of the L schedule
-  I.lu.alloc(s->nnz);
-  TFELCU_CK(cudaMemcpyAsync(I.lu.p, s->val, s->nnz * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  I.lu.alloc(I.nnz);
+  TFELCU_CK(cudaMemcpyAsync(I.lu.p, I.val, I.nnz * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   for (const LevelRun& r : plan_runs(I.level_ptr_l)) {
     if (r.cta) {
-      k_ilu0_levels_cta<<<1, 1024, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, I.order_l.p, I.d_level_ptr_l.p,
+      k_ilu0_levels_cta<<<1, 1024, 0, ctx->stream>>>(I.rowptr, I.colind, I.diag.p, I.order_l.p, I.d_level_ptr_l.p,
                                                     r.l0, r.l1, I.lu.p);
     } else {
       const int b = I.level_ptr_l[r.l0], e = I.level_ptr_l[r.l1];
-      k_ilu0_level<<<grid_for((size_t)(e - b), 128), 128, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, I.order_l.p, b, e, I.lu.p);
+      k_ilu0_level<<<grid_for((size_t)(e - b), 128), 128, 0, ctx->stream>>>(I.rowptr, I.colind, I.diag.p, I.order_l.p, b, e, I.lu.p);
     }
     ctx->count(); TFELCU_LAUNCH_CHECK();
   }
@@ -371,13 +414,13 @@ static void tri_launches(tfelcu_solver* s, const double* d_in, double* d_out, bo
       while (lpr > 1 && widest * lpr > 1024) lpr >>= 1;
       int threads = ((widest * lpr + 31) / 32) * 32;
       if (threads < 32) threads = 32;
-      if (lower) k_tri_levels_cta<true><<<1, threads, smem, ctx->stream>>>(s->colind, I.diag.p, I.lu.p, meta, pos, d_lp, r.l0, r.l1, lpr, d_in, d_out, S);
-      else k_tri_levels_cta<false><<<1, threads, smem, ctx->stream>>>(s->colind, I.diag.p, I.lu.p, meta, pos, d_lp, r.l0, r.l1, lpr, d_in, d_out, S);
+      if (lower) k_tri_levels_cta<true><<<1, threads, smem, ctx->stream>>>(I.colind, I.diag.p, I.lu.p, meta, pos, d_lp, r.l0, r.l1, lpr, d_in, d_out, S);
+      else k_tri_levels_cta<false><<<1, threads, smem, ctx->stream>>>(I.colind, I.diag.p, I.lu.p, meta, pos, d_lp, r.l0, r.l1, lpr, d_in, d_out, S);
     } else {
       const int b = lp[r.l0], e = lp[r.l1];
       const unsigned g = grid_for((size_t)(e - b), 128);
-      if (lower) k_tri_level<true><<<g, 128, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, I.lu.p, order, b, e, d_in, d_out, S);
-      else k_tri_level<false><<<g, 128, 0, ctx->stream>>>(s->rowptr, s->colind, I.diag.p, I.lu.p, order, b, e, d_in, d_out, S);
+      if (lower) k_tri_level<true><<<g, 128, 0, ctx->stream>>>(I.rowptr, I.colind, I.diag.p, I.lu.p, order, b, e, d_in, d_out, S);
+      else k_tri_level<false><<<g, 128, 0, ctx->stream>>>(I.rowptr, I.colind, I.diag.p, I.lu.p, order, b, e, d_in, d_out, S);
     }
     ctx->count();
   }

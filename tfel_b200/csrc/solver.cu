@@ -326,7 +326,6 @@ void solver_setup(tfelcu_solver* s) {
   const size_t n = s->n;
   size_t n_halo = 0;
   if (s->dist) {
-    TFELCU_REQUIRE(s->params.precond != TFELCU_PC_ILU0, "ILU(0) on a row-distributed operator is not available yet");
     dist_setup(s);                       // needs the global column indices
     s->colind = s->dist->colind_local.p;
     n_halo = s->dist->n_halo;

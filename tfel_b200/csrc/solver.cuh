@@ -53,6 +53,11 @@ struct SpmvPlan {
 struct LevelRun { int l0, l1; bool cta; };
 
 struct Ilu0 {
+  // the matrix that is factorised: the operator itself, or (row-distributed operators) the diagonal block of this rank
+  const int32_t* rowptr = nullptr; const int32_t* colind = nullptr; const double* val = nullptr;
+  size_t nnz = 0;
+  DevBuf<int32_t> own_rowptr, own_colind;
+  DevBuf<double> own_val;
   DevBuf<double> lu;                     // factors on the pattern of A
   DevBuf<int32_t> diag;                  // position of the diagonal in each row
   DevBuf<int32_t> order_l, order_u;      // rows grouped by level
