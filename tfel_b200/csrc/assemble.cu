@@ -399,7 +399,7 @@ static void assemble_bilinear_dim(tfelcu_matrix* m, int quad, const tfelcu_facto
   const bool colored = (m->scatter == TFELCU_SCATTER_COLORED);
   if (colored) matrix_build_colors(m);
   else if (!m->has_slots && !m->slots_failed && !std::getenv("TFELCU_NO_SLOTS")) {
-    try { matrix_build_slots(m); } catch (const Error&) { m->has_slots = false; m->slots_failed = true; }   // rows > 256 entries: search
+    try { matrix_build_slots(m); } catch (const Refusal&) { m->has_slots = false; m->slots_failed = true; }   // rows > 256 entries: search
   }
   for (int a = 0; a < m->test.n; ++a)
     for (int b = 0; b < m->trial.n; ++b) {
@@ -489,7 +489,7 @@ void assemble_bilinear(tfelcu_matrix* m, int quad, const tfelcu_factor* factors,
   if (mode == TFELCU_SCATTER_PATCH) {
     if (requested == TFELCU_SCATTER_PATCH) { assemble_bilinear_patch(m, quad, factors, n_factors, terms, n_terms); return; }
     try { assemble_bilinear_patch(m, quad, factors, n_factors, terms, n_terms); return; }
-    catch (const Error&) { m->patch_refused = true; mode = TFELCU_SCATTER_ROW_GATHER; }   // refused before touching a value
+    catch (const Refusal&) { m->patch_refused = true; mode = TFELCU_SCATTER_ROW_GATHER; }   // refused before touching a value
   }
   const int saved = m->scatter;
   m->scatter = mode;
@@ -537,7 +537,7 @@ void assemble_linear(tfelcu_vector* v, int quad, const tfelcu_factor* factors, i
     if (requested == TFELCU_SCATTER_PATCH) { assemble_linear_patch(v, quad, factors, n_factors, terms, n_terms); return; }
     // AUTO: a refusal (shared memory) before the first launch falls back to rows; later ones would double count
     try { assemble_linear_patch(v, quad, factors, n_factors, terms, n_terms); return; }
-    catch (const Error&) { if (v->space.n != 1 || v->rows.n != 1) throw; v->patch_refused = true; }
+    catch (const Refusal&) { if (v->space.n != 1 || v->rows.n != 1) throw; v->patch_refused = true; }
   }
   if (v->space.fes[0]->mesh->dim == 2) assemble_linear_dim<2>(v, quad, factors, n_factors, terms, n_terms);
   else assemble_linear_dim<3>(v, quad, factors, n_factors, terms, n_terms);

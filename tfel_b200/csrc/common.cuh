@@ -20,7 +20,13 @@ struct Error : std::runtime_error {
   explicit Error(const std::string& m) : std::runtime_error(m) {}
 };
 
+// a strategy that does not apply to this input (the caller may fall back to another one); never a CUDA failure
+struct Refusal : Error {
+  explicit Refusal(const std::string& m) : Error(m) {}
+};
+
 [[noreturn]] inline void fail(const std::string& m) { throw Error(m); }
+[[noreturn]] inline void refuse(const std::string& m) { throw Refusal(m); }
 
 #define TFELCU_CK(call)                                                                         \
   do {                                                                                          \

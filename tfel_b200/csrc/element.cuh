@@ -371,7 +371,7 @@ __device__ __forceinline__ double element_entry(const FormDev& F, const double* 
 __device__ __forceinline__ int find_in_row(const int32_t* __restrict__ colind, int rs, int re, int32_t col) {
   int lo = rs, hi = re;
   while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
+    const int mid = lo + ((hi - lo) >> 1);   // lo + hi overflows int32 beyond 2^30 stored entries
     if (__ldg(colind + mid) < col) lo = mid + 1; else hi = mid;
   }
   return lo;

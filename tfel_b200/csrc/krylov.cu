@@ -35,7 +35,7 @@ __global__ void k_diag_pos(const int32_t* __restrict__ rowptr, const int32_t* __
   int lo = rowptr[r], hi = rowptr[r + 1];
   const int end = hi;
   while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
+    const int mid = lo + ((hi - lo) >> 1);   // lo + hi overflows int32 beyond 2^30 stored entries
     if (colind[mid] < (int32_t)r) lo = mid + 1; else hi = mid;
   }
   if (lo >= end || colind[lo] != (int32_t)r) { atomicExch(missing, 1); diag[r] = -1; }

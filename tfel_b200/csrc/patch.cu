@@ -181,7 +181,7 @@ __global__ void k_patch_adj_local(const uint32_t* __restrict__ adj, size_t a_beg
   const uint32_t c0 = cell_ptr[patch];
   uint32_t lo = c0, hi = cell_ptr[patch + 1];
   while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
+    const uint32_t mid = lo + ((hi - lo) >> 1);
     if (cells[mid] < k) lo = mid + 1; else hi = mid;
   }
   adj_local[p] = (lo - c0) * (uint32_t)nd + i;
@@ -559,8 +559,8 @@ static void assemble_bilinear_patch_dim(tfelcu_matrix* m, int quad, const tfelcu
   Ctx* ctx = m->ctx;
   tfelcu_mesh* mesh = m->mesh;
   if (!m->has_slots) {
-    TFELCU_REQUIRE(!m->slots_failed, "patch assembly needs the slot map (a row has more than 256 stored entries)");
-    try { matrix_build_slots(m); } catch (const Error&) { m->has_slots = false; m->slots_failed = true; throw; }
+    if (m->slots_failed) refuse("patch assembly needs the slot map (a row has more than 256 stored entries)");
+    try { matrix_build_slots(m); } catch (const Refusal&) { m->has_slots = false; m->slots_failed = true; throw; }
   }
   matrix_build_patches(m);
   const bool single_block = (m->test.n == 1 && m->trial.n == 1);
@@ -576,7 +576,7 @@ static void assemble_bilinear_patch_dim(tfelcu_matrix* m, int quad, const tfelcu
         if (m->rows.comp[sg] != a) continue;
         const size_t nnp = (size_t)(te->nd * tr->nd) | 1;
         const size_t smem = ((size_t)fb->F.n_stage + m->patch_plan[sg]->max_cells * nnp + m->patch_max_stage[sg]) * sizeof(double);
-        TFELCU_REQUIRE(smem <= kMaxPatchSmem, "patch assembly: the element matrices of a patch do not fit in shared memory");
+        if (smem > kMaxPatchSmem) refuse("patch assembly: the element matrices of a patch do not fit in shared memory");
       }
       forms[(size_t)a * m->trial.n + b] = std::move(fb);
     }
@@ -630,7 +630,7 @@ static void launch_vector_patch(Ctx* ctx, const FormBuild& fb, const VecPatchBlo
   if (!P->n_patch) return;
   constexpr int NDP = ND_TE | 1;
   const size_t smem = ((size_t)fb.F.n_stage + P->max_cells * NDP) * sizeof(double);
-  TFELCU_REQUIRE(smem <= kMaxPatchSmem, "patch assembly: the element vectors of a patch do not fit in shared memory");
+  if (smem > kMaxPatchSmem) refuse("patch assembly: the element vectors of a patch do not fit in shared memory");
   const int threads = patch_threads();
   if (fb.const_coef) {
     auto kern = k_assemble_vector_patch<DIM, ND_TE, true>;

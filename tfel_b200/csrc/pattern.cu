@@ -184,7 +184,7 @@ __global__ void k_build_slots(const uint32_t* __restrict__ adj, size_t a_begin, 
     const int32_t col = (int32_t)(off_tr + map_tr[k * nd_tr + j]);
     int lo = rs, hi = re;
     while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
+      const int mid = lo + ((hi - lo) >> 1);   // lo + hi overflows int32 beyond 2^30 stored entries
       if (colind[mid] < col) lo = mid + 1; else hi = mid;
     }
     if (lo >= re || colind[lo] != col || lo - rs > 255) { atomicExch(bad, 1); return; }
@@ -216,7 +216,7 @@ void matrix_build_slots(tfelcu_matrix* m) {
       ctx->count(); TFELCU_LAUNCH_CHECK();
     }
   int h = 0; ctx->download(&h, bad.p, 1);
-  if (h) { m->slots.clear(); fail("slot map: a row has more than 256 stored entries or the pattern is inconsistent"); }
+  if (h) { m->slots.clear(); refuse("slot map: a row has more than 256 stored entries or the pattern is inconsistent"); }
   m->has_slots = true;
 }
 

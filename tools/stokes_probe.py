@@ -9,8 +9,9 @@ import cuda_runner  # noqa: E402
 import problems  # noqa: E402
 from tfel_b200 import capi  # noqa: E402
 
+ASSEMBLY_ONLY = "--assembly-only" in sys.argv   # full-size runs (n = 2048: 8.4 M cells, 37.8 M dofs, 1.1e9 stored entries)
 ctx = capi.Context(0)
-for n in [int(v) for v in sys.argv[1:]] or [64, 128]:
+for n in [int(v) for v in sys.argv[1:] if not v.startswith("--")] or [64, 128]:
     p = problems.stokes(n)
     t0 = time.perf_counter()
     B = cuda_runner.build(ctx, p)
@@ -20,6 +21,11 @@ for n in [int(v) for v in sys.argv[1:]] or [64, 128]:
         t0 = time.perf_counter()
         cuda_runner.assemble(B)
         ctx.synchronize(); t_asm = time.perf_counter() - t0
+    if ASSEMBLY_ONLY:
+        print("stokes n=%d: cells %d dofs %d nnz %d | structure %.3f s, assembly (A and b, 2nd pass) %.4f s (%.3g cells/s)"
+              % (n, B.mesh.n_cells, B.matrix.n_rows, B.matrix.nnz, t_struct, t_asm, B.mesh.n_cells / t_asm), flush=True)
+        cuda_runner.close(B)
+        continue
     s = capi.Solver(ctx, method="gmres", precond="ilu0", maxits=3000, restart=300, rtol=1e-8)
     t0 = time.perf_counter()
     x, rep = B.matrix.solve(B.vector, s)
