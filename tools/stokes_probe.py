@@ -22,6 +22,14 @@ for n in [int(v) for v in sys.argv[1:] if not v.startswith("--")] or [64, 128]:
         cuda_runner.assemble(B)
         ctx.synchronize(); t_asm = time.perf_counter() - t0
     if ASSEMBLY_ONLY:
+        if "--spmv-check" in sys.argv:   # the two SpMV kernels on the full-size operator (indices beyond 2^30 entries)
+            import numpy as np
+            xr = np.random.RandomState(3).standard_normal(B.matrix.n_rows)
+            ys = []
+            for kern in ("vector", "stream"):
+                sk = capi.Solver(ctx, method="gmres", precond="none", spmv=kern); sk.set_operator(B.matrix)
+                ys.append(sk.spmv(xr)); sk.close()
+            print("stokes n=%d: spmv vector vs stream max rel diff %.3e" % (n, np.abs(ys[0] - ys[1]).max() / np.abs(ys[0]).max()), flush=True)
         print("stokes n=%d: cells %d dofs %d nnz %d | structure %.3f s, assembly (A and b, 2nd pass) %.4f s (%.3g cells/s)"
               % (n, B.mesh.n_cells, B.matrix.n_rows, B.matrix.nnz, t_struct, t_asm, B.mesh.n_cells / t_asm), flush=True)
         cuda_runner.close(B)
