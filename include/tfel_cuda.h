@@ -182,6 +182,11 @@ int tfelcu_fes_add_dirichlet(tfelcu_fes* fes, const uint32_t* dofs, const double
 int tfelcu_fes_add_dirichlet_const(tfelcu_fes* fes, double value);
 int tfelcu_fes_dirichlet_count(const tfelcu_fes* fes, size_t* n);
 int tfelcu_fes_dirichlet_get(const tfelcu_fes* fes, uint32_t* dofs, double* values);
+/* output side (fes.hpp:464-504). to_mesh_vertex_data: out[V], out[cells[k][n]] = coefficients[dof(k, n)] for the vertex
+ * dofs of every cell (0 for vertices no cell uses); to_mesh_cell_data: out[K], the value of the discrete function at the
+ * barycentre of every cell (element::evaluate, fes.hpp:247-255). coefficients / out: host or device. */
+int tfelcu_fes_vertex_values(const tfelcu_fes* fes, const double* coefficients, double* out);
+int tfelcu_fes_cell_values(const tfelcu_fes* fes, const double* coefficients, double* out);
 
 /* ---- bilinear form / sparse matrix ----------------------------------------------------------
  * bilinear_form<te, tr> (bilinear_form.hpp:9-19; composite: composite_bilinear_form.hpp:33-62):

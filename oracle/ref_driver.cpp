@@ -18,6 +18,8 @@
 //             synthetic previous iterates
 //   laplace2  test/composite_fe.cpp:82-131 (two decoupled Laplacians)
 //   quadrature  dumps every quadrature table of src/core/quadrature.cpp
+//   export    the output side (fes.hpp:464-504, export.hpp): nodal interpolants written by the reference's own
+//             exporters into the directory --out (the files are the fixtures of tests/golden/export)
 #include <iostream>
 #include <fstream>
 #include <chrono>
@@ -33,6 +35,8 @@
 #include "core/composite_fe.hpp"
 #include "core/composite_fes.hpp"
 #include "core/composite_form.hpp"
+#include "core/projector.hpp"
+#include "core/export.hpp"
 
 extern "C" {
   // CPU Krylov restatement (oracle/tfel_oracle.c)
@@ -691,6 +695,50 @@ namespace {
   }
 }
 
+namespace {
+  double export_g(const double* x) { return 1.0 + x[0] + 2.0 * x[1] + x[0] * x[1]; }
+  double export_h(const double* x) { return x[0] * x[0] - 0.5 * x[1]; }
+  double export_t(const double* x) { return 1.0 + x[0] - x[1] + 2.0 * x[2]; }
+
+  // every exporter entry point on small meshes: scalar per node / per element, a two-component vector per node, P2
+  // vertex data, the plain ASCII dump, a tetrahedral geometry and a transient series
+  void run_export(const run_options& opt) {
+    const std::string dir(opt.out);
+    {
+      using cell_type = cell::triangle;
+      using mesh_type = fe_mesh<cell_type>;
+      using p1 = cell_type::fe::lagrange_p1;
+      using p2 = cell_type::fe::lagrange_p2;
+      mesh_type m(gen_square_mesh(1.0, 1.0, opt.n, opt.n));
+      finite_element_space<p1> fes1(m);
+      finite_element_space<p2> fes2(m);
+      const auto g1(projector::lagrange<p1>(export_g, fes1));
+      const auto h1(projector::lagrange<p1>(export_h, fes1));
+      const auto g2(projector::lagrange<p2>(export_g, fes2));
+      exporter::ensight6(dir + "/square", to_mesh_vertex_data<p1>(g1), "g", to_mesh_cell_data<p1>(h1), "hc",
+                         to_mesh_vertex_data<p2>(g2), "g2");
+      const auto dg(to_mesh_vertex_data<p1>(g1));
+      const auto dh(to_mesh_vertex_data<p1>(h1));
+      exporter::ensight6(dir + "/vector", mesh_data<double, mesh_type>(m, mesh_data_kind::vertex, dg, dh), "gh");
+      exporter::ascii<mesh_type>(dir + "/square_vertex.dat", to_mesh_vertex_data<p1>(g1));
+      exporter::ascii<mesh_type>(dir + "/square_cell.dat", to_mesh_cell_data<p2>(g2));
+      exporter::ensight6_geometry(dir + "/geometry_only", m);
+      exporter::ensight6_transient<mesh_type> series(dir + "/series", m, "g");
+      series.export_time_step(0.0, to_mesh_vertex_data<p1>(g1));
+      series.export_time_step(0.25, to_mesh_vertex_data<p1>(h1));
+    }
+    {
+      using cell_type = cell::tetrahedron;
+      using mesh_type = fe_mesh<cell_type>;
+      using p1 = cell_type::fe::lagrange_p1;
+      mesh_type m(gen_cube_mesh(1.0, 1.0, 1.0, 2, 2, 2));
+      finite_element_space<p1> fes(m);
+      const auto t1(projector::lagrange<p1>(export_t, fes));
+      exporter::ensight6(dir + "/cube", to_mesh_vertex_data<p1>(t1), "t", to_mesh_cell_data<p1>(t1), "tc");
+    }
+  }
+}
+
 int main(int argc, char* argv[]) {
   try {
     run_options opt;
@@ -720,6 +768,7 @@ int main(int argc, char* argv[]) {
     else if (opt.problem == "ns") run_ns(opt);
     else if (opt.problem == "laplace2") run_laplace2(opt);
     else if (opt.problem == "tables") run_tables(opt);
+    else if (opt.problem == "export") run_export(opt);
     else throw std::string("unknown problem");
   } catch (const std::string& e) {
     std::cerr << "ref_driver: " << e << std::endl;

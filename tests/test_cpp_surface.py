@@ -17,8 +17,42 @@ def build():
 
 def test_reference_programs_compile_against_the_cuda_headers():
     build()
-    for name in ("poisson", "stokes_2d_p2_p1", "navier_stokes_2d_p2_p1", "plugin_and_forms", "expression_algebra", "device_functor"):
+    for name in ("poisson", "stokes_2d_p2_p1", "navier_stokes_2d_p2_p1", "plugin_and_forms", "expression_algebra", "device_functor",
+                 "export_ensight", "export_format_host"):
         assert os.path.exists(os.path.join(BIN, name))
+
+
+EXPORT_GOLDEN = os.path.join(ROOT, "tests", "golden", "export")   # written by the UNMODIFIED reference (oracle/ref_driver.cpp)
+
+
+def _compare_export(tmp_path, program, expect_all):
+    (tmp_path / "export").mkdir()
+    r = subprocess.run([os.path.join(BIN, program), "export"], capture_output=True, text=True, cwd=str(tmp_path), timeout=300)
+    assert r.returncode == 0 and program + ": ok" in r.stdout, r.stdout + r.stderr
+    written = sorted(os.listdir(str(tmp_path / "export")))
+    golden = sorted(os.listdir(EXPORT_GOLDEN))
+    assert written and set(written) <= set(golden), (written, golden)
+    if expect_all:
+        assert written == golden
+    for name in written:
+        got = open(os.path.join(str(tmp_path), "export", name), "rb").read()
+        ref = open(os.path.join(EXPORT_GOLDEN, name), "rb").read()
+        assert got == ref, name
+
+
+def test_exporters_write_the_reference_files_host_only(tmp_path):
+    """exporter::ensight6 / ensight6_geometry / ensight6_transient / ascii (export.hpp) on a host mesh: byte-identical to
+    the files the unmodified reference wrote for the same data (tests/golden/export)."""
+    build()
+    _compare_export(tmp_path, "export_format_host", expect_all=False)
+
+
+@pytest.mark.gpu
+def test_exporters_and_mesh_data_on_the_cuda_path(tmp_path):
+    """to_mesh_vertex_data / to_mesh_cell_data (fes.hpp:464-504) gathered on the device + the exporters: every file of the
+    reference's run (P1 / P2 triangles, tetrahedra, vector data, transient series), byte for byte."""
+    build()
+    _compare_export(tmp_path, "export_ensight", expect_all=True)
 
 
 def test_expression_algebra_matches_reference_assertions():

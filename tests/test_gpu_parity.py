@@ -398,6 +398,31 @@ def test_quadrature_points_and_kind_offsets(ctx):
     m.close()
 
 
+def test_vertex_and_cell_values(ctx):
+    """to_mesh_vertex_data / to_mesh_cell_data on the device (fes.hpp:464-504): the vertex dofs per vertex, the discrete
+    function at the barycentre of every cell -- against numpy on the downloaded maps and the oracle's basis tables."""
+    rng = np.random.RandomState(11)
+    for p in (problems.poisson("p1", 5), problems.poisson("p2", 7), problems.tet("p1b", 3), problems.tet("p2", 3)):
+        B = cuda_runner.build(ctx, p)
+        try:
+            sp = B.spaces[0]
+            dm = sp.dof_map().astype(np.int64)
+            _, cells = B.mesh.download()
+            dim = B.mesh.dim
+            coef = rng.standard_normal(sp.n_dof)
+            ref_v = np.zeros(B.mesh.n_vertices)
+            ref_v[cells.astype(np.int64)] = coef[dm[:, :dim + 1]]
+            assert np.array_equal(sp.vertex_values(coef), ref_v)
+            bc = np.full((1, dim), 1.0 / (dim + 1))
+            phi = orc.fe_tabulate(dim, orc.FE_BY_NAME[p.comps[0]], bc)[0, :, 0]
+            ref_c = np.zeros(B.mesh.n_cells)
+            for i in range(dm.shape[1]):
+                ref_c = ref_c + coef[dm[:, i]] * phi[i]
+            assert np.abs(sp.cell_values(coef) - ref_c).max() <= 1e-14 * np.abs(ref_c).max()
+        finally:
+            cuda_runner.close(B)
+
+
 def test_mesh_with_unused_vertices_and_unsorted_cells(ctx):
     """Edge cases of the mesh / space constructors: vertices no cell uses are skipped by the numbering
     (get_vertex_list, cell.hpp:393-405: dofs are ranks among the USED vertices); cells whose first nv - 1 ids are not

@@ -71,7 +71,7 @@ SYMBOLS = [
     "tfelcu_fes_create", "tfelcu_fes_destroy", "tfelcu_fes_info", "tfelcu_fes_kind_offsets", "tfelcu_fes_download_dof_map",
     "tfelcu_fes_download_g2l", "tfelcu_fes_dof_coordinates", "tfelcu_fes_boundary_dofs",
     "tfelcu_fes_boundary_dofs_get", "tfelcu_fes_add_dirichlet", "tfelcu_fes_add_dirichlet_const",
-    "tfelcu_fes_dirichlet_count", "tfelcu_fes_dirichlet_get",
+    "tfelcu_fes_dirichlet_count", "tfelcu_fes_dirichlet_get", "tfelcu_fes_vertex_values", "tfelcu_fes_cell_values",
     "tfelcu_matrix_create", "tfelcu_matrix_create_rows", "tfelcu_matrix_local_rows", "tfelcu_matrix_destroy", "tfelcu_matrix_clear", "tfelcu_matrix_info",
     "tfelcu_matrix_set_scatter", "tfelcu_matrix_assemble", "tfelcu_matrix_download_csr",
     "tfelcu_matrix_color_count",
@@ -278,6 +278,20 @@ class Space:
         x = np.zeros((dofs.shape[0], self.mesh.dim))
         _ck(lib().tfelcu_fes_dof_coordinates(self.h, _ptr(dofs), _sz(dofs.shape[0]), _ptr(x)))
         return x
+
+    def vertex_values(self, coefficients):
+        """to_mesh_vertex_data (fes.hpp:483-504)"""
+        c = np.ascontiguousarray(coefficients, dtype=np.float64)
+        out = np.zeros(self.mesh.n_vertices)
+        _ck(lib().tfelcu_fes_vertex_values(self.h, _ptr(c), _ptr(out)))
+        return out
+
+    def cell_values(self, coefficients):
+        """to_mesh_cell_data (fes.hpp:464-481): the discrete function at the barycentre of every cell"""
+        c = np.ascontiguousarray(coefficients, dtype=np.float64)
+        out = np.zeros(self.mesh.n_cells)
+        _ck(lib().tfelcu_fes_cell_values(self.h, _ptr(c), _ptr(out)))
+        return out
 
     def boundary_dofs(self, bcells=None, with_coordinates=False):
         """dofs add_dirichlet_boundary would touch (fes.hpp:100-122); bcells None = whole boundary."""

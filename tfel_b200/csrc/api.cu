@@ -425,6 +425,28 @@ int tfelcu_fes_dirichlet_get(const tfelcu_fes* fes, uint32_t* dofs, double* valu
   });
 }
 
+static void fes_values(const tfelcu_fes* fes, const double* coefficients, double* out, bool vertex) {
+  TFELCU_REQUIRE(fes && coefficients && out, "null pointer");
+  use_device(fes->ctx);
+  Ctx* ctx = fes->ctx;
+  const size_t n_out = vertex ? fes->mesh->V : fes->mesh->K;
+  Staged<double> c(ctx, coefficients, fes->n_dof);
+  const bool dev_out = tfelcu::is_device_pointer(out);
+  tfelcu::DevBuf<double> tmp;
+  if (!dev_out) tmp.alloc(n_out);
+  double* d_out = dev_out ? out : tmp.p;
+  if (vertex) tfelcu::fes_vertex_values(fes, c.p, d_out); else tfelcu::fes_cell_values(fes, c.p, d_out);
+  if (!dev_out) copy_out(ctx, out, d_out, n_out); else ctx->sync();
+}
+
+int tfelcu_fes_vertex_values(const tfelcu_fes* fes, const double* coefficients, double* out) {
+  return guarded([&] { fes_values(fes, coefficients, out, true); });
+}
+
+int tfelcu_fes_cell_values(const tfelcu_fes* fes, const double* coefficients, double* out) {
+  return guarded([&] { fes_values(fes, coefficients, out, false); });
+}
+
 // ---- bilinear form / matrix -----------------------------------------------------------------------
 
 static void matrix_create_impl(tfelcu_ctx* ctx, int n_test, tfelcu_fes* const* test, int n_trial, tfelcu_fes* const* trial,

@@ -265,4 +265,56 @@ void fes_dirichlet_get(const tfelcu_fes* f, uint32_t* h_dofs, double* h_values) 
   if (h_values) ctx->download(h_values, values.p, f->n_dirichlet);
 }
 
+// ------------------------------------------------------------------------------------------
+// output side: to_mesh_vertex_data / to_mesh_cell_data (fes.hpp:464-504)
+// ------------------------------------------------------------------------------------------
+
+// values[cells[k][n]] = coefficients[dof(k, n)] for the vertex dofs n < dim + 1 of every cell (fes.hpp:498-501; all
+// writers of a vertex store the same number for a continuous element)
+__global__ void k_vertex_values(const uint32_t* __restrict__ cells, const uint32_t* __restrict__ dof_map, int nv, int nd,
+                                size_t K, const double* __restrict__ coef, double* __restrict__ out) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= K * (size_t)nv) return;
+  const size_t k = t / nv; const int n = (int)(t - k * nv);
+  out[cells[k * nv + n]] = coef[dof_map[k * nd + n]];
+}
+
+struct BasisAt { double phi[kMaxNd]; };
+
+// values[k] = sum_i coefficients[dof(k, i)] phi_i(barycentre) (fes.hpp:476-479: element::evaluate at cell_type::barycenter())
+__global__ void k_cell_values(const uint32_t* __restrict__ dof_map, int nd, size_t K, BasisAt B,
+                              const double* __restrict__ coef, double* __restrict__ out) {
+  const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double v = 0.0;
+  for (int i = 0; i < nd; ++i) v = __dadd_rn(v, __dmul_rn(coef[dof_map[k * nd + i]], B.phi[i]));
+  out[k] = v;
+}
+
+void fes_vertex_values(const tfelcu_fes* f, const double* d_coef, double* d_out) {
+  Ctx* ctx = f->ctx;
+  const tfelcu_mesh* m = f->mesh;
+  ctx->zero(d_out, m->V);
+  const int nv = m->dim + 1;
+  const size_t n = m->K * (size_t)nv;
+  if (!n) return;
+  k_vertex_values<<<grid_for(n, 256), 256, 0, ctx->stream>>>(m->cells.p, f->dof_map, nv, f->nd, m->K, d_coef, d_out);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+}
+
+void fes_cell_values(const tfelcu_fes* f, const double* d_coef, double* d_out) {
+  Ctx* ctx = f->ctx;
+  const tfelcu_mesh* m = f->mesh;
+  if (!m->K) return;
+  const int dim = m->dim, w = dim + 1;
+  double bc[kMaxDim];
+  for (int d = 0; d < dim; ++d) bc[d] = 1.0 / (dim + 1);
+  double hat[kMaxNd * (kMaxDim + 1)];
+  fe_eval_hat(dim, f->fe, bc, hat);
+  BasisAt B;
+  for (int i = 0; i < kMaxNd; ++i) B.phi[i] = i < f->nd ? hat[i * w] : 0.0;
+  k_cell_values<<<grid_for(m->K, 256), 256, 0, ctx->stream>>>(f->dof_map, f->nd, m->K, B, d_coef, d_out);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+}
+
 }  // namespace tfelcu

@@ -210,6 +210,8 @@ void fes_boundary_dofs(tfelcu_fes* f, const uint32_t* d_bcells, size_t F, int nv
 void fes_dof_coordinates(const tfelcu_fes* f, const uint32_t* d_dofs, size_t n, double* d_x);
 void fes_add_dirichlet(tfelcu_fes* f, const uint32_t* d_dofs, const double* d_values, double constant, size_t n);
 void fes_dirichlet_get(const tfelcu_fes* f, uint32_t* h_dofs, double* h_values);
+void fes_vertex_values(const tfelcu_fes* f, const double* d_coef, double* d_out);
+void fes_cell_values(const tfelcu_fes* f, const double* d_coef, double* d_out);
 
 // ---- pattern.cu
 void matrix_snapshot_dirichlet(tfelcu_matrix* m);
