@@ -24,6 +24,12 @@ int main(int argc, char* argv[]) {
       const auto g1(projector::lagrange<p1>(export_g, fes1));
       const auto h1(projector::lagrange<p1>(export_h, fes1));
       const auto g2(projector::lagrange<p2>(export_g, fes2));
+      {
+        // element algebra (fes.hpp:314-405): (2 g - g) / 1 + (h - h) is g again, coefficient for coefficient
+        const auto again((2.0 * g1 - g1) / 1.0 + (h1 - h1).transformed([](double c) { return 3.0 * c; }));
+        for (std::size_t i(0); i < fes1.get_dof_number(); ++i)
+          if (again.get_coefficients().at(i) != g1.get_coefficients().at(i)) throw std::string("element algebra is wrong");
+      }
       exporter::ensight6(dir + "/square", to_mesh_vertex_data<p1>(g1), "g", to_mesh_cell_data<p1>(h1), "hc",
                          to_mesh_vertex_data<p2>(g2), "g2");
       const auto dg(to_mesh_vertex_data<p1>(g1));

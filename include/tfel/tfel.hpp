@@ -283,7 +283,27 @@ public:
     element(const finite_element_space& f, array<double> c) : fes(&f), coefficients(std::move(c)) {}
     const finite_element_space& get_finite_element_space() const { return *fes; }
     const array<double>& get_coefficients() const { return coefficients; }
+    // coefficient-wise algebra of fes.hpp:314-359 (discrete functions of one space are a vector space)
+    element& transform(const std::function<double(double)>& f) {
+      for (std::size_t i(0); i < coefficients.get_element_number(); ++i) coefficients.at(i) = f(coefficients.at(i));
+      return *this;
+    }
+    element transformed(const std::function<double(double)>& f) const { element r(*this); r.transform(f); return r; }
+    element& operator*=(double s) { return transform([s](double c) { return c * s; }); }
+    element& operator/=(double s) { return transform([s](double c) { return c / s; }); }
+    element& operator+=(const element& o) { same_space(o); for (std::size_t i(0); i < size(); ++i) coefficients.at(i) += o.coefficients.at(i); return *this; }
+    element& operator-=(const element& o) { same_space(o); for (std::size_t i(0); i < size(); ++i) coefficients.at(i) -= o.coefficients.at(i); return *this; }
+    // fes.hpp:366-405 (hidden friends: the reference's free templates cannot deduce fe from a nested type)
+    friend element operator+(element a, const element& b) { a += b; return a; }
+    friend element operator-(element a, const element& b) { a -= b; return a; }
+    friend element operator*(double s, element a) { a *= s; return a; }
+    friend element operator*(element a, double s) { a *= s; return a; }
+    friend element operator/(element a, double s) { a /= s; return a; }
   private:
+    std::size_t size() const { return coefficients.get_element_number(); }
+    void same_space(const element& o) const {
+      if (fes != o.fes) throw std::string("operations between elements of different finite element spaces are not supported.");
+    }
     const finite_element_space* fes;
     array<double> coefficients;
   };
