@@ -284,7 +284,7 @@ def run_own(args):
     assembly = {"cells_per_s": cells / (asm_avg_ms * 1e-3), "ms": asm_avg_ms,
                 "algorithmic_bytes": asm_bytes, "achieved_gbs": asm_bytes / (asm_avg_ms * 1e-3) / 1e9,
                 "frac_of_peak": asm_bytes / (asm_avg_ms * 1e-3) / 1e9 / peak,
-                "kernels": "k_assemble_rows<2,3,3,const,staged> + k_assemble_vector_rows<2,3,const>"}
+                "kernels": "k_assemble_rows<2,3,3,const,staged,rec> (packed 16-byte row records) + k_assemble_vector_rows<2,3,const>"}
     solve = {"s": float(np.mean(solve_ms)) * 1e-3, "cg_iterations": int(np.mean(its_seen)),
              "ms_per_iteration": float(np.mean(solve_ms)) / max(float(np.mean(its_seen)), 1.0)}
 

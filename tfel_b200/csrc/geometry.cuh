@@ -49,6 +49,17 @@ __device__ __forceinline__ void finish_cell_geometry(CellGeom<DIM>& g) {
   }
 }
 
+// triangle whose three vertex ids are already in registers (packed row records of the owner-computes assembly)
+__device__ __forceinline__ void triangle_geometry_from_ids(const double* __restrict__ vertices, uint32_t i0, uint32_t i1,
+                                                           uint32_t i2, CellGeom<2>& g) {
+  const double2* v2 = reinterpret_cast<const double2*>(vertices);
+  const double2 p0 = __ldg(v2 + i0), p1 = __ldg(v2 + i1), p2 = __ldg(v2 + i2);
+  g.v0[0] = p0.x; g.v0[1] = p0.y;
+  g.J[0][0] = p1.x - p0.x; g.J[1][0] = p1.y - p0.y;
+  g.J[0][1] = p2.x - p0.x; g.J[1][1] = p2.y - p0.y;
+  finish_cell_geometry<2>(g);
+}
+
 template <int DIM>
 __device__ __forceinline__ void load_cell_geometry(const double* __restrict__ vertices,
                                                    const uint32_t* __restrict__ cell,

@@ -161,6 +161,8 @@ void matrix_build_pattern(tfelcu_matrix* m) {
   m->slots.clear();
   m->has_patches = false;
   m->patch_stage_off.clear();
+  m->has_recs = false;
+  m->recs.clear();
 }
 
 // one thread per entry a of the owned slice of the transposed test dof map: positions of its nd_tr columns in the row
@@ -218,6 +220,40 @@ void matrix_build_slots(tfelcu_matrix* m) {
   int h = 0; ctx->download(&h, bad.p, 1);
   if (h) { m->slots.clear(); refuse("slot map: a row has more than 256 stored entries or the pattern is inconsistent"); }
   m->has_slots = true;
+}
+
+// packed row records of P1 triangles: (v0, v1, v2, slot bytes | local dof << 24) per entry of the transposed dof map
+__global__ void k_build_rec(const uint32_t* __restrict__ adj, size_t a_begin, size_t n_adj, const uint32_t* __restrict__ cells,
+                            const uint32_t* __restrict__ slots, uint4* __restrict__ rec) {
+  const size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= n_adj) return;
+  const uint32_t code = adj[a_begin + p];
+  const uint32_t k = code / 3u, i = code - 3u * k;
+  const uint32_t* c = cells + (size_t)k * 3;
+  rec[p] = make_uint4(c[0], c[1], c[2], (slots ? (slots[p] & 0x00ffffffu) : 0u) | (i << 24));
+}
+
+void matrix_build_recs(tfelcu_matrix* m) {
+  if (m->has_recs) return;
+  Ctx* ctx = m->ctx;
+  const RowMap& R = m->rows;
+  m->recs.clear();
+  m->recs.resize((size_t)R.n * m->trial.n);
+  m->has_recs = true;
+  if (!m->has_slots || m->mesh->dim != 2) return;
+  for (int sg = 0; sg < R.n; ++sg)
+    for (int b = 0; b < m->trial.n; ++b) {
+      tfelcu_fes* te = m->test.fes[R.comp[sg]]; tfelcu_fes* tr = m->trial.fes[b];
+      if (te->nd != 3 || tr->nd != 3) continue;
+      const size_t n = m->a_count[sg];
+      DevBuf<uint32_t>& Rc = m->recs[(size_t)sg * m->trial.n + b];
+      Rc.alloc(n * 4);
+      if (!n) continue;
+      k_build_rec<<<grid_for(n, 256), 256, 0, ctx->stream>>>(te->adj.p, m->a_begin[sg], n, m->mesh->cells.p,
+                                                           m->slots[(size_t)sg * m->trial.n + b].p,
+                                                           reinterpret_cast<uint4*>(Rc.p));
+      ctx->count(); TFELCU_LAUNCH_CHECK();
+    }
 }
 
 // clear(): zero everything, identity on the Dirichlet rows (bilinear_form.hpp:159-165)

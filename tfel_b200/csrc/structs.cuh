@@ -177,6 +177,10 @@ struct tfelcu_matrix {
   size_t a_begin[tfelcu::kMaxSeg] = {0}, a_count[tfelcu::kMaxSeg] = {0};
   bool has_slots = false, slots_failed = false;
   std::vector<tfelcu::DevBuf<uint32_t>> slots;   // [segment * n_trial + trial component][a_count * slot_words(nd_tr)]
+  // P1 x P1 triangle blocks: 16-byte records (three vertex ids of the cell | three slot bytes + local dof) replacing the
+  // separate reads of the transposed dof map, the slot map and the cell (same indexing as slots; empty when not built)
+  bool has_recs = false;
+  std::vector<tfelcu::DevBuf<uint32_t>> recs;
   // patch assembly (TFELCU_SCATTER_PATCH): per row segment the plan (owned by the test space) and, per row in patch
   // order, the offset of the row inside the shared-memory stage of its patch
   bool has_patches = false;
@@ -219,6 +223,7 @@ void matrix_build_pattern(tfelcu_matrix* m);
 void matrix_build_colors(tfelcu_matrix* m);
 void matrix_ensure_cleared(tfelcu_matrix* m);
 void matrix_build_slots(tfelcu_matrix* m);
+void matrix_build_recs(tfelcu_matrix* m);
 void fes_transpose(tfelcu_fes* f);
 void build_transpose(Ctx* ctx, const uint32_t* dof_map, size_t K, int nd, size_t n_dof,
                      DevBuf<uint32_t>& ptr, DevBuf<uint32_t>& adj);

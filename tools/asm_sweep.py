@@ -32,7 +32,14 @@ ref = None
 for cfg in a.configs:
     parts = cfg.split(":")
     scatter = parts[0]
-    os.environ.pop("TFELCU_PATCH_ROWS", None); os.environ.pop("TFELCU_PATCH_THREADS", None)
+    os.environ.pop("TFELCU_PATCH_ROWS", None); os.environ.pop("TFELCU_PATCH_THREADS", None); os.environ.pop("TFELCU_NO_REC", None)
+    if scatter == "rows-norec":   # owner-computes rows without the packed (cell | slots | local dof) records
+        scatter = "rows"
+        os.environ["TFELCU_NO_REC"] = "1"
+    os.environ.pop("TFELCU_ROWS_PER_CTA", None)
+    if "@" in scatter:   # rows@64: rows (= threads) per CTA of the owner-computes kernel
+        scatter, rpc = scatter.split("@")
+        os.environ["TFELCU_ROWS_PER_CTA"] = rpc
     if len(parts) > 1:
         os.environ["TFELCU_PATCH_ROWS"] = parts[1]
     if len(parts) > 2:
