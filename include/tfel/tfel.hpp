@@ -311,6 +311,20 @@ public:
   explicit finite_element_space(const fe_mesh<cell_type>& m) : msh(&m) {
     tfel_cuda::ck(tfelcu_fes_create(tfel_cuda::context(), m.handle(), fe_t::id, &h));
   }
+  // fes.hpp:84-98: space + Dirichlet data on a submesh in one go
+  template <typename sm_t>
+  finite_element_space(const fe_mesh<cell_type>& m, const sm_t& dm, double value = 0.0) : finite_element_space(m) {
+    add_dirichlet_boundary(dm, value);
+  }
+  template <typename sm_t>
+  finite_element_space(const fe_mesh<cell_type>& m, const sm_t& dm, double (*f)(const double*)) : finite_element_space(m) {
+    add_dirichlet_boundary(dm, f);
+  }
+  template <typename sm_t>
+  finite_element_space(const fe_mesh<cell_type>& m, const sm_t& dm, const std::function<double(const double*)>& f)
+    : finite_element_space(m) {
+    add_dirichlet_boundary(dm, f);
+  }
   finite_element_space(const finite_element_space&) = delete;
   ~finite_element_space() { if (h) tfelcu_fes_destroy(h); }
 

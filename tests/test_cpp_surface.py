@@ -18,7 +18,7 @@ def build():
 def test_reference_programs_compile_against_the_cuda_headers():
     build()
     for name in ("poisson", "stokes_2d_p2_p1", "navier_stokes_2d_p2_p1", "plugin_and_forms", "expression_algebra", "device_functor",
-                 "export_ensight", "export_format_host"):
+                 "export_ensight", "export_format_host", "laplacian_transient"):
         assert os.path.exists(os.path.join(BIN, name))
 
 
@@ -139,3 +139,17 @@ def test_device_functor_coefficients():
     r = subprocess.run([os.path.join(BIN, "device_functor"), "40"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "device_functor: ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_reference_transient_laplacian_program(tmp_path):
+    """test/laplacian_transient.cpp on the CUDA path: one bilinear form solved at every implicit Euler step, the right-hand
+    side reassembled from the previous iterate, every step exported (ensight6_transient); the exact solution
+    (1 - t) sin(pi x) sin(pi y) is reproduced up to the spatial error."""
+    build()
+    r = subprocess.run([os.path.join(BIN, "laplacian_transient"), "40", "10", str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "laplacian_transient: ok" in r.stdout, r.stdout + r.stderr
+    case = open(os.path.join(str(tmp_path), "solution.case")).read()
+    assert "number of steps: 11" in case and "scalar per node: 1 c" in case
+    assert os.path.exists(os.path.join(str(tmp_path), "solution.var.c.000010"))
+    assert os.path.exists(os.path.join(str(tmp_path), "initial_condition.var.c_init"))
