@@ -75,6 +75,17 @@ int main() {
     thrown = false; try { p.get<double>("maxits"); } catch (const std::string&) { thrown = true; } assert(thrown);
     thrown = false; try { p.get<double>("atol"); } catch (const std::string&) { thrown = true; } assert(thrown);
 
+    // array<T> (spikes array.hpp subset): extents, row-major at(...) of any rank, fill / set_data, value semantics
+    array<double> t3{2, 3, 4};
+    assert(t3.get_rank() == 3 and t3.get_size(0) == 2 and t3.get_size(2) == 4 and t3.get_element_number() == 24);
+    for (std::size_t i(0); i < 24; ++i) t3.get_data()[i] = static_cast<double>(i);
+    assert(t3.at(1, 2, 3) == 23.0 and t3.at(0, 1, 0) == 4.0 and t3.at(1, 0, 2) == 14.0);
+    array<double> t2{3, 2};
+    t2.fill(7.0); t2.at(2, 1) = -1.0;
+    array<double> copy(t2);
+    copy.at(0, 0) = 0.0;
+    assert(t2.at(0, 0) == 7.0 and copy.at(2, 1) == -1.0 and array<double>().get_rank() == 0);
+
     std::cout << "expression_algebra: ok" << std::endl;
   } catch (const std::string& e) {
     std::cerr << "expression_algebra: " << e << std::endl;

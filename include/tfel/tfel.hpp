@@ -75,7 +75,17 @@ public:
   const T& at(std::size_t i) const { return data[i]; }
   T& at(std::size_t i, std::size_t j) { return data[i * size[1] + j]; }
   const T& at(std::size_t i, std::size_t j) const { return data[i * size[1] + j]; }
+  // any rank, row-major (spikes array.hpp: at(i, j, k, ...))
+  template <typename... more_t>
+  T& at(std::size_t i, std::size_t j, std::size_t k, more_t... more) { return data[offset({i, j, k, static_cast<std::size_t>(more)...})]; }
+  template <typename... more_t>
+  const T& at(std::size_t i, std::size_t j, std::size_t k, more_t... more) const { return data[offset({i, j, k, static_cast<std::size_t>(more)...})]; }
 private:
+  std::size_t offset(std::initializer_list<std::size_t> idx) const {
+    std::size_t o(0), d(0);
+    for (std::size_t i : idx) { o = o * size[d] + i; ++d; }
+    return o;
+  }
   std::size_t count() const { std::size_t n(1); for (auto s : size) n *= s; return size.empty() ? 0 : n; }
   std::vector<std::size_t> size;
   std::vector<T> data;
