@@ -296,6 +296,17 @@ def gmres_ilu(rowptr, colind, val, b, restart=1000, levels=2, rtol=1e-8, atol=1e
     return x, its, rn.value
 
 
+def iluk_pattern(rowptr, colind, levels):
+    """(rowptr, colind) of the ILU(levels) factors (sequential row-merge, sum rule)"""
+    rowptr = _i32(rowptr); colind = _i32(colind)
+    n = rowptr.shape[0] - 1
+    out_rp = np.zeros(n + 1, dtype=np.int32)
+    out_ci = C.POINTER(C.c_int)()
+    lib().orc_iluk_pattern.restype = C.c_size_t
+    nnz = lib().orc_iluk_pattern(n, _p(rowptr, C.c_int), _p(colind, C.c_int), int(levels), _p(out_rp, C.c_int), C.byref(out_ci))
+    return out_rp, _take(out_ci, nnz, np.int32)
+
+
 def ilu0(rowptr, colind, val):
     rowptr = _i32(rowptr); colind = _i32(colind); val = _f64(val)
     lu = np.zeros_like(val)

@@ -925,6 +925,8 @@ static int ilu_build(int n, const int* rowptr, const int* colind, const double* 
   int* w_next = (int*)malloc(sizeof(int) * ((size_t)n + 1));  /* sorted linked list over columns */
   for (int i = 0; i < n; ++i) w_lev[i] = -1;
   for (int i = 0; i < n; ++i) {
+    /* row i starts here; known before the merge so that the U part of row i - 1 ends at the right place */
+    f->rowptr[i] = (int)nnz;
     /* load row i */
     int head = n; /* sentinel */
     int prev = -1;
@@ -1013,6 +1015,22 @@ static void ilu_solve(const ilu_t* f, const double* b, double* x) {
     for (int e = f->diag[i] + 1; e < f->rowptr[i + 1]; ++e) acc -= f->lu[e] * x[f->colind[e]];
     x[i] = acc / f->lu[f->diag[i]];
   }
+}
+
+/* pattern of ILU(levels) (row-merge with the sum rule lev = lev_ik + lev_kj + 1, entries above `levels` dropped):
+ * out_rowptr has n + 1 entries, *out_colind is malloc'ed (orc_free). Returns the number of stored entries. */
+size_t orc_iluk_pattern(int n, const int* rowptr, const int* colind, int levels, int* out_rowptr, int** out_colind) {
+  ilu_t f;
+  double* ones = (double*)malloc(sizeof(double) * ((size_t)rowptr[n] + 1));
+  for (int e = 0; e < rowptr[n]; ++e) ones[e] = 1.0;
+  ilu_build(n, rowptr, colind, ones, levels, &f);
+  free(ones);
+  const size_t nnz = (size_t)f.rowptr[n];
+  memcpy(out_rowptr, f.rowptr, sizeof(int) * ((size_t)n + 1));
+  *out_colind = (int*)malloc(sizeof(int) * (nnz + 1));
+  memcpy(*out_colind, f.colind, sizeof(int) * nnz);
+  ilu_free(&f);
+  return nnz;
 }
 
 int orc_ilu0(int n, const int* rowptr, const int* colind, const double* val, double* lu) {
