@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <functional>
 #include <initializer_list>
+#include <iomanip>
 #include <iostream>
 #include <map>
 #include <memory>
@@ -848,6 +849,14 @@ struct gmres_ilu0 : krylov { explicit gmres_ilu0(const dictionary& p) : krylov(p
 struct gmres_jacobi : krylov { explicit gmres_jacobi(const dictionary& p) : krylov(p, TFELCU_METHOD_GMRES, TFELCU_PC_JACOBI) {} };
 
 }  // namespace cuda
+
+#ifdef TFEL_CUDA_AS_PETSC
+// Opt-in (define TFEL_CUDA_AS_PETSC before including this header): programs written against the reference keep their
+// `solver::petsc::gmres_ilu s(p);` line (solver.hpp:122-210) and get the device GMRES(restart) with modified Gram-Schmidt
+// and ILU(0) -- same required dictionary keys, so a program that passes "abstol" instead of "atol" throws here exactly
+// as it does in the reference. The factorisation level differs (ilufill is accepted, ILU(0) is used).
+namespace petsc { using gmres_ilu = cuda::gmres_ilu0; }
+#endif
 }  // namespace solver
 
 // ---- forms (bilinear_form.hpp, linear_form.hpp, composite_*_form.hpp) -------------------------------------------------
@@ -1014,5 +1023,9 @@ lagrange(const std::function<double(const double*)>& fun, const finite_element_s
 }
 
 }  // namespace projector
+
+// the output side (mesh_data, to_mesh_vertex_data / to_mesh_cell_data, exporter::*): part of the umbrella header like
+// the reference's export.hpp / mesh_data.hpp
+#include "tfel_export.hpp"
 
 #endif  // TFEL_TFEL_HPP

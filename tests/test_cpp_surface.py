@@ -22,6 +22,37 @@ def test_reference_programs_compile_against_the_cuda_headers():
         assert os.path.exists(os.path.join(BIN, name))
 
 
+REFERENCE = "/root/reference"
+# programs of the reference that compile UNCHANGED against include/tfel/tfel.hpp (with TFEL_CUDA_AS_PETSC their
+# `solver::petsc::gmres_ilu s(p);` line runs the device GMRES + ILU(0))
+UNCHANGED_REFERENCE_PROGRAMS = ("laplacian_transient", "tetrahedron_cube", "stokes_2d_p2_p1", "navier_stokes_2d_p2_p1",
+                                "fe_derivative_form", "quadrature_2d", "l2_p1_bubble_projection")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "test")), reason="needs the reference tree (build container only)")
+@pytest.mark.parametrize("name", UNCHANGED_REFERENCE_PROGRAMS)
+def test_reference_test_programs_compile_unchanged(name, tmp_path):
+    """Source compatibility of the drop-in surface, checked on the reference's own test programs: the file is copied
+    (into a scratch directory, never into the repo) next to forwarding headers src/core/*.hpp -> <tfel/tfel.hpp>, and
+    has to pass g++ -std=c++14 -fsyntax-only as it is."""
+    import shutil
+    core = tmp_path / "src" / "core"
+    core.mkdir(parents=True)
+    for h in os.listdir(os.path.join(REFERENCE, "src", "core")):
+        if h.endswith(".hpp"):
+            (core / h).write_text("#include <tfel/tfel.hpp>\n")
+    (tmp_path / "spikes").mkdir()
+    (tmp_path / "spikes" / "timer.hpp").write_text(
+        "#pragma once\n#include <chrono>\nclass timer { public: timer() : t0(std::chrono::steady_clock::now()) {}\n"
+        "  double tic() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }\n"
+        "private: std::chrono::steady_clock::time_point t0; };\n")
+    (tmp_path / "test").mkdir()
+    shutil.copy(os.path.join(REFERENCE, "test", name + ".cpp"), str(tmp_path / "test" / (name + ".cpp")))
+    r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-w", "-DTFEL_CUDA_AS_PETSC", "-I", os.path.join(ROOT, "include"),
+                        "-I", str(tmp_path), str(tmp_path / "test" / (name + ".cpp"))], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
 EXPORT_GOLDEN = os.path.join(ROOT, "tests", "golden", "export")   # written by the UNMODIFIED reference (oracle/ref_driver.cpp)
 
 
