@@ -295,6 +295,16 @@ public:
     const finite_element_space& get_finite_element_space() const { return *fes; }
     const array<double>& get_coefficients() const { return coefficients; }
     // coefficient-wise algebra of fes.hpp:314-359 (discrete functions of one space are a vector space)
+    // fes.hpp:247-255: sum_n coefficients[dof(k, n)] phi_n(x_hat) (the dof map is fetched from the device once per space)
+    double evaluate(std::size_t k, const double* x_hat) const {
+      const array<unsigned int>& dm(fes->cached_dof_map());
+      double table[10 * 4];
+      int nd(0);
+      tfel_cuda::ck(tfelcu_fe_tabulate(cell_type::dim, fe_t::id, x_hat, table, &nd));
+      double value(0.0);
+      for (int n(0); n < nd; ++n) value += coefficients.at(dm.at(k, n)) * table[n * (cell_type::dim + 1)];
+      return value;
+    }
     element& transform(const std::function<double(double)>& f) {
       for (std::size_t i(0); i < coefficients.get_element_number(); ++i) coefficients.at(i) = f(coefficients.at(i));
       return *this;
@@ -371,8 +381,14 @@ public:
     add_dirichlet_boundary(dm, std::function<double(const double*)>(f));
   }
 
+  std::size_t get_dof(std::size_t k, std::size_t n) const { return cached_dof_map().at(k, n); }   // fes.hpp:151-153
+  const array<unsigned int>& cached_dof_map() const {
+    if (dof_map_cache.get_rank() == 0) dof_map_cache = get_dof_map();
+    return dof_map_cache;
+  }
   tfelcu_fes* handle() const { return h; }
 private:
+  mutable array<unsigned int> dof_map_cache;
   template <typename sm_t>
   std::size_t select(const sm_t& dm) {
     std::size_t n(0);

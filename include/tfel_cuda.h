@@ -185,6 +185,9 @@ int tfelcu_fes_dirichlet_get(const tfelcu_fes* fes, uint32_t* dofs, double* valu
 /* output side (fes.hpp:464-504). to_mesh_vertex_data: out[V], out[cells[k][n]] = coefficients[dof(k, n)] for the vertex
  * dofs of every cell (0 for vertices no cell uses); to_mesh_cell_data: out[K], the value of the discrete function at the
  * barycentre of every cell (element::evaluate, fes.hpp:247-255). coefficients / out: host or device. */
+/* reference-element basis of a finite element (fe.hpp:260-654: phi / dphi), host only: out[i][0] = phi_i(x_hat),
+ * out[i][1 + s] = d phi_i / d x_hat_s for the n_dof_per_element basis functions; returns their number in *n_dof */
+int tfelcu_fe_tabulate(int dim, int fe, const double* x_hat, double* out, int* n_dof);
 int tfelcu_fes_vertex_values(const tfelcu_fes* fes, const double* coefficients, double* out);
 int tfelcu_fes_cell_values(const tfelcu_fes* fes, const double* coefficients, double* out);
 

@@ -28,6 +28,16 @@ class TfelCudaError(RuntimeError):
     pass
 
 
+def fe_tabulate(dim, fe, x_hat):
+    """reference-element basis values and gradients at one point (host only): [nd][dim + 1]"""
+    x = np.ascontiguousarray(x_hat, dtype=np.float64)
+    out = np.zeros((10, dim + 1))
+    n = C.c_int()
+    _ck(lib().tfelcu_fe_tabulate(int(dim), FE[fe] if isinstance(fe, str) else int(fe), x.ctypes.data_as(C.c_void_p),
+                                 out.ctypes.data_as(C.c_void_p), C.byref(n)))
+    return out[:n.value].copy()
+
+
 class Op(C.Structure):
     _fields_ = [("op", C.c_int32), ("pad", C.c_int32), ("imm", C.c_double)]
 
@@ -71,7 +81,7 @@ SYMBOLS = [
     "tfelcu_fes_create", "tfelcu_fes_destroy", "tfelcu_fes_info", "tfelcu_fes_kind_offsets", "tfelcu_fes_download_dof_map",
     "tfelcu_fes_download_g2l", "tfelcu_fes_dof_coordinates", "tfelcu_fes_boundary_dofs",
     "tfelcu_fes_boundary_dofs_get", "tfelcu_fes_add_dirichlet", "tfelcu_fes_add_dirichlet_const",
-    "tfelcu_fes_dirichlet_count", "tfelcu_fes_dirichlet_get", "tfelcu_fes_vertex_values", "tfelcu_fes_cell_values",
+    "tfelcu_fes_dirichlet_count", "tfelcu_fes_dirichlet_get", "tfelcu_fes_vertex_values", "tfelcu_fes_cell_values", "tfelcu_fe_tabulate",
     "tfelcu_matrix_create", "tfelcu_matrix_create_rows", "tfelcu_matrix_local_rows", "tfelcu_matrix_destroy", "tfelcu_matrix_clear", "tfelcu_matrix_info",
     "tfelcu_matrix_set_scatter", "tfelcu_matrix_assemble", "tfelcu_matrix_download_csr",
     "tfelcu_matrix_color_count",

@@ -439,6 +439,16 @@ static void fes_values(const tfelcu_fes* fes, const double* coefficients, double
   if (!dev_out) copy_out(ctx, out, d_out, n_out); else ctx->sync();
 }
 
+int tfelcu_fe_tabulate(int dim, int fe, const double* x_hat, double* out, int* n_dof) {
+  return guarded([&] {
+    TFELCU_REQUIRE(x_hat && out, "null pointer");
+    TFELCU_REQUIRE(dim == 2 || dim == 3, "dimension must be 2 or 3");
+    TFELCU_REQUIRE(fe == TFELCU_FE_P1 || fe == TFELCU_FE_P1_BUBBLE || fe == TFELCU_FE_P2, "unknown finite element id");
+    tfelcu::fe_eval_hat(dim, fe, x_hat, out);
+    if (n_dof) *n_dof = tfelcu::fe_ndof(dim, fe);
+  });
+}
+
 int tfelcu_fes_vertex_values(const tfelcu_fes* fes, const double* coefficients, double* out) {
   return guarded([&] { fes_values(fes, coefficients, out, true); });
 }
