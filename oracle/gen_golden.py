@@ -66,5 +66,17 @@ def main():
             print(stem, "nnz", meta.get("nnz"), "its", meta.get("solve_its"), "rnorm", meta.get("solve_rnorm"))
 
 
+def export_fixtures():
+    """tests/golden/export/*: the files the reference's own exporters write (export.hpp) for nodal interpolants on small
+    meshes; the case files embed the relative prefix "export/", so the reference runs with tests/golden as its cwd."""
+    import shutil
+    out = os.path.join(GOLDEN, "export")
+    shutil.rmtree(out, ignore_errors=True)
+    os.makedirs(out)
+    subprocess.check_call([REF, "--problem", "export", "--n", "3", "--out", "export"], cwd=GOLDEN)
+    print("export:", len(os.listdir(out)), "files")
+
+
 if __name__ == "__main__":
     main()
+    export_fixtures()
