@@ -478,3 +478,35 @@ def test_empty_and_tiny_inputs(ctx):
     assert rep["converged"] == 1 and np.allclose(x, 1.5)
     assert capi.integrate(m, "qf5pT", [dict(c=2.0)]) == pytest.approx(1.0)   # 2 |K| = 1
     s.close(); s2.close(); a.close(); b.close(); sp.close(); m.close()
+
+
+def test_beyond_2_30_stored_entries(ctx):
+    """configs[3] at its full size (Stokes P2-P2-P1, n = 2048: 8 388 608 cells, 37 769 219 dofs, 1 119 416 369 stored
+    entries, i.e. CSR positions beyond 2^30 where `lo + hi` of an int32 binary search overflows -- the bug this size
+    exposed): structure, assembly of A and b, and the two SpMV kernels against each other on the assembled operator.
+    The same steps as `tools/stokes_probe.py --assembly-only --spmv-check 2048` (about 3 s on a B200)."""
+    import ctypes as C
+    from tfel_b200 import capi
+    free_b, _ = __import__("torch").cuda.mem_get_info()
+    if free_b < 100e9:
+        pytest.skip("needs ~70 GB of device memory")
+    n = 2048
+    B = cuda_runner.build(ctx, problems.stokes(n))
+    try:
+        assert B.mesh.n_cells == 2 * n * n and B.matrix.n_rows == 2 * (2 * n + 1) ** 2 + (n + 1) ** 2
+        assert B.matrix.nnz == 1119416369 and B.matrix.nnz > 2 ** 30
+        cuda_runner.assemble(B)
+        rowptr = np.zeros(B.matrix.n_rows + 1, dtype=np.int32)
+        assert capi.lib().tfelcu_matrix_download_csr(B.matrix.h, rowptr.ctypes.data_as(C.c_void_p), None, None) == 0
+        assert rowptr[0] == 0 and rowptr[-1] == B.matrix.nnz and np.all(np.diff(rowptr) >= 1)
+        x = np.random.RandomState(3).standard_normal(B.matrix.n_rows)
+        ys = []
+        for kern in ("vector", "stream"):
+            s = capi.Solver(ctx, method="gmres", precond="none", spmv=kern)
+            s.set_operator(B.matrix)
+            ys.append(s.spmv(x))
+            s.close()
+        assert np.all(np.isfinite(ys[0])) and np.abs(ys[0]).max() > 0.0
+        assert np.abs(ys[0] - ys[1]).max() <= 1e-13 * np.abs(ys[0]).max()
+    finally:
+        cuda_runner.close(B)
