@@ -487,11 +487,13 @@ def test_beyond_2_30_stored_entries(ctx):
     The same steps as `tools/stokes_probe.py --assembly-only --spmv-check 2048` (about 3 s on a B200)."""
     import ctypes as C
     from tfel_b200 import capi
-    free_b, _ = __import__("torch").cuda.mem_get_info()
-    if free_b < 100e9:
-        pytest.skip("needs ~70 GB of device memory")
     n = 2048
-    B = cuda_runner.build(ctx, problems.stokes(n))
+    try:
+        B = cuda_runner.build(ctx, problems.stokes(n))
+    except capi.TfelCudaError as e:   # ~70 GB of device memory during the pattern build
+        if "memory" in str(e):
+            pytest.skip("not enough device memory for the full-size Stokes pattern")
+        raise
     try:
         assert B.mesh.n_cells == 2 * n * n and B.matrix.n_rows == 2 * (2 * n + 1) ** 2 + (n + 1) ** 2
         assert B.matrix.nnz == 1119416369 and B.matrix.nnz > 2 ** 30
