@@ -120,19 +120,6 @@ __device__ __forceinline__ double term_coefficient(const DevTerm& t, const doubl
   return c;
 }
 
-// reference-gradient weights of "derivative d of a basis function": D^d phi = sum_a T[a] hat[a]
-template <int DIM>
-__device__ __forceinline__ void pullback(int d, const CellGeom<DIM>& g, double (&T)[DIM + 1]) {
-  T[0] = d == 0 ? 1.0 : 0.0;
-#pragma unroll
-  for (int s = 0; s < DIM; ++s) {
-    double v = 0.0;
-#pragma unroll
-    for (int dd = 0; dd < DIM; ++dd) v = (d == dd + 1) ? g.jmt[dd][s] : v;
-    T[1 + s] = v;
-  }
-}
-
 // row i of the element matrix of cell k (without the |K| factor): acc[j], j = 0..ND_TR-1
 template <int DIM, int ND_TE, int ND_TR, bool CONST_COEF>
 __device__ __forceinline__ void element_row(const FormDev& F, const double* sm, size_t k, int i,
