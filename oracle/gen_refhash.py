@@ -21,7 +21,12 @@ CASES = [("poisson_p1_n1024", ["--problem", "poisson", "--fe", "p1", "--n", "102
          ("poisson_p1_n2048", ["--problem", "poisson", "--fe", "p1", "--n", "2048"]),
          ("poisson_p1_n4096", ["--problem", "poisson", "--fe", "p1", "--n", "4096"]),
          ("stokes_n256", ["--problem", "stokes", "--n", "256"]),
-         ("tet_p1_n48", ["--problem", "tet", "--fe", "p1", "--n", "48"])]
+         ("tet_p1_n48", ["--problem", "tet", "--fe", "p1", "--n", "48"]),
+         # a1 / a2 / a3 / a4 alone (vertices, cells, geometry, face neighbours, boundary submesh): minutes, not hours
+         ("mesh_square_n1024", ["--problem", "mesh", "--n", "1024"]),
+         ("mesh_square_n4096", ["--problem", "mesh", "--n", "4096"]),
+         ("mesh_cube_n48", ["--problem", "meshcube", "--n", "48"]),
+         ("mesh_cube_n142", ["--problem", "meshcube", "--n", "142"])]
 
 if __name__ == "__main__":
     for name, args in CASES:

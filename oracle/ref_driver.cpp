@@ -696,6 +696,22 @@ namespace {
 }
 
 namespace {
+  // a1 / a2 / a4 at full size: vertices, cells, geometry, face neighbours and the boundary submesh of the generators
+  template<typename cell_type>
+  void run_mesh(const run_options& opt, mesh<cell_type>&& generated) {
+    dumper dmp(opt.out, opt.hash_only);
+    auto t0(clk::now());
+    fe_mesh<cell_type> m(std::move(generated));
+    dmp.note_num("t_fe_mesh_s", seconds_since(t0));
+    t0 = clk::now();
+    submesh<cell_type> dm(m.get_boundary_submesh());
+    dmp.note_num("t_boundary_s", seconds_since(t0));
+    dump_mesh(dmp, m);
+    dump_submesh(dmp, "boundary", dm);
+    dmp.note_num("n_cells", m.get_cell_number());
+    finish(dmp, opt);
+  }
+
   double export_g(const double* x) { return 1.0 + x[0] + 2.0 * x[1] + x[0] * x[1]; }
   double export_h(const double* x) { return x[0] * x[0] - 0.5 * x[1]; }
   double export_t(const double* x) { return 1.0 + x[0] - x[1] + 2.0 * x[2]; }
@@ -769,6 +785,8 @@ int main(int argc, char* argv[]) {
     else if (opt.problem == "laplace2") run_laplace2(opt);
     else if (opt.problem == "tables") run_tables(opt);
     else if (opt.problem == "export") run_export(opt);
+    else if (opt.problem == "mesh") run_mesh<cell::triangle>(opt, gen_square_mesh(1.0, 1.0, opt.n, opt.n));
+    else if (opt.problem == "meshcube") run_mesh<cell::tetrahedron>(opt, gen_cube_mesh(1.0, 1.0, 1.0, opt.n, opt.n, opt.n));
     else throw std::string("unknown problem");
   } catch (const std::string& e) {
     std::cerr << "ref_driver: " << e << std::endl;

@@ -377,6 +377,28 @@ def test_full_size_fingerprints_match_the_reference(ctx, name, problem, golden_d
         cuda_runner.close(got["_built"])
 
 
+@pytest.mark.parametrize("name,dim,n", [("mesh_square_n1024", 2, 1024), ("mesh_square_n4096", 2, 4096),
+                                        ("mesh_cube_n48", 3, 48), ("mesh_cube_n142", 3, 142)])
+def test_full_size_mesh_fingerprints_match_the_reference(ctx, name, dim, n, golden_dir):
+    """a1-a4 on the device at the sizes of configs[1] (n = 4096 square) and configs[2] (n = 142 cube): vertices, cells, |K|,
+    J^{-T}, face neighbours and the boundary submesh hash to what the UNMODIFIED reference printed
+    (tests/golden/refhash_mesh_*.json, oracle/gen_refhash.py)."""
+    import json
+    import refhash
+    from tfel_b200 import capi
+    ref = json.load(open(os.path.join(golden_dir, "refhash_%s.json" % name)))
+    m = capi.Mesh.square(ctx, 1.0, 1.0, n, n) if dim == 2 else capi.Mesh.cube(ctx, 1.0, 1.0, 1.0, n, n, n)
+    try:
+        got = {}
+        got["vertices"], got["cells"] = m.download()
+        got["cell_volume"], got["jmt"] = m.geometry()
+        got["boundary_cells"], got["boundary_parent_cell"], got["boundary_parent_subdomain"] = m.boundary()
+        got["cell_neighbours"] = m.neighbours()
+        assert refhash.check(got, ref, None) == 8
+    finally:
+        m.close()
+
+
 def test_quadrature_points_and_kind_offsets(ctx):
     """tfelcu_mesh_quadrature_points (cell.hpp:456-468) against the oracle; entity-kind offsets of fes.hpp:33-72."""
     from tfel_b200 import capi
