@@ -819,10 +819,12 @@ public:
 namespace cuda {
 
 // Krylov solvers on the B200, same dictionary keys as solver::petsc::gmres_ilu (solver.hpp:125-133):
-// maxits, restart, rtol, atol, dtol, ilufill (ilufill is accepted for compatibility; the factorisation is ILU(0))
+// maxits, restart, rtol, atol, dtol, ilufill. ilufill is the level of fill of the incomplete factorisation
+// (PCFactorSetLevels, solver.hpp:163) and is honoured by the ILU-preconditioned solvers; fixed_ilu_levels >= 0 pins it
+// (gmres_ilu0) whatever the dictionary says.
 class krylov : public basic_solver {
 public:
-  krylov(const dictionary& params, int method, int precond, int block_size = 0) {
+  krylov(const dictionary& params, int method, int precond, int block_size = 0, int fixed_ilu_levels = -1) {
     if (not params.keys_exist({"maxits", "restart", "rtol", "atol", "dtol", "ilufill"}))
       throw std::string("solver::cuda: missing key(s) in the dictionary");   // solver.hpp:125-133
     tfelcu_solver_params p;
@@ -830,6 +832,10 @@ public:
     p.maxits = params.get<unsigned>("maxits"); p.restart = params.get<unsigned>("restart");
     p.rtol = params.get<double>("rtol"); p.atol = params.get<double>("atol"); p.dtol = params.get<double>("dtol");
     p.block_size = block_size; p.check_every = 0; p.spmv_kernel = TFELCU_SPMV_AUTO; p.profile_every = 0;
+    p.ilu_levels = 0;
+    if (precond == TFELCU_PC_ILU)
+      p.ilu_levels = fixed_ilu_levels >= 0 ? fixed_ilu_levels : static_cast<int>(params.get<unsigned>("ilufill"));
+    p.pad = 0;
     tfel_cuda::ck(tfelcu_solver_create(tfel_cuda::context(), &p, &h));
   }
   krylov(const krylov&) = delete;
@@ -850,7 +856,11 @@ public:
   static void fill(dictionary& report, const tfelcu_solver_report& r) {
     report.set("its", static_cast<unsigned>(r.its)).set("rnorm", r.rnorm).set("bnorm", r.bnorm)
           .set("converged", r.converged == 1).set("reason", static_cast<int>(r.converged))
-          .set("t_setup_s", r.t_setup_s).set("t_solve_s", r.t_solve_s);
+          .set("t_setup_s", r.t_setup_s).set("t_solve_s", r.t_solve_s)
+          .set("t_precond_setup_s", r.t_precond_setup_s).set("t_symbolic_s", r.t_symbolic_s)
+          .set("restart_used", static_cast<unsigned>(r.restart_used))
+          .set("ilufill_used", static_cast<int>(r.ilu_levels)).set("ilu_nnz", static_cast<double>(r.ilu_nnz))
+          .set("ilu_zero_pivot_row", static_cast<int>(r.ilu_zero_pivot_row));
   }
 private:
   tfelcu_solver* h = nullptr;
@@ -861,7 +871,12 @@ struct cg_jacobi : krylov { explicit cg_jacobi(const dictionary& p) : krylov(p, 
 struct cg_block_jacobi : krylov {
   explicit cg_block_jacobi(const dictionary& p, int block_size = 4) : krylov(p, TFELCU_METHOD_CG, TFELCU_PC_BLOCK_JACOBI, block_size) {}
 };
-struct gmres_ilu0 : krylov { explicit gmres_ilu0(const dictionary& p) : krylov(p, TFELCU_METHOD_GMRES, TFELCU_PC_ILU0) {} };
+// GMRES(restart) with modified Gram-Schmidt, left-preconditioned by ILU(ilufill) in natural ordering: the device
+// counterpart of solver::petsc::gmres_ilu (solver.hpp:139-163)
+struct gmres_ilu : krylov { explicit gmres_ilu(const dictionary& p) : krylov(p, TFELCU_METHOD_GMRES, TFELCU_PC_ILU) {} };
+// the same with the level of fill pinned to 0 whatever "ilufill" says
+struct gmres_ilu0 : krylov { explicit gmres_ilu0(const dictionary& p) : krylov(p, TFELCU_METHOD_GMRES, TFELCU_PC_ILU, 0, 0) {} };
+struct cg_ilu : krylov { explicit cg_ilu(const dictionary& p) : krylov(p, TFELCU_METHOD_CG, TFELCU_PC_ILU) {} };
 struct gmres_jacobi : krylov { explicit gmres_jacobi(const dictionary& p) : krylov(p, TFELCU_METHOD_GMRES, TFELCU_PC_JACOBI) {} };
 
 }  // namespace cuda
@@ -869,9 +884,9 @@ struct gmres_jacobi : krylov { explicit gmres_jacobi(const dictionary& p) : kryl
 #ifdef TFEL_CUDA_AS_PETSC
 // Opt-in (define TFEL_CUDA_AS_PETSC before including this header): programs written against the reference keep their
 // `solver::petsc::gmres_ilu s(p);` line (solver.hpp:122-210) and get the device GMRES(restart) with modified Gram-Schmidt
-// and ILU(0) -- same required dictionary keys, so a program that passes "abstol" instead of "atol" throws here exactly
-// as it does in the reference. The factorisation level differs (ilufill is accepted, ILU(0) is used).
-namespace petsc { using gmres_ilu = cuda::gmres_ilu0; }
+// and ILU(ilufill) -- same required dictionary keys, so a program that passes "abstol" instead of "atol" throws here
+// exactly as it does in the reference, and the same level of fill as PCFactorSetLevels(pc, ilufill).
+namespace petsc { using gmres_ilu = cuda::gmres_ilu; }
 #endif
 }  // namespace solver
 

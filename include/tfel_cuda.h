@@ -81,7 +81,10 @@ typedef struct {
 } tfelcu_term;
 
 enum { TFELCU_METHOD_CG = 1, TFELCU_METHOD_GMRES = 2 };
-enum { TFELCU_PC_NONE = 0, TFELCU_PC_JACOBI = 1, TFELCU_PC_BLOCK_JACOBI = 2, TFELCU_PC_ILU0 = 3 };
+/* TFELCU_PC_ILU: incomplete LU in natural ordering with level of fill tfelcu_solver_params::ilu_levels -- PCILU +
+ * PCFactorSetLevels(pc, ilufill) of the reference (solver.hpp:162-163). TFELCU_PC_ILU0 is the same value: ilu_levels = 0
+ * (the default of a zero-initialised parameter block) is ILU(0). */
+enum { TFELCU_PC_NONE = 0, TFELCU_PC_JACOBI = 1, TFELCU_PC_BLOCK_JACOBI = 2, TFELCU_PC_ILU0 = 3, TFELCU_PC_ILU = 3 };
 /* Scatter strategies of the assembly, all free of atomics and bitwise reproducible. ROW_GATHER: one thread per row
  * recomputes its row of every incident element matrix. COLORED: one launch per colour of the cell conflict graph.
  * PATCH: rows grouped into compact patches of the mesh (quadtree / octree leaves of the dof coordinates); one CTA
@@ -100,18 +103,27 @@ typedef struct {
   int32_t spmv_kernel;         /* TFELCU_SPMV_* */
   int32_t profile_every;       /* > 0: bracket the SpMV launch of every profile_every-th iteration with CUDA events
                                   (at most 512 samples per solve) and report their average duration */
+  int32_t ilu_levels;          /* TFELCU_PC_ILU: level of fill, the dictionary's "ilufill" (solver.hpp:163); 0 = ILU(0) */
+  int32_t pad;
 } tfelcu_solver_params;
 
 typedef struct {
   uint32_t its;
-  int32_t converged;           /* 1 converged, 0 maxits reached, -1 diverged (dtol), -2 breakdown */
+  int32_t converged;           /* 1 converged, 0 maxits reached, -1 diverged (dtol), -2 breakdown,
+                                  -3 a peer rank did not answer in time (distributed solves; the context falls back to NCCL) */
   double rnorm, bnorm;         /* norm the convergence test used */
   double t_setup_s, t_solve_s; /* device time, CUDA events */
   uint64_t n_launches;         /* kernels launched by the solve */
   uint64_t n_spmv;
   double spmv_avg_ms;          /* profile_every > 0: average duration of the sampled SpMV launches */
   uint32_t spmv_samples;
-  uint32_t pad;
+  uint32_t restart_used;       /* GMRES: restart length actually used (the dictionary's, bounded by maxits and by the device
+                                  memory the Krylov basis may take); smaller than requested => a warning on stderr */
+  uint64_t ilu_nnz;            /* TFELCU_PC_ILU: stored entries of the factors (0 otherwise) */
+  int32_t ilu_levels;          /* level of fill the factorisation used */
+  int32_t ilu_zero_pivot_row;  /* first row whose pivot is exactly 0, or -1 */
+  double t_precond_setup_s;    /* part of t_setup_s spent building the preconditioner */
+  double t_symbolic_s;         /* part of it spent in the symbolic phase (0 when the cached pattern was reused) */
 } tfelcu_solver_report;
 
 /* ---- context ------------------------------------------------------------------------ */
@@ -248,7 +260,11 @@ int tfelcu_mesh_quadrature_points(tfelcu_mesh* mesh, int quad, double* xq);
 
 int tfelcu_solver_create(tfelcu_ctx* ctx, const tfelcu_solver_params* params, tfelcu_solver** s);
 int tfelcu_solver_destroy(tfelcu_solver* s);
-/* set_operator(const sparse_matrix&): device-resident matrix of a bilinear form (zero copy) ... */
+/* set_operator(const sparse_matrix&): like the reference (solver.cpp:71-96: the matrix is COPIED into the solver's own
+ * storage), the solver keeps a device copy of the rows this process owns, so the form may be cleared, re-assembled or
+ * destroyed afterwards; a later set_operator on a form with the same pattern only copies the values and reuses the
+ * SpMV plan and the symbolic phase of ILU(k) (Newton / time loops, test/navier_stokes_2d_p2_p1.cpp:292-438).
+ * tfelcu_matrix_solve below works on the form's arrays without a copy and detaches the solver on return. */
 int tfelcu_solver_set_operator(tfelcu_solver* s, tfelcu_matrix* m);
 /* ... or a host CSR (what solver.cpp:71-96 builds from the std::map) */
 int tfelcu_solver_set_operator_csr(tfelcu_solver* s, size_t n, const int32_t* rowptr,
@@ -267,6 +283,11 @@ int tfelcu_matrix_make_rhs(const tfelcu_matrix* m, const tfelcu_vector* b, doubl
 int tfelcu_solver_gather(tfelcu_solver* s, const double* x_local, double* x_global);
 int tfelcu_solver_spmv(tfelcu_solver* s, const double* x, double* y);
 int tfelcu_solver_spmv_bench(tfelcu_solver* s, int reps, double* avg_ms, double* algorithmic_bytes);
+/* TFELCU_PC_ILU, for parity checks: size of the factors, then the factors themselves -- rows ascending, columns
+ * ascending, L (unit diagonal not stored) left of the diagonal, U from the diagonal on; host buffers rowptr[n + 1],
+ * colind[nnz], lu[nnz], any of which may be NULL. Same layout as PETSc's / the oracle's row-merge result. */
+int tfelcu_solver_ilu_info(const tfelcu_solver* s, size_t* n, size_t* nnz, int* levels);
+int tfelcu_solver_ilu_download(const tfelcu_solver* s, int64_t* rowptr, int32_t* colind, double* lu);
 
 #ifdef __cplusplus
 }

@@ -307,6 +307,18 @@ def iluk_pattern(rowptr, colind, levels):
     return out_rp, _take(out_ci, nnz, np.int32)
 
 
+def iluk(rowptr, colind, val, levels):
+    """(rowptr, colind, lu) of the ILU(levels) factors: L (unit diagonal not stored) left of the diagonal, U from it on"""
+    rowptr = _i32(rowptr); colind = _i32(colind); val = _f64(val)
+    n = rowptr.shape[0] - 1
+    out_rp = np.zeros(n + 1, dtype=np.int32)
+    out_ci = C.POINTER(C.c_int)(); out_lu = C.POINTER(C.c_double)()
+    lib().orc_iluk.restype = C.c_size_t
+    nnz = lib().orc_iluk(n, _p(rowptr, C.c_int), _p(colind, C.c_int), _p(val, C.c_double), int(levels),
+                         _p(out_rp, C.c_int), C.byref(out_ci), C.byref(out_lu))
+    return out_rp, _take(out_ci, nnz, np.int32), _take(out_lu, nnz, np.float64)
+
+
 def ilu0(rowptr, colind, val):
     rowptr = _i32(rowptr); colind = _i32(colind); val = _f64(val)
     lu = np.zeros_like(val)

@@ -1033,6 +1033,22 @@ size_t orc_iluk_pattern(int n, const int* rowptr, const int* colind, int levels,
   return nnz;
 }
 
+/* ILU(levels): pattern and factors together (what PCILU + PCFactorSetLevels builds, solver.hpp:162-163). out_rowptr has
+ * n + 1 entries; *out_colind / *out_lu are malloc'ed (orc_free). Returns the number of stored entries. */
+size_t orc_iluk(int n, const int* rowptr, const int* colind, const double* val, int levels, int* out_rowptr,
+                int** out_colind, double** out_lu) {
+  ilu_t f;
+  ilu_build(n, rowptr, colind, val, levels, &f);
+  const size_t nnz = (size_t)f.rowptr[n];
+  memcpy(out_rowptr, f.rowptr, sizeof(int) * ((size_t)n + 1));
+  *out_colind = (int*)malloc(sizeof(int) * (nnz + 1));
+  *out_lu = (double*)malloc(sizeof(double) * (nnz + 1));
+  memcpy(*out_colind, f.colind, sizeof(int) * nnz);
+  memcpy(*out_lu, f.lu, sizeof(double) * nnz);
+  ilu_free(&f);
+  return nnz;
+}
+
 int orc_ilu0(int n, const int* rowptr, const int* colind, const double* val, double* lu) {
   ilu_t f;
   const int st = ilu_build(n, rowptr, colind, val, 0, &f);

@@ -104,6 +104,8 @@ int orc_gmres_ilu(int n, const int* rowptr, const int* colind, const double* val
 /* ILU(0) in place on a copy of val: returns factors in lu[nnz] (unit L below diag, U on/above) */
 int orc_ilu0(int n, const int* rowptr, const int* colind, const double* val, double* lu);
 /* pattern of ILU(levels) as PCFactorSetLevels builds it (solver.hpp:162-163); *out_colind is malloc'ed (orc_free) */
+size_t orc_iluk(int n, const int* rowptr, const int* colind, const double* val, int levels, int* out_rowptr,
+                int** out_colind, double** out_lu);
 size_t orc_iluk_pattern(int n, const int* rowptr, const int* colind, int levels, int* out_rowptr, int** out_colind);
 
 #ifdef __cplusplus

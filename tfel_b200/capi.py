@@ -19,7 +19,7 @@ QUAD = {"qf1pT": 1, "qf2pT": 2, "qf5pT": 3, "qf1pTlump": 4,
         "qfSym35pTet": 17, "qfSym56pTet": 18}
 FACTOR_FIELD, FACTOR_TABLE, FACTOR_PROGRAM = 1, 2, 3
 METHOD = {"cg": 1, "gmres": 2}
-PRECOND = {"none": 0, "jacobi": 1, "block_jacobi": 2, "ilu0": 3}
+PRECOND = {"none": 0, "jacobi": 1, "block_jacobi": 2, "ilu0": 3, "ilu": 3}
 SCATTER = {"rows": 0, "colored": 1, "patch": 2, "auto": 3}
 SPMV = {"auto": 0, "vector": 1, "stream": 2}
 
@@ -57,14 +57,17 @@ class SolverParams(C.Structure):
     _fields_ = [("method", C.c_int32), ("precond", C.c_int32), ("maxits", C.c_uint32),
                 ("restart", C.c_uint32), ("rtol", C.c_double), ("atol", C.c_double),
                 ("dtol", C.c_double), ("block_size", C.c_int32), ("check_every", C.c_int32),
-                ("spmv_kernel", C.c_int32), ("profile_every", C.c_int32)]
+                ("spmv_kernel", C.c_int32), ("profile_every", C.c_int32),
+                ("ilu_levels", C.c_int32), ("pad", C.c_int32)]
 
 
 class SolverReport(C.Structure):
     _fields_ = [("its", C.c_uint32), ("converged", C.c_int32), ("rnorm", C.c_double),
                 ("bnorm", C.c_double), ("t_setup_s", C.c_double), ("t_solve_s", C.c_double),
                 ("n_launches", C.c_uint64), ("n_spmv", C.c_uint64), ("spmv_avg_ms", C.c_double),
-                ("spmv_samples", C.c_uint32), ("pad", C.c_uint32)]
+                ("spmv_samples", C.c_uint32), ("restart_used", C.c_uint32), ("ilu_nnz", C.c_uint64),
+                ("ilu_levels", C.c_int32), ("ilu_zero_pivot_row", C.c_int32), ("t_precond_setup_s", C.c_double),
+                ("t_symbolic_s", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -91,6 +94,7 @@ SYMBOLS = [
     "tfelcu_solver_create", "tfelcu_solver_destroy", "tfelcu_solver_set_operator",
     "tfelcu_solver_set_operator_csr", "tfelcu_solver_solve", "tfelcu_matrix_solve", "tfelcu_matrix_make_rhs",
     "tfelcu_solver_gather", "tfelcu_solver_spmv", "tfelcu_solver_spmv_bench",
+    "tfelcu_solver_ilu_info", "tfelcu_solver_ilu_download",
 ]
 
 _lib = None
@@ -533,10 +537,12 @@ class Solver:
     solver::petsc::gmres_ilu (solver.hpp:125-133) plus method / precond."""
 
     def __init__(self, ctx, method="cg", precond="jacobi", maxits=2000, restart=1000, rtol=1e-8, atol=1e-50,
-                 dtol=1e20, block_size=0, check_every=0, spmv="auto", profile_every=0):
+                 dtol=1e20, block_size=0, check_every=0, spmv="auto", profile_every=0, ilufill=0):
         self.ctx = ctx
+        if precond == "ilu0":
+            ilufill = 0
         p = SolverParams(METHOD[method], PRECOND[precond], int(maxits), int(restart), float(rtol), float(atol),
-                         float(dtol), int(block_size), int(check_every), SPMV[spmv], int(profile_every))
+                         float(dtol), int(block_size), int(check_every), SPMV[spmv], int(profile_every), int(ilufill), 0)
         self.h = C.c_void_p()
         _ck(lib().tfelcu_solver_create(ctx.h, C.byref(p), C.byref(self.h)))
         self.n = 0
@@ -584,6 +590,14 @@ class Solver:
             out = np.zeros(self.n_global)
         _ck(lib().tfelcu_solver_gather(self.h, _ptr(x_local), _ptr(out)))
         return out
+
+    def ilu_factors(self):
+        """(rowptr int64 [n + 1], colind int32, lu) of the ILU(ilufill) factors the solver holds (parity checks)"""
+        n = C.c_size_t(); nnz = C.c_size_t(); lv = C.c_int()
+        _ck(lib().tfelcu_solver_ilu_info(self.h, C.byref(n), C.byref(nnz), C.byref(lv)))
+        rp = np.zeros(n.value + 1, dtype=np.int64); ci = np.zeros(nnz.value, dtype=np.int32); lu = np.zeros(nnz.value)
+        _ck(lib().tfelcu_solver_ilu_download(self.h, _ptr(rp), _ptr(ci), _ptr(lu)))
+        return rp, ci, lu
 
     def spmv_bench(self, reps=20):
         ms = C.c_double(); nbytes = C.c_double()

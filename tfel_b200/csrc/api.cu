@@ -134,6 +134,9 @@ int tfelcu_ctx_destroy(tfelcu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (tfelcu_matrix* m : ctx->matrix_pool) delete m;
+    for (tfelcu_solver* sv : ctx->solver_pool) delete sv;
+    ctx->matrix_pool.clear(); ctx->solver_pool.clear();
     tfelcu::p2p_teardown(ctx);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -299,12 +302,26 @@ int tfelcu_fes_create(tfelcu_ctx* ctx, tfelcu_mesh* mesh, int fe, tfelcu_fes** f
     std::unique_ptr<tfelcu_fes> f(new tfelcu_fes());
     f->ctx = ctx; f->mesh = mesh; f->fe = fe;
     tfelcu::fes_build(f.get());
+    ctx->live_fes.push_back(f.get());
     *fes = f.release();
   });
 }
 
 int tfelcu_fes_destroy(tfelcu_fes* fes) {
-  return guarded([&] { if (fes) { use_device(fes->ctx); fes->ctx->sync(); delete fes; } });
+  return guarded([&] {
+    if (!fes) return;
+    use_device(fes->ctx); fes->ctx->sync();
+    auto& live = fes->ctx->live_fes;
+    for (size_t i = 0; i < live.size(); ++i) if (live[i] == fes) { live.erase(live.begin() + i); break; }
+    auto& pool = fes->ctx->matrix_pool;   // parked forms on this space go with it
+    for (size_t i = 0; i < pool.size();) {
+      bool uses = false;
+      for (int c = 0; c < pool[i]->test.n; ++c) uses = uses || pool[i]->test.fes[c] == fes;
+      for (int c = 0; c < pool[i]->trial.n; ++c) uses = uses || pool[i]->trial.fes[c] == fes;
+      if (uses) { delete pool[i]; pool.erase(pool.begin() + i); } else ++i;
+    }
+    delete fes;
+  });
 }
 
 int tfelcu_fes_info(const tfelcu_fes* fes, int* fe, size_t* n_dof, int* n_dof_per_cell) {
@@ -471,6 +488,21 @@ static void matrix_create_impl(tfelcu_ctx* ctx, int n_test, tfelcu_fes* const* t
   A->mesh = A->test.fes[0]->mesh;
   A->n_rows = A->test.total(); A->n_cols = A->trial.total();
   A->rows = tfelcu::make_row_map(A->test, n_seg, row_begin, row_end);
+  // a parked form on the same spaces, the same Dirichlet sets and the same rows: reuse its structure (pattern, slot map,
+  // colouring, patches); the values are cleared lazily like after clear()
+  for (size_t i = 0; i < ctx->matrix_pool.size(); ++i) {
+    tfelcu_matrix* P = ctx->matrix_pool[i];
+    bool same = P->test.n == A->test.n && P->trial.n == A->trial.n && P->rows.n == A->rows.n && P->rows.n_global == A->rows.n_global;
+    for (int c = 0; same && c < A->test.n; ++c) same = P->test.fes[c] == A->test.fes[c] && P->dir_version[c] == A->test.fes[c]->dirichlet_version;
+    for (int c = 0; same && c < A->trial.n; ++c) same = P->trial.fes[c] == A->trial.fes[c];
+    for (int g = 0; same && g < A->rows.n; ++g) same = P->rows.g_begin[g] == A->rows.g_begin[g] && P->rows.g_end[g] == A->rows.g_end[g];
+    if (!same) continue;
+    ctx->matrix_pool.erase(ctx->matrix_pool.begin() + i);
+    P->val_valid = false; P->pristine = true;
+    P->scatter = TFELCU_SCATTER_AUTO; P->patch_refused = false;
+    *m = P;
+    return;
+  }
   tfelcu::matrix_snapshot_dirichlet(A.get());
   tfelcu::matrix_build_pattern(A.get());
   ctx->sync();
@@ -495,7 +527,22 @@ int tfelcu_matrix_local_rows(const tfelcu_matrix* m, size_t* n_local) {
 }
 
 int tfelcu_matrix_destroy(tfelcu_matrix* m) {
-  return guarded([&] { if (m) { use_device(m->ctx); m->ctx->sync(); delete m; } });
+  return guarded([&] {
+    if (!m) return;
+    use_device(m->ctx); m->ctx->sync();
+    auto& pool = m->ctx->matrix_pool;
+    bool spaces_alive = true;
+    auto alive = [&](const tfelcu_fes* f) {
+      for (const void* p : m->ctx->live_fes) if (p == f) return true;
+      return false;
+    };
+    for (int c = 0; c < m->test.n; ++c) spaces_alive = spaces_alive && alive(m->test.fes[c]);
+    for (int c = 0; c < m->trial.n; ++c) spaces_alive = spaces_alive && alive(m->trial.fes[c]);
+    if (!std::getenv("TFELCU_NO_POOL") && spaces_alive) {   // park it (see Ctx::matrix_pool); the oldest of more than three goes
+      pool.push_back(m);
+      if (pool.size() > 3) { delete pool.front(); pool.erase(pool.begin()); }
+    } else delete m;
+  });
 }
 
 // clear() re-reads the Dirichlet sets of the test spaces (bilinear_form.hpp:159-165). When they changed since the
@@ -674,8 +721,20 @@ int tfelcu_solver_create(tfelcu_ctx* ctx, const tfelcu_solver_params* params, tf
   return guarded([&] {
     TFELCU_REQUIRE(ctx && params && s, "null pointer");
     TFELCU_REQUIRE(params->method == TFELCU_METHOD_CG || params->method == TFELCU_METHOD_GMRES, "unknown Krylov method");
-    TFELCU_REQUIRE(params->precond >= TFELCU_PC_NONE && params->precond <= TFELCU_PC_ILU0, "unknown preconditioner");
+    TFELCU_REQUIRE(params->precond >= TFELCU_PC_NONE && params->precond <= TFELCU_PC_ILU, "unknown preconditioner");
     TFELCU_REQUIRE(params->rtol >= 0.0 && params->atol >= 0.0, "negative tolerance");
+    TFELCU_REQUIRE(params->ilu_levels >= 0 && params->ilu_levels <= 16, "ilufill out of range (0 .. 16)");
+    // a parked solver with the same structural parameters keeps its SpMV plan and ILU symbolic phase (Ctx::solver_pool)
+    for (size_t i = 0; i < ctx->solver_pool.size(); ++i) {
+      tfelcu_solver* P = ctx->solver_pool[i];
+      if (P->params.method == params->method && P->params.precond == params->precond && P->params.ilu_levels == params->ilu_levels &&
+          P->params.block_size == params->block_size && P->params.spmv_kernel == params->spmv_kernel) {
+        ctx->solver_pool.erase(ctx->solver_pool.begin() + i);
+        P->params = *params;
+        *s = P;
+        return;
+      }
+    }
     std::unique_ptr<tfelcu_solver> S(new tfelcu_solver());
     S->ctx = ctx; S->params = *params;
     *s = S.release();
@@ -683,20 +742,50 @@ int tfelcu_solver_create(tfelcu_ctx* ctx, const tfelcu_solver_params* params, tf
 }
 
 int tfelcu_solver_destroy(tfelcu_solver* s) {
-  return guarded([&] { if (s) { use_device(s->ctx); s->ctx->sync(); delete s; } });
+  return guarded([&] {
+    if (!s) return;
+    use_device(s->ctx); s->ctx->sync();
+    auto& pool = s->ctx->solver_pool;
+    if (!std::getenv("TFELCU_NO_POOL") && s->pattern_id != 0) {
+      s->basis.release(); s->hess.release(); s->gmres_m = 0;   // the Krylov basis is the large part: not kept while parked
+      pool.push_back(s);
+      if (pool.size() > 2) { delete pool.front(); pool.erase(pool.begin()); }
+    } else delete s;
+  });
 }
 
-// the solver works on the device arrays of the bilinear form (zero copy); a form that holds only the rows this rank
-// owns makes the solve distributed
-static void attach_matrix(tfelcu_solver* s, tfelcu_matrix* m) {
-  s->own_rowptr.release(); s->own_colind.release(); s->own_val.release();
-  s->n = m->rows.n_local(); s->n_global = m->n_rows; s->nnz = m->nnz;
-  s->rowptr = m->rowptr.p; s->colind = m->colind.p; s->val = m->val.p;
-  s->dist.reset();
-  if (!m->rows.whole()) {
-    s->dist.reset(new tfelcu::DistPlan());
-    s->dist->rows = m->rows;
+// The solver either COPIES the rows of the bilinear form (set_operator, like solver.cpp:71-96) or borrows its device
+// arrays for the duration of one tfelcu_matrix_solve. A form that holds only the rows this rank owns makes the solve
+// distributed. Returns true when the pattern is the one the solver's structural data were built for.
+static bool attach_matrix(tfelcu_solver* s, tfelcu_matrix* m, bool copy) {
+  Ctx* ctx = s->ctx;
+  const size_t n = m->rows.n_local();
+  const bool same = s->pattern_id != 0 && s->pattern_id == m->pattern_id && s->n == n && s->nnz == m->nnz &&
+                    (bool)s->dist == !m->rows.whole();
+  s->n = n; s->n_global = m->n_rows; s->nnz = m->nnz;
+  if (copy) {
+    if (!same || s->own_val.n != m->nnz || s->own_rowptr.n != n + 1) {
+      s->own_rowptr.alloc(n + 1); s->own_colind.alloc(m->nnz); s->own_val.alloc(m->nnz);
+      TFELCU_CK(cudaMemcpyAsync(s->own_rowptr.p, m->rowptr.p, (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+      if (m->nnz) TFELCU_CK(cudaMemcpyAsync(s->own_colind.p, m->colind.p, m->nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (m->nnz) TFELCU_CK(cudaMemcpyAsync(s->own_val.p, m->val.p, m->nnz * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    s->rowptr = s->own_rowptr.p; s->colind = s->own_colind.p; s->val = s->own_val.p;
+    s->borrowed = false;
+  } else {
+    s->own_rowptr.release(); s->own_colind.release(); s->own_val.release();
+    s->rowptr = m->rowptr.p; s->colind = m->colind.p; s->val = m->val.p;
+    s->borrowed = true;
   }
+  if (!same) {
+    s->dist.reset();
+    if (!m->rows.whole()) {
+      s->dist.reset(new tfelcu::DistPlan());
+      s->dist->rows = m->rows;
+    }
+  }
+  s->pattern_id = 0;   // set by the caller once the set-up has succeeded
+  return same;
 }
 
 int tfelcu_solver_set_operator(tfelcu_solver* s, tfelcu_matrix* m) {
@@ -705,8 +794,9 @@ int tfelcu_solver_set_operator(tfelcu_solver* s, tfelcu_matrix* m) {
     TFELCU_REQUIRE(m->n_rows == m->n_cols, "the operator of a linear solve must be square");
     use_device(s->ctx);
     tfelcu::matrix_ensure_cleared(m);
-    attach_matrix(s, m);
-    tfelcu::solver_setup(s);
+    const bool same = attach_matrix(s, m, true);
+    tfelcu::solver_setup(s, !same);
+    s->pattern_id = m->pattern_id;
   });
 }
 
@@ -729,6 +819,7 @@ int tfelcu_solver_set_operator_csr(tfelcu_solver* s, size_t n, const int32_t* ro
     s->n = n; s->n_global = n; s->nnz = (size_t)nnz;
     s->rowptr = s->own_rowptr.p; s->colind = s->own_colind.p; s->val = s->own_val.p;
     s->dist.reset();
+    s->pattern_id = 0; s->borrowed = false;
     tfelcu::solver_setup(s);
   });
 }
@@ -788,10 +879,13 @@ int tfelcu_matrix_solve(tfelcu_matrix* m, const tfelcu_vector* b, tfelcu_solver*
     TFELCU_REQUIRE(m->n_rows == m->n_cols, "the operator of a linear solve must be square");
     use_device(m->ctx);
     Ctx* ctx = m->ctx;
-    // s.set_operator(a) on every solve, like bilinear_form.hpp:139
+    // s.set_operator(a) on every solve, like bilinear_form.hpp:139 -- without the copy: the form outlives this call
     tfelcu::matrix_ensure_cleared(m);
-    attach_matrix(s, m);
-    tfelcu::solver_setup(s);
+    const bool same = attach_matrix(s, m, false);
+    struct Live { tfelcu_solver* s; ~Live() { s->borrowed_live = false; } } live{s};
+    s->borrowed_live = true;
+    tfelcu::solver_setup(s, !same);
+    s->pattern_id = m->pattern_id;
     tfelcu_solver_report local;
     tfelcu_solver_report* rep = report ? report : &local;
     const size_t n_local = m->rows.n_local();
@@ -840,7 +934,7 @@ int tfelcu_solver_gather(tfelcu_solver* s, const double* x_local, double* x_glob
 int tfelcu_solver_spmv(tfelcu_solver* s, const double* x, double* y) {
   return guarded([&] {
     TFELCU_REQUIRE(s && x && y, "null pointer");
-    TFELCU_REQUIRE(s->rowptr != nullptr, "solver has no operator: call set_operator first");
+    TFELCU_REQUIRE(s->rowptr != nullptr && !s->borrowed, "solver has no operator: call set_operator first");
     use_device(s->ctx);
     Ctx* ctx = s->ctx;
     Staged<double> dx(ctx, x, s->n);
@@ -864,7 +958,7 @@ int tfelcu_solver_spmv(tfelcu_solver* s, const double* x, double* y) {
 int tfelcu_solver_spmv_bench(tfelcu_solver* s, int reps, double* avg_ms, double* algorithmic_bytes) {
   return guarded([&] {
     TFELCU_REQUIRE(s && avg_ms, "null pointer");
-    TFELCU_REQUIRE(s->rowptr != nullptr, "solver has no operator: call set_operator first");
+    TFELCU_REQUIRE(s->rowptr != nullptr && !s->borrowed, "solver has no operator: call set_operator first");
     TFELCU_REQUIRE(reps >= 1, "at least one repetition");
     use_device(s->ctx);
     Ctx* ctx = s->ctx;
@@ -881,6 +975,26 @@ int tfelcu_solver_spmv_bench(tfelcu_solver* s, int reps, double* avg_ms, double*
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *avg_ms = (double)ms / reps;
     if (algorithmic_bytes) *algorithmic_bytes = 12.0 * (double)s->nnz + 4.0 * (double)(s->n + 1) + 16.0 * (double)s->n;
+  });
+}
+
+int tfelcu_solver_ilu_info(const tfelcu_solver* s, size_t* n, size_t* nnz, int* levels) {
+  return guarded([&] {
+    TFELCU_REQUIRE(s && s->ilu && s->ilu->syncfree, "the solver holds no ILU factorisation");
+    if (n) *n = s->n;
+    if (nnz) *nnz = s->ilu->fnnz;
+    if (levels) *levels = s->ilu->levels;
+  });
+}
+
+int tfelcu_solver_ilu_download(const tfelcu_solver* s, int64_t* rowptr, int32_t* colind, double* lu) {
+  return guarded([&] {
+    TFELCU_REQUIRE(s && s->ilu && s->ilu->syncfree, "the solver holds no ILU factorisation");
+    use_device(s->ctx);
+    static_assert(sizeof(long long) == sizeof(int64_t), "64-bit row pointers");
+    copy_out(s->ctx, reinterpret_cast<long long*>(rowptr), s->ilu->fptr.p, s->n + 1);
+    copy_out(s->ctx, colind, s->ilu->fcol, s->ilu->fnnz);
+    copy_out(s->ctx, lu, s->ilu->lu.p, s->ilu->fnnz);
   });
 }
 

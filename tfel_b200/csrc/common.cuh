@@ -14,6 +14,9 @@
 
 #include "../../include/tfel_cuda.h"
 
+struct tfelcu_matrix;
+struct tfelcu_solver;
+
 namespace tfelcu {
 
 struct Error : std::runtime_error {
@@ -100,6 +103,13 @@ struct Ctx {
   unsigned long long* seq_dev = nullptr;   // [0]: reductions done, [1 + q]: halo exchanges done with rank q (device counters,
                                            // advanced by the kernels themselves so that the loop can live in a CUDA graph)
   DevBuf<double> table_scratch;   // reference-element tables of the form being assembled (stream ordered reuse)
+  // Newton / time loops construct a bilinear_form and a solver per step (test/navier_stokes_2d_p2_p1.cpp:292-438): destroyed
+  // forms and solvers are parked here (a few of each) and handed out again when a form on the same spaces with the same
+  // Dirichlet sets / a solver with the same parameters is created, so that the CSR pattern, slot map, colouring, SpMV plan
+  // and the symbolic phase of ILU(k) are built once. TFELCU_NO_POOL=1 disables it.
+  std::vector<const void*> live_fes;   // spaces alive in this context (a form is parked only while its spaces are)
+  std::vector<struct ::tfelcu_matrix*> matrix_pool;
+  std::vector<struct ::tfelcu_solver*> solver_pool;
 
   void count(uint64_t n = 1) { launches += n; }
   void sync() { TFELCU_CK(cudaStreamSynchronize(stream)); }

@@ -307,15 +307,17 @@ __global__ void k_block_compact(const int32_t* __restrict__ colind, const double
   if (e < nnz && keep[e]) { out_col[pos[e]] = colind[e]; out_val[pos[e]] = val[e]; }
 }
 
-void ilu0_setup(tfelcu_solver* s) {
+void ilu0_setup(tfelcu_solver* s, bool symbolic) {
   Ctx* ctx = s->ctx;
   const size_t n = s->n;
-  TFELCU_REQUIRE(n < 0x7fffffffull, "ILU(0): too many rows");
-  s->ilu.reset(new Ilu0());
+  TFELCU_REQUIRE(n < 0x7fffffffull, "ILU: too many rows");
+  if (!s->ilu || s->ilu->levels != s->params.ilu_levels) symbolic = true;
+  if (symbolic) s->ilu.reset(new Ilu0());
   Ilu0& I = *s->ilu;
+  I.levels = s->params.ilu_levels;
   I.rowptr = s->rowptr; I.colind = s->colind; I.val = s->val; I.nnz = s->nnz;
   if (s->dist) {
-    // row-distributed operator: ILU(0) of the DIAGONAL BLOCK of this rank (block-Jacobi over the ranks with an
+    // row-distributed operator: ILU of the DIAGONAL BLOCK of this rank (block-Jacobi over the ranks with an
     // incomplete factorisation inside). Owned columns are the local indices < n and keep their ascending order.
     DevBuf<uint32_t> keep(s->nnz), pos(s->nnz);
     if (s->nnz) {
@@ -326,7 +328,8 @@ void ilu0_setup(tfelcu_solver* s) {
     uint32_t last_pos = 0, last_keep = 0;
     if (s->nnz) { ctx->download(&last_pos, pos.p + (s->nnz - 1), 1); ctx->download(&last_keep, keep.p + (s->nnz - 1), 1); }
     I.nnz = (size_t)last_pos + last_keep;
-    I.own_rowptr.alloc(n + 1); I.own_colind.alloc(I.nnz); I.own_val.alloc(I.nnz);
+    if (symbolic) { I.own_rowptr.alloc(n + 1); I.own_colind.alloc(I.nnz); I.own_val.alloc(I.nnz); }
+    TFELCU_REQUIRE(I.own_val.n == I.nnz, "ILU: the pattern changed under a values-only refresh");
     k_block_rowptr<<<grid_for(n + 1, 256), 256, 0, ctx->stream>>>(s->rowptr, pos.p, n, s->nnz, (int32_t)I.nnz, I.own_rowptr.p);
     ctx->count(); TFELCU_LAUNCH_CHECK();
     if (s->nnz) {
@@ -337,6 +340,10 @@ void ilu0_setup(tfelcu_solver* s) {
     ctx->sync();
     I.rowptr = I.own_rowptr.p; I.colind = I.own_colind.p; I.val = I.own_val.p;
   }
+  // default: ILU(levels) without level scheduling (iluk.cu). TFELCU_ILU=levels keeps the launch-per-level ILU(0).
+  const char* mode = std::getenv("TFELCU_ILU");
+  I.syncfree = !(mode && std::string(mode) == "levels" && I.levels == 0);
+  if (I.syncfree) { iluk_factorize(s, symbolic); return; }
   I.diag.alloc(n);
   DevBuf<int> missing(1);
   ctx->zero(missing.p, 1);
@@ -429,6 +436,7 @@ static void tri_launches(tfelcu_solver* s, const double* d_in, double* d_out, bo
 
 // out = U^-1 L^-1 in. The backward solve runs in place on the forward result.
 void ilu0_apply(tfelcu_solver* s, const double* d_in, double* d_out) {
+  if (s->ilu->syncfree) { iluk_apply(s, d_in, d_out); return; }
   tri_launches(s, d_in, d_out, true);
   tri_launches(s, d_out, d_out, false);
 }
@@ -640,6 +648,11 @@ void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep) {
     s->gmres_m = (int)m;
   } else if (s->gmres_m > 0 && m > s->gmres_m) m = s->gmres_m;
   const int M = (int)m;
+  s->restart_used = (uint32_t)M;
+  const long long wanted = std::min<long long>((long long)s->params.restart, (long long)maxits);
+  if ((long long)M < wanted && ctx->rank == 0)
+    std::fprintf(stderr, "[tfelcu] warning: GMRES restart %lld does not fit in device memory, using restart %d\n", wanted, M);
+  TFELCU_REQUIRE((long long)M * 4 >= wanted || M >= 30, "GMRES: the Krylov basis that fits in device memory is far shorter than the requested restart");
   s->hess.alloc((size_t)(M + 1) * M + 4 * (size_t)(M + 1));
   double* H = s->hess.p;
   double* cs = H + (size_t)(M + 1) * M;
@@ -738,6 +751,7 @@ void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep) {
     if (h.done) break;
     if ((uint32_t)h.its >= maxits) break;
   }
+  if (s->params.precond == TFELCU_PC_ILU) iluk_check(s);
   rep->its = (uint32_t)h.its;
   rep->converged = h.done == 1 ? 1 : (h.done == 2 || h.done == 0 ? 0 : h.done);
   rep->rnorm = h.rnorm;

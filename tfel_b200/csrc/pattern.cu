@@ -163,6 +163,8 @@ void matrix_build_pattern(tfelcu_matrix* m) {
   m->patch_stage_off.clear();
   m->has_recs = false;
   m->recs.clear();
+  static uint64_t next_pattern_id = 0;   // one host thread drives a context (API not re-entrant)
+  m->pattern_id = ++next_pattern_id;
 }
 
 // one thread per entry a of the owned slice of the transposed test dof map: positions of its nd_tr columns in the row

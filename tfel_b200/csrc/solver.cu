@@ -318,52 +318,60 @@ void block_jacobi_apply(tfelcu_solver* s, const double* d_in, double* d_out) {
 // set-up and the CG driver
 // ------------------------------------------------------------------------------------------
 
-void solver_setup(tfelcu_solver* s) {
+void solver_setup(tfelcu_solver* s, bool structure) {
   Ctx* ctx = s->ctx;
-  cudaEvent_t e0, e1;
-  TFELCU_CK(cudaEventCreate(&e0)); TFELCU_CK(cudaEventCreate(&e1));
+  cudaEvent_t e0, e1, e2;
+  TFELCU_CK(cudaEventCreate(&e0)); TFELCU_CK(cudaEventCreate(&e1)); TFELCU_CK(cudaEventCreate(&e2));
   TFELCU_CK(cudaEventRecord(e0, ctx->stream));
   const size_t n = s->n;
   size_t n_halo = 0;
-  if (s->dist) {
-    dist_setup(s);                       // needs the global column indices
-    s->colind = s->dist->colind_local.p;
-    n_halo = s->dist->n_halo;
+  if (structure) {
+    if (s->dist) {
+      dist_setup(s);                       // needs the global column indices
+      s->colind = s->dist->colind_local.p;
+      n_halo = s->dist->n_halo;
+    }
+    s->x.alloc(n + n_halo); s->b.alloc(n); s->r.alloc(n); s->p.alloc(n + n_halo); s->q.alloc(n);
+    ctx->zero(s->x.p, n + n_halo); ctx->zero(s->p.p, n + n_halo);
+    s->scal.alloc(1);
+    ctx->zero(s->scal.p, 1);
+    spmv_plan(s);
+    if (s->dist) spmv_split_boundary(s, n);   // interior slabs first: they overlap the halo exchange
+    int np = spmv_partial_count(s);
+    const int vg = vec_grid(s);
+    if (vg > np) np = vg;
+    s->n_partial = np;
+    s->partial.alloc((size_t)np * 4);
+    ctx->zero(s->partial.p, (size_t)np * 4);
+  } else if (s->dist) {
+    s->colind = s->dist->colind_local.p;   // the caller re-attached the global columns; the local ones are unchanged
   }
-  s->x.alloc(n + n_halo); s->b.alloc(n); s->r.alloc(n); s->p.alloc(n + n_halo); s->q.alloc(n);
-  ctx->zero(s->x.p, n + n_halo); ctx->zero(s->p.p, n + n_halo);
-  s->scal.alloc(1);
-  ctx->zero(s->scal.p, 1);
-  spmv_plan(s);
-  if (s->dist) spmv_split_boundary(s, n);   // interior slabs first: they overlap the halo exchange
-  int np = spmv_partial_count(s);
-  const int vg = vec_grid(s);
-  if (vg > np) np = vg;
-  s->n_partial = np;
-  s->partial.alloc((size_t)np * 4);
-  ctx->zero(s->partial.p, (size_t)np * 4);
+  TFELCU_CK(cudaEventRecord(e1, ctx->stream));
   const int pc = s->params.precond;
   if (pc == TFELCU_PC_JACOBI) {
-    s->dinv.alloc(n);
+    if (structure) s->dinv.alloc(n);
     k_extract_diag<<<grid_for(n, 256), 256, 0, ctx->stream>>>(s->rowptr, s->colind, s->val, n, 1, s->dinv.p);
     ctx->count(); TFELCU_LAUNCH_CHECK();
   } else if (pc == TFELCU_PC_BLOCK_JACOBI) {
-    s->z.alloc(n);
+    if (structure) s->z.alloc(n);
     block_jacobi_setup(s);
-  } else if (pc == TFELCU_PC_ILU0) {
-    s->z.alloc(n);
-    ilu0_setup(s);
+  } else if (pc == TFELCU_PC_ILU) {
+    if (structure) s->z.alloc(n);
+    ilu0_setup(s, structure);
   }
-  TFELCU_CK(cudaEventRecord(e1, ctx->stream));
-  TFELCU_CK(cudaEventSynchronize(e1));
-  float ms = 0.f; TFELCU_CK(cudaEventElapsedTime(&ms, e0, e1));
+  TFELCU_CK(cudaEventRecord(e2, ctx->stream));
+  TFELCU_CK(cudaEventSynchronize(e2));
+  float ms = 0.f; TFELCU_CK(cudaEventElapsedTime(&ms, e0, e2));
   s->t_setup_s = ms * 1e-3;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  TFELCU_CK(cudaEventElapsedTime(&ms, e1, e2));
+  s->t_precond_s = ms * 1e-3;
+  s->t_symbolic_s = (pc == TFELCU_PC_ILU && s->ilu && structure) ? s->ilu->t_symbolic_s : 0.0;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
 }
 
 static void apply_precond(tfelcu_solver* s, const double* d_in, double* d_out) {
   if (s->params.precond == TFELCU_PC_BLOCK_JACOBI) block_jacobi_apply(s, d_in, d_out);
-  else if (s->params.precond == TFELCU_PC_ILU0) ilu0_apply(s, d_in, d_out);
+  else if (s->params.precond == TFELCU_PC_ILU) ilu0_apply(s, d_in, d_out);
   else fail("preconditioner has no stand-alone apply");
 }
 
@@ -717,7 +725,7 @@ void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep) {
   // The loop is launch-bound once a rank's share of the matrix is small (8 GPUs: ~60 us of HBM work per iteration):
   // `check - 1` iterations are captured once in a CUDA graph and replayed; one eager iteration per chunk carries the
   // optional SpMV timing events. NCCL fallbacks and ILU(0) level launches stay eager.
-  const bool graph_ok = !std::getenv("TFELCU_NO_GRAPH") && pc != TFELCU_PC_ILU0 && (!dist || ctx->p2p) && check >= 8 &&
+  const bool graph_ok = !std::getenv("TFELCU_NO_GRAPH") && pc != TFELCU_PC_ILU && (!dist || ctx->p2p) && check >= 8 &&
                         maxits >= (uint32_t)(2 * check);
   cudaGraphExec_t graph_exec = nullptr;
   uint64_t graph_launches = 0, graph_spmv = 0;
@@ -758,6 +766,7 @@ void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep) {
     rep->spmv_avg_ms = cnt ? total / cnt : 0.0;
     rep->spmv_samples = cnt;
   }
+  if (pc == TFELCU_PC_ILU) iluk_check(s);
   rep->its = (uint32_t)h.its;
   rep->converged = h.done == 1 ? 1 : (h.done == 0 ? 0 : h.done);
   rep->rnorm = sqrt(h.rr);
@@ -769,6 +778,7 @@ void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep) {
 void solver_solve(tfelcu_solver* s, const double* d_rhs, double* d_x, tfelcu_solver_report* rep) {
   Ctx* ctx = s->ctx;
   TFELCU_REQUIRE(s->rowptr != nullptr, "solver has no operator: call set_operator first");
+  TFELCU_REQUIRE(!s->borrowed || s->borrowed_live, "the solver only borrowed the arrays of a bilinear form during tfelcu_matrix_solve: call set_operator");
   std::memset(rep, 0, sizeof(*rep));
   cudaEvent_t e0, e1;
   TFELCU_CK(cudaEventCreate(&e0)); TFELCU_CK(cudaEventCreate(&e1));
@@ -789,6 +799,15 @@ void solver_solve(tfelcu_solver* s, const double* d_rhs, double* d_x, tfelcu_sol
   float ms = 0.f; TFELCU_CK(cudaEventElapsedTime(&ms, e0, e1));
   rep->t_solve_s = ms * 1e-3;
   rep->t_setup_s = s->t_setup_s;
+  rep->t_precond_setup_s = s->t_precond_s;
+  rep->t_symbolic_s = s->t_symbolic_s;
+  rep->restart_used = s->params.method == TFELCU_METHOD_GMRES ? s->restart_used : 0;
+  rep->ilu_zero_pivot_row = -1;
+  if (s->params.precond == TFELCU_PC_ILU && s->ilu) {
+    rep->ilu_nnz = s->ilu->syncfree ? s->ilu->fnnz : s->ilu->nnz;
+    rep->ilu_levels = s->ilu->levels;
+    rep->ilu_zero_pivot_row = s->ilu->zero_pivot_row;
+  }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
 }
 

@@ -66,6 +66,19 @@ struct Ilu0 {
   DevBuf<int32_t> meta_l, meta_u;        // [n][4] in schedule order: row, first entry, end entry of its L / U part
   DevBuf<int32_t> pos_l, pos_u;          // [n]: schedule position of every row
   std::vector<LevelRun> runs_l, runs_u;
+  // ---- ILU(k) without level scheduling (iluk.cu): factors on the level-of-fill pattern, 64-bit row pointers
+  int levels = 0;                        // level of fill (the dictionary's "ilufill")
+  bool syncfree = true;                  // false: level-scheduled launches (TFELCU_ILU=levels), ILU(0) only
+  DevBuf<long long> fptr, fdiag;         // [n + 1] first entry of a row, [n] position of its diagonal
+  const int32_t* fcol = nullptr;         // columns of the factors, ascending per row (levels == 0: the columns of A)
+  DevBuf<int32_t> fcol_store;
+  size_t fnnz = 0;
+  DevBuf<unsigned int> ticket;           // rows are started in dependency order
+  DevBuf<int> stuck, rowdone;
+  DevBuf<double> ytmp;                   // result of the forward sweep
+  int lanes = 8;                         // lanes per row of the triangular sweeps
+  int zero_pivot_row = -1;
+  double t_symbolic_s = 0.0;
 };
 
 // halo exchange plan of a row-block distributed operator (dist.cu)
@@ -106,11 +119,19 @@ struct tfelcu_solver {
   int gmres_m = 0;                         // restart length the allocated basis holds
   std::unique_ptr<tfelcu::DistPlan> dist;  // set when the operator holds only the rows this rank owns
   size_t n_global = 0;
+  // identity of the pattern the structural data (SpMV plan, halo plan, ILU symbolic phase) were built for: a later
+  // set_operator with the same pattern only refreshes the values (0: none)
+  uint64_t pattern_id = 0;
+  bool borrowed = false;                   // the arrays belong to a bilinear form (tfelcu_matrix_solve): not usable afterwards
+  bool borrowed_live = false;              // ... and the call that borrowed them is still running
+  double t_precond_s = 0.0, t_symbolic_s = 0.0;
+  uint32_t restart_used = 0;
 };
 
 namespace tfelcu {
 
-void solver_setup(tfelcu_solver* s);
+// structure == false: the pattern is the one of the previous call, only the values changed
+void solver_setup(tfelcu_solver* s, bool structure = true);
 void solver_spmv(tfelcu_solver* s, const double* d_x, double* d_y);
 void solver_solve(tfelcu_solver* s, const double* d_rhs, double* d_x, tfelcu_solver_report* rep);
 void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep);
@@ -121,8 +142,12 @@ int spmv_launch(tfelcu_solver* s, const double* d_x, double* d_y, double* dot_pa
 int spmv_partial_count(tfelcu_solver* s);
 int spmv_launch_part(tfelcu_solver* s, int part, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal);
 void spmv_split_boundary(tfelcu_solver* s, size_t n_local);
-void ilu0_setup(tfelcu_solver* s);
+void ilu0_setup(tfelcu_solver* s, bool symbolic = true);
 void ilu0_apply(tfelcu_solver* s, const double* d_in, double* d_out);
+// ---- iluk.cu
+void iluk_factorize(tfelcu_solver* s, bool symbolic);
+void iluk_apply(tfelcu_solver* s, const double* d_in, double* d_out);
+void iluk_check(tfelcu_solver* s);
 void block_jacobi_setup(tfelcu_solver* s);
 void block_jacobi_apply(tfelcu_solver* s, const double* d_in, double* d_out);
 // ---- dist.cu

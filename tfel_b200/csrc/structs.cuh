@@ -165,6 +165,7 @@ struct tfelcu_matrix {
   uint64_t dir_version[tfelcu::kMaxComp] = {0, 0, 0, 0};
   tfelcu::DevBuf<int32_t> rowptr, colind;
   tfelcu::DevBuf<double> val;
+  uint64_t pattern_id = 0;              // unique per pattern build: solvers recognise an unchanged pattern by it
   bool pristine = true;                 // no += since clear()
   int scatter = TFELCU_SCATTER_AUTO;
   bool patch_refused = false;           // AUTO: the patch strategy did not apply to this form once; stay on rows
