@@ -230,6 +230,70 @@ __global__ void k_diag_pos64(const int32_t* __restrict__ rowptr, const int32_t* 
 }
 
 // ------------------------------------------------------------------------------------------
+// dependency levels -> the order in which rows are started
+// ------------------------------------------------------------------------------------------
+// Rows started in index order keep only a window of consecutive rows in flight, and in a lexicographic FE numbering
+// consecutive rows form a dependency chain (row i needs row i - 1): the window holds a few grid lines, i.e. a few
+// independent chains, however many rows it spans (measured: 45 ms per sweep at 592 k rows). Started in LEVEL order
+// (level(i) = 1 + max level of the rows i needs; rows of one level are independent) the window holds whole wavefronts.
+// A row's dependencies have smaller levels, hence earlier tickets: they are resident or done when it waits for them.
+
+template <bool LOWER>
+__global__ void __launch_bounds__(128)
+k_levels64(const long long* __restrict__ fptr, const int32_t* __restrict__ fcol, const long long* __restrict__ fdiag,
+           size_t n, unsigned int* __restrict__ ticket, int* level, int* __restrict__ stuck) {
+  __shared__ unsigned int blk;
+  if (threadIdx.x == 0) blk = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const size_t t = (size_t)blk * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const size_t r = LOWER ? t : n - 1 - t;
+  const long long e0 = LOWER ? fptr[r] : fdiag[r] + 1;
+  const long long e1 = LOWER ? fdiag[r] : fptr[r + 1];
+  int lv = 0;
+  for (long long e = e0; e < e1; ++e) {
+    const int c = fcol[e];
+    int l;
+    const long long t0 = clock64();
+    while ((l = ld_acquire_i32(level + c)) < 0) {
+      if (clock64() - t0 > kWaitLimit) { atomicExch(stuck, 1); l = 0; break; }
+      __nanosleep(20);
+    }
+    lv = l + 1 > lv ? l + 1 : lv;
+  }
+  st_release_i32(level + r, lv);
+}
+
+__global__ void k_max_level(const int* __restrict__ a, size_t n, int* __restrict__ out) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) atomicMax(out, a[i]);
+}
+
+// rows sorted by level (ascending row index inside a level); returns the number of levels
+template <bool LOWER>
+int level_order(Ctx* ctx, Ilu0& I, size_t n, DevBuf<int32_t>& order) {
+  DevBuf<int> level(n), mx(1);
+  TFELCU_CK(cudaMemsetAsync(level.p, 0xff, n * sizeof(int), ctx->stream));
+  ctx->zero(I.ticket.p, 1);
+  ctx->zero(mx.p, 1);
+  k_levels64<LOWER><<<grid_for(n, 128), 128, 0, ctx->stream>>>(I.fptr.p, I.fcol, I.fdiag.p, n, I.ticket.p, level.p, I.stuck.p);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  k_max_level<<<grid_for(n, 256), 256, 0, ctx->stream>>>(level.p, n, mx.p);
+  ctx->count(); TFELCU_LAUNCH_CHECK();
+  int h_stuck = 0, n_levels = 0;
+  ctx->download(&h_stuck, I.stuck.p, 1);
+  TFELCU_REQUIRE(!h_stuck, "ILU: level analysis did not terminate");
+  ctx->download(&n_levels, mx.p, 1);
+  n_levels += 1;
+  DevBuf<uint32_t> ids(n), keys_sorted(n);
+  iota_u32(ctx, ids.p, n);
+  order.alloc(n);
+  sort_pairs<uint32_t, uint32_t>(ctx, reinterpret_cast<const uint32_t*>(level.p), keys_sorted.p, ids.p,
+                                 reinterpret_cast<uint32_t*>(order.p), n, 0, bits_for((size_t)n_levels + 1));
+  return n_levels;
+}
+
+// ------------------------------------------------------------------------------------------
 // numeric phase
 // ------------------------------------------------------------------------------------------
 
@@ -248,16 +312,17 @@ __device__ __forceinline__ int find_col(const int32_t* cols, int lo, int hi, int
 __global__ void __launch_bounds__(kNumWarps * 32)
 k_iluk_numeric(const int32_t* __restrict__ a_rowptr, const int32_t* __restrict__ a_col, const double* __restrict__ a_val,
                const long long* __restrict__ fptr, const int32_t* __restrict__ fcol, const long long* __restrict__ fdiag,
-               int n, double* lu, unsigned int* __restrict__ ticket, int* rowdone, int* __restrict__ status) {
+               const int32_t* __restrict__ order, int n, double* lu, unsigned int* __restrict__ ticket, int* rowdone,
+               int* __restrict__ status) {
   __shared__ int32_t sh_col[kNumWarps][kNumRowCap];
   __shared__ double sh_w[kNumWarps][kNumRowCap];
   __shared__ unsigned int blk;
   if (threadIdx.x == 0) blk = atomicAdd(ticket, 1u);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blk * kNumWarps + warp;
-  if (row >= n) return;
-  const int i = (int)row;
+  const long long pos = (long long)blk * kNumWarps + warp;
+  if (pos >= n) return;
+  const int i = order[pos];
   const long long rs = fptr[i];
   const int len = (int)(fptr[i + 1] - rs);
   const int dpos = (int)(fdiag[i] - rs);
@@ -315,11 +380,19 @@ constexpr int kTriThreads = 256;
 
 // forward (LOWER): out_i = in_i - sum_{j<i} l_ij out_j ; backward: out_i = (in_i - sum_{j>i} u_ij out_j) / u_ii.
 // `out` holds the sentinel wherever the value is not known yet.
+//
+// A row first waits at a GATE: one lane re-reads the value of the dependency closest to the row (the last column of its
+// L part / the first column of its U part: in an FE numbering the row that finishes last) with a pause between reads;
+// only when that value is there do all lanes collect theirs. Without the gate every lane of every row in flight (~300 k
+// threads, most of them dozens of dependency levels ahead of the front) re-reads L2 without pause and the rows on the
+// critical path queue behind that traffic (measured: 17 us per dependency level).
+// Entries are accumulated in a fixed order whatever the arrival order of the values: bitwise reproducible.
 template <bool LOWER, int G>
 __global__ void __launch_bounds__(kTriThreads)
 k_tri_syncfree(const long long* __restrict__ fptr, const int32_t* __restrict__ fcol, const long long* __restrict__ fdiag,
-               const double* __restrict__ lu, int n, const double* __restrict__ in, double* out,
-               unsigned int* __restrict__ ticket, int* __restrict__ stuck, const KrylovScalars* __restrict__ S) {
+               const double* __restrict__ lu, const int32_t* __restrict__ order, int n, const double* __restrict__ in,
+               double* out, unsigned int* __restrict__ ticket, int* __restrict__ stuck, int gate_sleep_ns,
+               const KrylovScalars* __restrict__ S) {
   __shared__ unsigned int blk;
   if (S && S->done) return;
   if (threadIdx.x == 0) blk = atomicAdd(ticket, 1u);
@@ -328,7 +401,7 @@ k_tri_syncfree(const long long* __restrict__ fptr, const int32_t* __restrict__ f
   const int g = threadIdx.x / G, lane = threadIdx.x % G;
   const long long t = (long long)blk * kRows + g;
   if (t >= n) return;
-  const int i = LOWER ? (int)t : n - 1 - (int)t;
+  const int i = __ldg(order + t);
   const long long d = fdiag[i];
   const long long b = LOWER ? fptr[i] : d + 1;
   const long long e = LOWER ? d : fptr[i + 1];
@@ -337,29 +410,44 @@ k_tri_syncfree(const long long* __restrict__ fptr, const int32_t* __restrict__ f
   double rhs = 0.0, piv = 1.0;
   if (lane == 0) { rhs = in[i]; if (!LOWER) piv = lu[d]; }
   bool bad = false;
-  // the columns and factors of four entries are requested before the first wait (they do not depend on the solution)
-  for (long long p = b + lane; p < e; p += 4 * G) {
-    int c[4]; double l[4];
+  bool first = true;
+  // the columns and factors of four entries per lane are requested before the first wait (they do not depend on the
+  // solution), and so are the four values -- re-read after the gate if they were not there yet
+  for (long long p = b + lane; p - lane < e; p += 4 * G) {
+    int c[4]; double l[4]; unsigned long long x[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long q = p + (long long)u * G;
-      const bool in = q < e;
-      c[u] = in ? __ldg(fcol + q) : -1;
-      l[u] = in ? __ldg(lu + q) : 0.0;
+      const bool in_row = q < e;
+      c[u] = in_row ? __ldg(fcol + q) : -1;
+      l[u] = in_row ? __ldg(lu + q) : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (c[u] < 0) continue;
-      unsigned long long bits = ld_relaxed_u64(out + c[u]);
-      if (bits == kSentinel) {
+    for (int u = 0; u < 4; ++u) x[u] = c[u] >= 0 ? ld_relaxed_u64(out + c[u]) : 0ull;
+    if (first && gate_sleep_ns >= 0) {
+      if (lane == 0) {
+        const int gc = __ldg(fcol + (LOWER ? e - 1 : b));
         const long long t0 = clock64();
         int spins = 0;
-        while ((bits = ld_relaxed_u64(out + c[u])) == kSentinel) {
+        while (ld_relaxed_u64(out + gc) == kSentinel) {
+          if (gate_sleep_ns > 0) __nanosleep(gate_sleep_ns);
           if ((++spins & 63) == 0 && (clock64() - t0 > kWaitLimit || *(volatile int*)stuck)) { bad = true; break; }
         }
       }
-      acc += l[u] * __longlong_as_double((long long)bits);
+      __syncwarp(gmask);
     }
+    first = false;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (c[u] < 0 || x[u] != kSentinel) continue;
+      const long long t0 = clock64();
+      int spins = 0;
+      while ((x[u] = ld_relaxed_u64(out + c[u])) == kSentinel) {
+        if ((++spins & 63) == 0 && (clock64() - t0 > kWaitLimit || *(volatile int*)stuck)) { bad = true; break; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc += l[u] * __longlong_as_double((long long)x[u]);
   }
   if (bad) atomicExch(stuck, 1);
 #pragma unroll
@@ -378,9 +466,12 @@ void launch_tri(Ctx* ctx, Ilu0& I, int n, int G, const double* in, double* out, 
   TFELCU_CK(cudaMemsetAsync(out, 0xff, (size_t)n * sizeof(double), ctx->stream));
   const long long* fptr = I.fptr.p; const int32_t* fcol = I.fcol; const long long* fdiag = I.fdiag.p; const double* lu = I.lu.p;
   unsigned int* tk = I.ticket.p; int* st = I.stuck.p;
-#define TFELCU_TRI(GG)                                                                                                  \
-  k_tri_syncfree<LOWER, GG><<<grid_for((size_t)n, kTriThreads / GG), kTriThreads, 0, ctx->stream>>>(fptr, fcol, fdiag, lu, n, \
-                                                                                                in, out, tk, st, S)
+  const int sleep_ns = I.gate_sleep_ns;
+  const size_t smem = I.tri_smem;   // > 0: fewer CTAs per SM, i.e. fewer rows in flight
+  const int32_t* order = LOWER ? I.order_l.p : I.order_u.p;
+#define TFELCU_TRI(GG)                                                                                                      \
+  k_tri_syncfree<LOWER, GG><<<grid_for((size_t)n, kTriThreads / GG), kTriThreads, smem, ctx->stream>>>(fptr, fcol, fdiag, lu, order, \
+                                                                                                   n, in, out, tk, st, sleep_ns, S)
   switch (G) {
     case 4: TFELCU_TRI(4); break;
     case 8: TFELCU_TRI(8); break;
@@ -389,6 +480,11 @@ void launch_tri(Ctx* ctx, Ilu0& I, int n, int G, const double* in, double* out, 
   }
 #undef TFELCU_TRI
   ctx->count(); TFELCU_LAUNCH_CHECK();
+}
+
+template <bool LOWER, int G>
+void tri_attr(size_t smem) {
+  TFELCU_CK(cudaFuncSetAttribute(k_tri_syncfree<LOWER, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 }
 
 int lanes_for(double avg_len) {
@@ -462,19 +558,32 @@ void iluk_factorize(tfelcu_solver* s, bool symbolic) {
       int h_over = 0; ctx->download(&h_over, overflow.p, 1);
       TFELCU_REQUIRE(!h_over, "ILU(k): symbolic phase overflowed in its second pass");
     }
+    I.n_levels_l = level_order<true>(ctx, I, n, I.order_l);
+    I.n_levels_u = level_order<false>(ctx, I, n, I.order_u);
     I.lu.alloc(I.fnnz);
     I.ytmp.alloc(n);
     const double avg = n ? 0.5 * (double)I.fnnz / (double)n : 1.0;
     I.lanes = lanes_for(avg);
     if (const char* g = std::getenv("TFELCU_TRI_LANES")) { const int v = std::atoi(g); if (v == 4 || v == 8 || v == 16 || v == 32) I.lanes = v; }
+    I.gate_sleep_ns = 200;
+    if (const char* g = std::getenv("TFELCU_TRI_GATE_NS")) I.gate_sleep_ns = std::atoi(g);   // < 0: no gate
+    I.tri_smem = 0;
+    if (const char* g = std::getenv("TFELCU_TRI_CTAS")) {   // CTAs per SM of the sweeps (default: as many as fit, 8)
+      const int v = std::atoi(g);
+      if (v >= 1 && v < 8) I.tri_smem = (size_t)(220 * 1024 / v) & ~(size_t)1023;
+    }
+    if (I.tri_smem) {
+      tri_attr<true, 4>(I.tri_smem); tri_attr<true, 8>(I.tri_smem); tri_attr<true, 16>(I.tri_smem); tri_attr<true, 32>(I.tri_smem);
+      tri_attr<false, 4>(I.tri_smem); tri_attr<false, 8>(I.tri_smem); tri_attr<false, 16>(I.tri_smem); tri_attr<false, 32>(I.tri_smem);
+    }
     TFELCU_CK(cudaEventRecord(e1, ctx->stream));
     TFELCU_CK(cudaEventSynchronize(e1));
     float ms = 0.f; TFELCU_CK(cudaEventElapsedTime(&ms, e0, e1));
     I.t_symbolic_s = ms * 1e-3;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (std::getenv("TFELCU_TRACE"))
-      std::fprintf(stderr, "[tfelcu trace] ILU(%d): n %zu, nnz(A) %zu, nnz(LU) %zu (x%.2f), %d lanes per row\n", levels, n, I.nnz,
-                   I.fnnz, I.nnz ? (double)I.fnnz / (double)I.nnz : 0.0, I.lanes);
+      std::fprintf(stderr, "[tfelcu trace] ILU(%d): n %zu, nnz(A) %zu, nnz(LU) %zu (x%.2f), %d lanes per row, dependency levels L %d U %d\n", levels, n, I.nnz,
+                   I.fnnz, I.nnz ? (double)I.fnnz / (double)I.nnz : 0.0, I.lanes, I.n_levels_l, I.n_levels_u);
   }
   if (levels == 0) I.fcol = I.colind;   // the arrays of A may have moved since the symbolic phase (same pattern)
   // numeric
@@ -483,7 +592,7 @@ void iluk_factorize(tfelcu_solver* s, bool symbolic) {
   DevBuf<int> status(1);
   ctx->zero(status.p, 1);
   k_iluk_numeric<<<grid_for(n, kNumWarps), kNumWarps * 32, 0, ctx->stream>>>(I.rowptr, I.colind, I.val, I.fptr.p, I.fcol, I.fdiag.p,
-                                                                            (int)n, I.lu.p, I.ticket.p, I.rowdone.p, status.p);
+                                                                            I.order_l.p, (int)n, I.lu.p, I.ticket.p, I.rowdone.p, status.p);
   ctx->count(); TFELCU_LAUNCH_CHECK();
   int h_status = 0; ctx->download(&h_status, status.p, 1);
   TFELCU_REQUIRE(h_status >= 0, "ILU: numeric factorisation did not terminate");

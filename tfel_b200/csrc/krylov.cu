@@ -463,10 +463,26 @@ __device__ __forceinline__ double blk_sum(double v, double* red) {
   return t;
 }
 
-__device__ __forceinline__ double sum_fixed(const double* __restrict__ p, int n) {
+// Sum of per-CTA partials in a fixed order (lane-strided slices combined by a butterfly: every lane, every CTA and every
+// run gets the same bits). Must be called by all threads of warp 0 of the CTA; the other warps get the value through
+// shared memory in cta_sum. A serial sum by every thread costs ~10 us per kernel at 592 partials.
+__device__ __forceinline__ double warp_sum_fixed(const double* __restrict__ p, int n) {
   double t = 0.0;
-  for (int i = 0; i < n; ++i) t += p[i];
+  for (int i = threadIdx.x & 31; i < n; i += 32) t += p[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
   return t;
+}
+
+__device__ __forceinline__ double cta_sum(const double* __restrict__ p, int n, double* sh) {
+  if (threadIdx.x < 32) {
+    const double t = warp_sum_fixed(p, n);
+    if (threadIdx.x == 0) sh[0] = t;
+  }
+  __syncthreads();
+  const double v = sh[0];
+  __syncthreads();
+  return v;
 }
 
 // partial sums of a . b
@@ -492,8 +508,9 @@ __global__ void k_jacobi_apply(const double* __restrict__ dinv, const double* __
 // ||M^-1 b|| -> tolerances
 __global__ void k_gmres_init(const double* __restrict__ partial, int np, double rtol, double atol, double dtol,
                              GmresDev* __restrict__ G) {
-  if (threadIdx.x || blockIdx.x) return;
-  const double bn = sqrt(sum_fixed(partial, np));
+  if (blockIdx.x || threadIdx.x >= 32) return;
+  const double bn = sqrt(warp_sum_fixed(partial, np));
+  if (threadIdx.x) return;
   G->bnorm = bn; G->target = fmax(rtol * bn, atol); G->dtol_abs = dtol * bn; G->rnorm = bn;
   G->done = 0; G->k = 0; G->its = 0;
 }
@@ -501,8 +518,9 @@ __global__ void k_gmres_init(const double* __restrict__ partial, int np, double 
 // start of a cycle: rnorm = ||v0||; test; g = rnorm e_0
 __global__ void k_gmres_cycle_start(const double* __restrict__ partial, int np, GmresDev* __restrict__ G,
                                     double* __restrict__ g, int m) {
-  if (threadIdx.x || blockIdx.x) return;
-  const double rn = sqrt(sum_fixed(partial, np));
+  if (blockIdx.x || threadIdx.x >= 32) return;
+  const double rn = sqrt(warp_sum_fixed(partial, np));
+  if (threadIdx.x) return;
   G->rnorm = rn; G->k = 0;
   if (!(rn == rn)) G->done = -2;
   else if (rn <= G->target) G->done = 1;
@@ -514,8 +532,9 @@ __global__ void k_gmres_cycle_start(const double* __restrict__ partial, int np, 
 // v *= 1 / sqrt(sum partial)   (normalisation by a norm whose square is in partial sums)
 __global__ void __launch_bounds__(kVecT)
 k_scale_by_norm(double* __restrict__ v, size_t n, const double* __restrict__ partial, int np, const GmresDev* __restrict__ G) {
+  __shared__ double bc[1];
   if (G->done) return;
-  const double nr = sqrt(sum_fixed(partial, np));
+  const double nr = sqrt(cta_sum(partial, np, bc));
   if (nr == 0.0) return;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) v[i] /= nr;
 }
@@ -528,10 +547,11 @@ k_mgs_step(double* __restrict__ w, const double* __restrict__ v_prev, const doub
            double* __restrict__ h_out, const double* __restrict__ v_next, int next_is_w, size_t n,
            double* __restrict__ partial_next, const GmresDev* __restrict__ G) {
   __shared__ double red[kVecT / 32];
+  __shared__ double bc[1];
   if (G->done) return;
   double h = 0.0;
   if (v_prev) {
-    h = sum_fixed(partial_prev, np);
+    h = cta_sum(partial_prev, np, bc);
     if (blockIdx.x == 0 && threadIdx.x == 0) *h_out = h;
   }
   double acc = 0.0;
@@ -549,9 +569,10 @@ k_mgs_step(double* __restrict__ w, const double* __restrict__ v_prev, const doub
 __global__ void k_gmres_givens(double* __restrict__ H, double* __restrict__ cs, double* __restrict__ sn, double* __restrict__ g,
                                const double* __restrict__ partial_norm, int np, int k, int m, uint32_t maxits,
                                GmresDev* __restrict__ G) {
-  if (threadIdx.x || blockIdx.x || G->done) return;
+  if (blockIdx.x || threadIdx.x >= 32 || G->done) return;
   double* Hk = H + (size_t)k * (m + 1);
-  const double hn = sqrt(sum_fixed(partial_norm, np));
+  const double hn = sqrt(warp_sum_fixed(partial_norm, np));
+  if (threadIdx.x) return;
   Hk[k + 1] = hn;
   for (int j = 0; j < k; ++j) {
     const double a = Hk[j], b = Hk[j + 1];
