@@ -10,7 +10,17 @@ b += integrate<qf5pT>(f*v, m); u = a.solve(b, s).  `value` = cells / step time w
 resident in HBM; `e2e` = the same through the C ABI from HOST mesh arrays (upload, DOF numbering, Dirichlet set,
 pattern, assembly, solve, solution copied back to the host), everything inside the timed region.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--mesh-n 4096] [--impl reference]
+The line also carries (all measured AFTER the timed region, none of it inside `value`):
+  like_for_like   the same GPU step and e2e pass at the mesh size the reference arm runs (--ref-n, default 1024), so that
+                  a same-configuration ratio against `--impl reference` can be read from one pair of lines;
+  other_configs   configs[2] (tetrahedron P2, n = 142), configs[3] (Stokes P2-P2-P1: assembly at n = 2048, GMRES + ILU(2)
+                  solve at n = 256) and configs[4] (Navier-Stokes program, a few time steps) -- N = 1 only;
+  parity          N > 1: position-weighted hashes of the owned rowptr / colind slices summed over the ranks against the
+                  unmodified reference's fingerprint (tests/golden/refhash_poisson_p1_n<n>.json), sums of csr_val, and
+                  the true residual |b - A x| / |b| of the gathered solution.
+`--config c3|c4|c5` makes one of the other configurations the measured workload of the line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mesh-n 4096] [--impl reference] [--config c1|c3|c4|c5]
 """
 import argparse
 import json
@@ -23,9 +33,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+ASSEMBLY_KERNELS = "k_assemble_rows<2,3,3,const,staged,rec> (packed 16-byte row records) + k_assemble_vector_rows<2,3,const>"
 METRIC = "cells/s assembled + solve s to rtol 1e-8 (Poisson P1 4096^2), SpMV HBM% @1-8 B200"
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "tfel_ref")
-REF_SAMPLE_N = 512
+REF_SAMPLE_N = 1024
 
 
 _REAL_STDOUT = None
@@ -97,16 +108,21 @@ class ClockSampler(threading.Thread):
 # compiled against stand-in third-party headers, CPU CG in place of the absent PETSc), else the oracle port.
 # --------------------------------------------------------------------------------------------------
 
-def cpu_reference_once(n, threads):
-    """One pass of the path on the CPU at mesh size n: returns (cells, seconds, kind, detail)."""
+def cpu_reference_passes(n, threads, passes):
+    """`passes` passes of the path on the CPU at mesh size n in ONE process (mesh, space and Dirichlet set built once,
+    like the resident structure of the GPU arm): returns (cells, [seconds per pass], kind, detail)."""
     if os.path.exists(REF_BIN):
         out = subprocess.run([REF_BIN, "--problem", "poisson", "--fe", "p1", "--n", str(n), "--hash-only",
-                              "--solve", "cg", "--solve-rtol", "1e-8", "--threads", str(threads)],
+                              "--solve", "cg", "--solve-rtol", "1e-8", "--threads", str(threads), "--repeat", str(passes)],
                              capture_output=True, text=True, check=True).stdout
         d = json.loads(out.strip().splitlines()[-1])
-        t = d["t_bilinear_s"] + d["t_linear_s"] + d["t_solve_s"]
-        return int(d["n_cells"]), t, "reference", {"t_bilinear_s": d["t_bilinear_s"], "t_linear_s": d["t_linear_s"],
-                                                   "t_solve_s": d["t_solve_s"], "cg_its": d["solve_its"]}
+        rows = [r[:3] + [r[4]] for r in d.get("passes_bilinear_linear_solve_solvecall_its", [])]
+        rows.append([d["t_bilinear_s"], d["t_linear_s"], d["t_solve_s"], d["solve_its"]])
+        times = [r[0] + r[1] + r[2] for r in rows]
+        last = rows[-1]
+        return int(d["n_cells"]), times, "reference", {
+            "t_bilinear_s": last[0], "t_linear_s": last[1], "t_solve_s": last[2], "cg_its": last[3],
+            "one_time_structure_s": d["t_mesh_s"] + d["t_boundary_s"] + d["t_fes_s"] + d["t_dirichlet_s"]}
     # the plain-C restatement (oracle/), single thread
     for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         if p not in sys.path:
@@ -114,24 +130,37 @@ def cpu_reference_once(n, threads):
     import oracle as orc
     import oracle_runner
     import problems
-    t0 = time.perf_counter()
-    got = oracle_runner.run(problems.poisson("p1", n))
-    t_asm = time.perf_counter() - t0   # includes the structure build of the port
-    t0 = time.perf_counter()
-    _, its, _ = orc.cg_jacobi(got["csr_rowptr"], got["csr_colind"], got["csr_val"], got["rhs"], rtol=1e-8)
-    t_solve = time.perf_counter() - t0
-    return 2 * n * n, t_asm + t_solve, "port", {"t_assembly_incl_structure_s": t_asm, "t_solve_s": t_solve, "cg_its": its}
+    times, detail = [], None
+    for _ in range(passes):
+        t0 = time.perf_counter()
+        got = oracle_runner.run(problems.poisson("p1", n))
+        t_asm = time.perf_counter() - t0   # includes the structure build of the port
+        t0 = time.perf_counter()
+        _, its, _ = orc.cg_jacobi(got["csr_rowptr"], got["csr_colind"], got["csr_val"], got["rhs"], rtol=1e-8)
+        t_solve = time.perf_counter() - t0
+        times.append(t_asm + t_solve)
+        detail = {"t_assembly_incl_structure_s": t_asm, "t_solve_s": t_solve, "cg_its": its}
+    return 2 * n * n, times, "port", detail
 
 
-def cpu_baseline(n=REF_SAMPLE_N):
+def cpu_baseline(n):
+    """bounded sample for the own arm's line: ONE pass at a smaller n (about 10 - 30 s of CPU work)"""
     threads = os.cpu_count() or 1
-    cells, t, kind, detail = cpu_reference_once(n, threads)
+    cells, times, kind, detail = cpu_reference_passes(n, threads, 1)
+    t = times[-1]
     return {"value": cells / t, "unit": "cells/s", "cores": threads if kind == "reference" else 1, "kind": kind,
             "sample": "same problem at n=%d (%d cells): a += ... (1 thread by construction, bilinear_form.hpp:64) + "
                       "b += ... (linear_form thread pool, %d threads) + Jacobi-CG to rtol 1e-8 (1 thread; PETSc absent, "
-                      "CPU restatement); %.1f s of CPU work. CG iterations grow ~1.83 n, so cells/s at n=4096 is ~%dx lower"
-                      % (n, cells, threads, t, 4096 // n),
-            "detail": detail}
+                      "CPU restatement); %.1f s of CPU work per pass. CG iterations grow ~1.83 n, so cells/s at n=4096 is "
+                      "~%dx lower; compare with like_for_like (the GPU at the same n)" % (n, cells, threads, t, 4096 // n),
+            "n": n, "detail": detail}
+
+
+def workload_config(n):
+    """the `config` both arms print (the reference arm runs a bounded sample of it, named in its cpu_baseline)"""
+    return {"workload": "configs[1]: 2D Poisson P1 on %dx%d square mesh, qf5pT, f=1, CG + Jacobi to rtol 1e-8" % (n, n),
+            "n": n, "cells": 2 * n * n, "dofs": (n + 1) * (n + 1), "nnz": 7 * (n - 1) * (n - 1) + 4 * n,
+            "l2": "inputs larger than L2 (CSR 1.5 GB, mesh 0.67 GB per pass vs 126 MB)"}
 
 
 def run_reference(args):
@@ -140,23 +169,20 @@ def run_reference(args):
         return 0
     threads = os.cpu_count() or 1
     n = args.ref_n
-    for _ in range(args.warmup):
-        cpu_reference_once(n, threads)
-    total = 0.0
-    cells = 0
-    detail = None
-    kind = "reference"
-    for _ in range(args.steps):
-        cells, t, kind, detail = cpu_reference_once(n, threads)
-        total += t
+    cells, times, kind, detail = cpu_reference_passes(n, threads, args.warmup + args.steps)
+    timed = times[args.warmup:]
+    total = sum(timed)
     value = cells * args.steps / total
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "Poisson P1 gen_square_mesh n=%d, qf5pT, f=1, CG+Jacobi rtol 1e-8 (bounded sample of the "
-                                   "n=4096 workload)" % n, "n": n, "cells": cells},
+            "config": workload_config(args.n),
+            "sample": {"n": n, "cells": cells, "why": "the reference needs ~1 h (add_dirichlet_boundary, fes.hpp:112-113) and ~20 GB "
+                       "to set configs[1] up at n=4096; each step is the same problem at n=%d. The own arm's line carries "
+                       "like_for_like = the GPU at this n" % n},
             "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads if kind == "reference" else 1, "kind": kind,
-                             "sample": "n=%d per step, %d steps; %s" % (n, args.steps, json.dumps(detail))},
+                             "sample": "n=%d per step (%d cells), %d steps after %d warm-up passes in one process; last pass: %s"
+                                       % (n, cells, args.steps, args.warmup, json.dumps(detail))},
             "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -169,6 +195,277 @@ def run_reference(args):
 
 STIFFNESS = [dict(test=(0, 1), trial=(0, 1), c=1.0), dict(test=(0, 2), trial=(0, 2), c=1.0)]
 SOURCE = [dict(test=(0, 0), c=1.0)]
+GOLD = 0x9E3779B97F4A7C15
+
+
+def hash_slice(a, start):
+    """the position-weighted fingerprint of oracle/ref_driver.cpp over positions [start, start + len(a)):
+    sum_i (a_i + 1) (2 (start + i) + 1) 0x9E3779B97F4A7C15 mod 2^64 -- additive, so slices owned by ranks add up"""
+    import numpy as np
+    a = np.ascontiguousarray(a).ravel()
+    h = np.uint64(0)
+    step = 1 << 24
+    with np.errstate(over="ignore"):
+        for s0 in range(0, a.shape[0], step):
+            v = a[s0:s0 + step].astype(np.int64).astype(np.uint32).astype(np.uint64) + np.uint64(1)
+            i = (np.arange(s0, s0 + v.shape[0], dtype=np.uint64) + np.uint64(start)) * np.uint64(2) + np.uint64(1)
+            h = h + np.sum(v * i * np.uint64(GOLD), dtype=np.uint64)
+    return int(h)
+
+
+class PoissonSession:
+    """configs[1] at mesh size n with the structure resident: mesh, space, Dirichlet set, forms, solver"""
+
+    def __init__(self, ctx, n, world, rank, args, stream):
+        from tfel_b200 import capi
+        from tfel_b200 import dist as tdist
+        import torch
+        self.ctx, self.n, self.world, self.rank, self.stream, self.args = ctx, n, world, rank, stream, args
+        t0 = time.perf_counter()
+        self.mesh = capi.Mesh.square(ctx, 1.0, 1.0, n, n)
+        self.space = capi.Space(self.mesh, "p1")
+        self.space.add_dirichlet_boundary(0.0)
+        self.segs = None
+        if world > 1:
+            # ONE n x n problem, rows of the reference numbering split into horizontal strips (strong scaling); mesh, DOF map
+            # and Dirichlet set are replicated (0.67 GB), every rank owns the CSR rows / vector entries of its strip
+            self.segs = tdist.strip_segments([self.space.kind_offsets()], world, rank)
+            self.a = capi.Matrix(self.space, self.space, rows=self.segs)
+            self.b = capi.Vector(self.space, rows=self.segs)
+        else:
+            self.a = capi.Matrix(self.space, self.space)
+            self.b = capi.Vector(self.space)
+        ctx.synchronize()
+        self.t_structure = time.perf_counter() - t0
+        self.cells = self.mesh.n_cells
+        self.solver = capi.Solver(ctx, method="cg", precond="jacobi", maxits=args.maxits, rtol=1e-8, atol=1e-50, dtol=1e20,
+                                  check_every=args.check_every, profile_every=args.profile_every)
+        self.x_dev = torch.empty(self.a.n_cols, dtype=torch.float64, device="cuda")
+        self.asm_ms, self.solve_ms, self.spmv_ms, self.its, self.spmv_samples = [], [], [], [], []
+
+    def step(self, timed):
+        import torch
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record(self.stream)
+        self.a.clear()
+        self.a.assemble("qf5pT", STIFFNESS)
+        self.b.clear()
+        self.b.assemble("qf5pT", SOURCE)
+        e1.record(self.stream)
+        _, rep = self.a.solve(self.b, self.solver, out=self.x_dev)
+        e2.record(self.stream)
+        if rep["converged"] != 1:
+            raise SystemExit("bench.py: CG did not converge: %r" % (rep,))
+        if timed:
+            e2.synchronize()
+            self.asm_ms.append(e0.elapsed_time(e1)); self.solve_ms.append(e1.elapsed_time(e2))
+            self.spmv_ms.append(rep["spmv_avg_ms"]); self.its.append(rep["its"]); self.spmv_samples.append(rep["spmv_samples"])
+        return rep
+
+    def close(self):
+        self.solver.close(); self.b.close(); self.a.close(); self.space.close(); self.mesh.close()
+
+
+def timed_steps(sess, warmup, steps, barrier, all_max):
+    """W untimed + K timed steps bracketed by barrier + synchronize; device time, max over ranks"""
+    import torch
+    for _ in range(warmup):
+        sess.step(False)
+    barrier()
+    launches0 = sess.ctx.launches
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record(sess.stream)
+    for _ in range(steps):
+        sess.step(True)
+    stop.record(sess.stream)
+    stop.synchronize()
+    barrier()
+    return all_max(start.elapsed_time(stop)), sess.ctx.launches - launches0
+
+
+def e2e_poisson(ctx, n, world, rank, args, stream, barrier, all_max, steps):
+    """host mesh arrays -> solution on the host through the C ABI, everything inside the timed region"""
+    import numpy as np
+    import torch
+    from tfel_b200 import capi
+    from tfel_b200 import dist as tdist
+    nv = (n + 1) * (n + 1)
+    ii, jj = np.meshgrid(np.arange(n + 1, dtype=np.float64), np.arange(n + 1, dtype=np.float64), indexing="xy")
+    verts = torch.empty((nv, 2), dtype=torch.float64).pin_memory()
+    verts.numpy()[:, 0] = ((1.0 / n) * ii).ravel(); verts.numpy()[:, 1] = ((1.0 / n) * jj).ravel()
+    q = (np.arange(n, dtype=np.int64)[None, :] + (n + 1) * np.arange(n, dtype=np.int64)[:, None]).ravel()
+    cells_h = torch.empty((2 * n * n, 3), dtype=torch.int32).pin_memory()
+    c = cells_h.numpy().view(np.uint32).reshape(n * n, 6)
+    c[:, 0] = q; c[:, 1] = q + 1; c[:, 2] = q + n + 2; c[:, 3] = q; c[:, 4] = q + n + 1; c[:, 5] = q + n + 2
+    x_host = torch.empty(nv, dtype=torch.float64).pin_memory()
+    del ii, jj, q
+
+    def one():
+        m2 = capi.Mesh.create(ctx, verts.numpy(), cells_h.numpy().view(np.uint32))
+        s2 = capi.Space(m2, "p1")
+        s2.add_dirichlet_boundary(0.0)
+        if world > 1:
+            segs = tdist.strip_segments([s2.kind_offsets()], world, rank)
+            a2, b2 = capi.Matrix(s2, s2, rows=segs), capi.Vector(s2, rows=segs)
+        else:
+            a2, b2 = capi.Matrix(s2, s2), capi.Vector(s2)
+        a2.assemble("qf5pT", STIFFNESS)
+        b2.assemble("qf5pT", SOURCE)
+        sv = capi.Solver(ctx, method="cg", precond="jacobi", maxits=args.maxits, rtol=1e-8, check_every=args.check_every)
+        _, rep = a2.solve(b2, sv, out=x_host.numpy())
+        sv.close(); b2.close(); a2.close(); s2.close(); m2.close()
+        return rep
+
+    one()   # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_ev.record(stream)
+    for _ in range(steps):
+        one()
+    e_ev.record(stream)
+    e_ev.synchronize()
+    barrier()
+    wall = time.perf_counter() - t0
+    sec = all_max(max(wall, s_ev.elapsed_time(e_ev) * 1e-3))
+    return {"value": 2 * n * n * steps / sec, "unit": "cells/s",
+            "h2d_bytes_per_step": int(verts.numel() * 8 + cells_h.numel() * 4), "d2h_bytes_per_step": int(x_host.numel() * 8),
+            "s_per_step": sec / steps, "steps": steps,
+            "includes": "mesh upload, DOF numbering, boundary + Dirichlet set, CSR pattern, assembly of A and b, CG solve, "
+                        "solution download", "max_u": float(x_host.max())}
+
+
+def parity_block(sess, dist, torch):
+    """N > 1: the distributed CSR against the unmodified reference's fingerprint, and the true residual of the solution"""
+    import numpy as np
+    import scipy.sparse as sp
+    a, b = sess.a, sess.b
+    rp, ci, val = a.csr()
+    n_local, N = a.n_local, a.n_rows
+    nnz_local = int(rp[-1])
+    dev = torch.device("cuda")
+    sizes = torch.zeros(sess.world, dtype=torch.int64, device=dev)
+    sizes[sess.rank] = nnz_local
+    dist.all_reduce(sizes)
+    off = int(sizes[:sess.rank].sum().item()); nnz_total = int(sizes.sum().item())
+    row0 = sess.segs[0][0]
+    h_rp = hash_slice(rp[:-1].astype(np.int64) + off, row0)
+    if sess.rank == sess.world - 1:
+        h_rp = (h_rp + hash_slice(np.array([nnz_total], dtype=np.int64), N)) & 0xFFFFFFFFFFFFFFFF
+    h_ci = hash_slice(ci, off)
+    x = sess.x_dev.cpu().numpy()
+    rhs = a.make_rhs(b)
+    A = sp.csr_matrix((val, ci, rp), shape=(n_local, N))
+    r = rhs - A @ x
+    acc = torch.tensor([float(val.sum()), float((val * val).sum()), float(r @ r), float(rhs @ rhs)], dtype=torch.float64, device=dev)
+    dist.all_reduce(acc)
+    hs = torch.from_numpy(np.array([h_rp, h_ci], dtype=np.uint64).view(np.int64)).to(dev)
+    dist.all_reduce(hs)      # int64 addition wraps: sums mod 2^64
+    h_rp, h_ci = [int(v) for v in hs.cpu().numpy().view(np.uint64)]
+    out = {"nnz": nnz_total, "hash_csr_rowptr": str(h_rp), "hash_csr_colind": str(h_ci), "sum_csr_val": float(acc[0]),
+           "sumsq_csr_val": float(acc[1]), "true_residual_rel": float(np.sqrt(acc[2] / acc[3])), "max_u": float(x.max())}
+    ref_path = os.path.join(ROOT, "tests", "golden", "refhash_poisson_p1_n%d.json" % sess.n)
+    if os.path.exists(ref_path):
+        ref = json.load(open(ref_path))
+        out["reference_fingerprint"] = os.path.relpath(ref_path, ROOT)
+        out["rowptr_equal"] = str(ref["hash_csr_rowptr"]) == out["hash_csr_rowptr"] and int(ref["nnz"]) == nnz_total
+        out["colind_equal"] = str(ref["hash_csr_colind"]) == out["hash_csr_colind"]
+        tol = 1e-11 + 2.3e-16 * nnz_total
+        out["csr_val_sums_equal"] = (abs(out["sum_csr_val"] - float(ref["sum_csr_val"])) <= tol * float(ref["sumabs_csr_val"]) and
+                                     abs(out["sumsq_csr_val"] - float(ref["sumsq_csr_val"])) <= tol * float(ref["sumsq_csr_val"]))
+    out["ok"] = bool(out.get("rowptr_equal", True) and out.get("colind_equal", True) and out.get("csr_val_sums_equal", True)
+                     and out["true_residual_rel"] <= 1.5e-8)
+    return out
+
+
+# ---- the other configurations of BASELINE.json (single GPU) --------------------------------------------------------
+
+def _generic(ctx, stream, problem, solver_kw, warmup, steps, solve=True, check=None):
+    """structure, assembly (A and b) and solve of a tests/problems.py problem through the C ABI; CUDA-event timed"""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cuda_runner
+    from tfel_b200 import capi
+    t0 = time.perf_counter()
+    B = cuda_runner.build(ctx, problem)
+    ctx.synchronize()
+    t_structure = time.perf_counter() - t0
+    out = {"cells": B.mesh.n_cells, "dofs": B.matrix.n_rows, "nnz": B.matrix.nnz, "structure_build_s": t_structure}
+    asm = []
+    for it in range(warmup + steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        B.matrix.clear(); B.vector.clear()
+        e0.record(stream)
+        cuda_runner.assemble(B)
+        e1.record(stream); e1.synchronize()
+        if it >= warmup:
+            asm.append(e0.elapsed_time(e1))
+    out["assembly_ms"] = float(np.mean(asm))
+    out["assembly_cells_per_s"] = B.mesh.n_cells / (out["assembly_ms"] * 1e-3)
+    if solve:
+        s = capi.Solver(ctx, **solver_kw)
+        x, rep = B.matrix.solve(B.vector, s)
+        x, rep = B.matrix.solve(B.vector, s)      # second call: structure of the solver reused (Newton / time loops)
+        out.update({"solver": {k: solver_kw[k] for k in solver_kw if k in ("method", "precond", "ilufill", "restart", "block_size")},
+                    "its": int(rep["its"]), "converged": int(rep["converged"]), "solve_s": rep["t_solve_s"],
+                    "ms_per_iteration": 1e3 * rep["t_solve_s"] / max(int(rep["its"]), 1), "solver_setup_s": rep["t_setup_s"],
+                    "rel_residual": rep["rnorm"] / max(rep["bnorm"], 1e-300)})
+        if rep.get("ilu_nnz"):
+            out["ilu_nnz"] = int(rep["ilu_nnz"]); out["restart_used"] = int(rep["restart_used"])
+        if check is not None:
+            out.update(check(B, x))
+        s.close()
+    cuda_runner.close(B)
+    return out
+
+
+def config_c3(ctx, stream, n=142):
+    """configs[2]: 3-D Laplacian, tetrahedron P2 (defined here: the reference has none, cell.hpp:948-952), u = |x|^2"""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import problems
+
+    def check(B, x):
+        xyz = B.spaces[0].dof_coordinates()
+        return {"max_abs_error_vs_x2": float(np.abs(x - (xyz ** 2).sum(1)).max())}
+    out = _generic(ctx, stream, problems.tet("p2", n), dict(method="cg", precond="block_jacobi", block_size=4, maxits=20000,
+                                                           rtol=1e-8, check_every=50), 1, 3, check=check)
+    out["workload"] = "configs[2]: 3D Laplacian P2 on gen_cube_mesh n=%d, qfSym10pTet, CG + block-Jacobi(4) to rtol 1e-8" % n
+    return out
+
+
+def config_c4(ctx, stream, n_assembly=2048, n_solve=256, ilufill=2):
+    """configs[3]: Stokes P2-P2-P1 (test/stokes_2d_p2_p1.cpp:36-106). Assembly at the full size; the GMRES + ILU(ilufill)
+    solve (the reference's own solver settings: restart 1000, ilufill 2) at n_solve."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import problems
+    out = {"workload": "configs[3]: Stokes 2D P2-P2-P1 on gen_square_mesh, qf5pT; assembly at n=%d, GMRES(1000) + ILU(%d) at n=%d"
+                       % (n_assembly, ilufill, n_solve)}
+    out["assembly"] = _generic(ctx, stream, problems.stokes(n_assembly), {}, 1, 3, solve=False)
+    out["solve"] = _generic(ctx, stream, problems.stokes(n_solve),
+                            dict(method="gmres", precond="ilu", ilufill=ilufill, maxits=6000, restart=1000, rtol=1e-8), 1, 2)
+    return out
+
+
+def config_c5(n=128, time_steps=3):
+    """configs[4]: the reference's navier_stokes(n) program (test/navier_stokes_2d_p2_p1.cpp:236-438) on the C++ face:
+    implicit Euler + Newton, a NEW bilinear_form and solver per Newton step, GMRES(1000) + ILU(2)"""
+    exe = os.path.join(ROOT, "examples", "bin", "navier_stokes_2d_p2_p1")
+    if not os.path.exists(exe):
+        return {"unavailable": "examples/bin/navier_stokes_2d_p2_p1 is not built (run __graft_entry__.build())"}
+    t0 = time.perf_counter()
+    r = subprocess.run([exe, str(n), str(time_steps)], capture_output=True, text=True, timeout=1500)
+    wall = time.perf_counter() - t0
+    out = {"workload": "configs[4]: Navier-Stokes 2D P2-P2-P1 (Re 5000, dt 0.5), n=%d, %d time steps, Newton to 1e-8, "
+                       "GMRES(1000) + ILU(2) per Newton step" % (n, time_steps), "wall_s": wall, "rc": r.returncode}
+    for ln in r.stdout.splitlines():
+        if ln.startswith("json: "):
+            out.update(json.loads(ln[6:]))
+    if r.returncode != 0:
+        out["stderr_tail"] = r.stderr[-400:]
+    return out
 
 
 def run_own(args):
@@ -194,164 +491,129 @@ def run_own(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def all_max(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     n = args.n
     ctx = tdist.init_context(local_rank)     # distributed (NCCL) when world > 1
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
     peak, peak_src = measured_peaks()
 
-    # ---- resident structure (one-time, reported separately) -------------------------------------
-    # N > 1: ONE n x n problem, rows of the reference numbering split into horizontal strips (strong scaling);
-    # mesh, DOF map and Dirichlet set are replicated (0.67 GB), every rank owns the CSR rows / vector entries of its strip
-    def make_forms(mesh_, space_):
-        if world == 1:
-            return capi.Matrix(space_, space_), capi.Vector(space_)
-        segs = tdist.strip_segments([space_.kind_offsets()], world, rank)
-        return capi.Matrix(space_, space_, rows=segs), capi.Vector(space_, rows=segs)
+    if args.config != "c1":
+        if world != 1:
+            raise SystemExit("bench.py: --config %s is a single-GPU measurement" % args.config)
+        sampler = ClockSampler(local_rank); sampler.start()
+        launches0 = ctx.launches
+        if args.config == "c3":
+            block = config_c3(ctx, stream, args.c3_n)
+            value, ms = block["cells"] / (block["assembly_ms"] * 1e-3 + block["solve_s"]), block["assembly_ms"] + 1e3 * block["solve_s"]
+        elif args.config == "c4":
+            block = config_c4(ctx, stream, args.c4_assembly_n, args.c4_solve_n, args.ilufill)
+            sv = block["solve"]
+            value, ms = sv["cells"] / (sv["assembly_ms"] * 1e-3 + sv["solve_s"]), sv["assembly_ms"] + 1e3 * sv["solve_s"]
+        else:
+            block = config_c5(args.c5_n, args.c5_steps)
+            value = block.get("cells_per_s_whole_run"); ms = block.get("ms_per_time_step")
+        emit({"metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": 1, "steps": 1, "warmup": 1, "ms_per_step": ms,
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+              "config": {"workload": block.get("workload")}, "detail": block, "clocks": sampler.summary(),
+              "gpu_launches": int(ctx.launches - launches0), "e2e": None,
+              "note": "value = cells / (assembly of A and b + solve) of ONE pass with the structure resident"})
+        return 0
 
-    t0 = time.perf_counter()
-    mesh = capi.Mesh.square(ctx, 1.0, 1.0, n, n)
-    space = capi.Space(mesh, "p1")
-    space.add_dirichlet_boundary(0.0)
-    a, b = make_forms(mesh, space)
-    ctx.synchronize()
-    t_structure = time.perf_counter() - t0
-    cells = mesh.n_cells
-    solver = capi.Solver(ctx, method="cg", precond="jacobi", maxits=args.maxits, rtol=1e-8, atol=1e-50, dtol=1e20,
-                         check_every=args.check_every, profile_every=args.profile_every)
-    x_dev = torch.empty(a.n_cols, dtype=torch.float64, device="cuda")
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    asm_ms, solve_ms, spmv_ms, its_seen, spmv_samples = [], [], [], [], []
-
-    def step(timed):
-        e0, e1, e2 = ev(), ev(), ev()
-        e0.record(stream)
-        a.clear()
-        a.assemble("qf5pT", STIFFNESS)
-        b.clear()
-        b.assemble("qf5pT", SOURCE)
-        e1.record(stream)
-        _, rep = a.solve(b, solver, out=x_dev)
-        e2.record(stream)
-        if rep["converged"] != 1:
-            raise SystemExit("bench.py: CG did not converge: %r" % (rep,))
-        if timed:
-            e2.synchronize()
-            asm_ms.append(e0.elapsed_time(e1)); solve_ms.append(e1.elapsed_time(e2))
-            spmv_ms.append(rep["spmv_avg_ms"]); its_seen.append(rep["its"]); spmv_samples.append(rep["spmv_samples"])
-        return rep
-
-    for _ in range(args.warmup):
-        step(False)
-    barrier()
+    # ---- configs[1]: resident structure (one-time, reported separately), W warm-up + K timed steps ----------------
+    sess = PoissonSession(ctx, n, world, rank, args, stream)
+    cells = sess.cells
     sampler = ClockSampler(local_rank)
+    for _ in range(args.warmup):
+        sess.step(False)
+    barrier()
     if rank == 0:
         sampler.start()
-    launches0 = ctx.launches
-    start, stop = ev(), ev()
-    start.record(stream)
-    for _ in range(args.steps):
-        step(True)
-    stop.record(stream)
-    stop.synchronize()
-    barrier()
+    ms_total, launches = timed_steps(sess, 0, args.steps, barrier, all_max)
     clocks = sampler.summary() if rank == 0 else None
-    launches = ctx.launches - launches0
-    ms_total = start.elapsed_time(stop)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
     value = cells * args.steps / (ms_total * 1e-3)
+    a = sess.a
 
     # ---- roofline of the dominant kernel (SpMV inside CG), measured live over the timed region ----
     nnz, N = a.nnz, a.n_local                                          # this rank's rows
-    spmv_bytes = 12.0 * nnz + 4.0 * (N + 1) + 16.0 * N
-    spmv_avg_ms = float(np.mean(spmv_ms)) if spmv_ms and spmv_ms[0] > 0 else None
-    asm_bytes = (4.0 * 3 * cells + 8.0 * 2 * mesh.n_vertices) / world + 8.0 * nnz + 8.0 * N   # A and b together (52 B/cell)
-    asm_avg_ms = float(np.mean(asm_ms))
+    spmv_bytes = 12.0 * nnz + 4.0 * (N + 1) + 16.0 * N               # the reference CSR (int32 columns)
+    moved_bytes = 10.0 * nnz + 4.0 * (N + 1) + 16.0 * N              # what the kernel streams: 16-bit column offsets
+    spmv_avg_ms = float(np.mean(sess.spmv_ms)) if sess.spmv_ms and sess.spmv_ms[0] > 0 else None
+    asm_bytes = (4.0 * 3 * cells + 8.0 * 2 * sess.mesh.n_vertices) / world + 8.0 * nnz + 8.0 * N   # A and b together (52 B/cell)
+    asm_avg_ms = float(np.mean(sess.asm_ms))
+    gbs = lambda nbytes: (nbytes / (spmv_avg_ms * 1e-3) / 1e9) if spmv_avg_ms else None
     roofline = {"kernel": "k_spmv_stream<DOT> (CSR fp64 SpMV + fused x.Ax partials, inside CG)", "bound": "hbm",
-                "achieved": (spmv_bytes / (spmv_avg_ms * 1e-3) / 1e9) if spmv_avg_ms else None, "peak": peak,
-                "unit": "GB/s", "frac": (spmv_bytes / (spmv_avg_ms * 1e-3) / 1e9 / peak) if spmv_avg_ms else None,
+                "achieved": gbs(spmv_bytes), "peak": peak, "unit": "GB/s", "frac": (gbs(spmv_bytes) / peak) if spmv_avg_ms else None,
                 "traffic": ncu_traffic("k_spmv_stream<true,1,1024,128,3,5,int16>", n, world),
-                "traffic_note": "ncu capture in profiles/: 1.508 GB per launch < algorithmic 1.7445 GB because the solver streams 16-bit "
-                                "column offsets (10 B per stored entry) instead of the reference CSR's int32 columns (12 B), which the "
-                                "algorithmic figure counts; hence frac > 1", "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
-                "avg_launch_ms": spmv_avg_ms, "samples_per_solve": int(np.mean(spmv_samples)) if spmv_samples else 0,
-                "frac_of_nominal_8TBs": (spmv_bytes / (spmv_avg_ms * 1e-3) / 1e9 / 8000.0) if spmv_avg_ms else None}
+                "moved_bytes_per_launch": moved_bytes, "moved_gbs": gbs(moved_bytes),
+                "moved_frac": (gbs(moved_bytes) / peak) if spmv_avg_ms else None,
+                "traffic_note": "`achieved` / `frac` divide the ALGORITHMIC bytes of the reference CSR (12 B per stored entry, SURVEY "
+                                "8d) by the kernel time; the kernel streams 16-bit column offsets (10 B per entry: moved_*), so frac "
+                                "can exceed 1 while moved_frac is the bandwidth fraction; ncu DRAM bytes per launch in `traffic`",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
+                "avg_launch_ms": spmv_avg_ms, "samples_per_solve": int(np.mean(sess.spmv_samples)) if sess.spmv_samples else 0,
+                "frac_of_nominal_8TBs": (gbs(spmv_bytes) / 8000.0) if spmv_avg_ms else None}
     assembly = {"cells_per_s": cells / (asm_avg_ms * 1e-3), "ms": asm_avg_ms,
                 "algorithmic_bytes": asm_bytes, "achieved_gbs": asm_bytes / (asm_avg_ms * 1e-3) / 1e9,
                 "frac_of_peak": asm_bytes / (asm_avg_ms * 1e-3) / 1e9 / peak,
-                "kernels": "k_assemble_rows<2,3,3,const,staged,rec> (packed 16-byte row records) + k_assemble_vector_rows<2,3,const>"}
-    solve = {"s": float(np.mean(solve_ms)) * 1e-3, "cg_iterations": int(np.mean(its_seen)),
-             "ms_per_iteration": float(np.mean(solve_ms)) / max(float(np.mean(its_seen)), 1.0)}
+                "kernels": ASSEMBLY_KERNELS}
+    solve = {"s": float(np.mean(sess.solve_ms)) * 1e-3, "cg_iterations": int(np.mean(sess.its)),
+             "ms_per_iteration": float(np.mean(sess.solve_ms)) / max(float(np.mean(sess.its)), 1.0)}
+    setup = {"structure_build_s": sess.t_structure, "rows_rank0": N, "nnz_rank0": nnz,
+             "parallelism": ("%d horizontal strips of rows (reference numbering); halo exchange + reductions over %s"
+                             % (world, "peer-mapped memory (CUDA IPC, NVLink)" if ctx.p2p else "NCCL send/recv + allreduce"))
+             if world > 1 else "single GPU"}
+    parity = parity_block(sess, dist, torch) if world > 1 else None
+    sess.close()
 
     # ---- e2e: host mesh arrays -> solution on the host, through the C ABI, everything timed -----------
-    e2e = None
-    if args.e2e_steps > 0:
-        nv = (n + 1) * (n + 1)
-        ii, jj = np.meshgrid(np.arange(n + 1, dtype=np.float64), np.arange(n + 1, dtype=np.float64), indexing="xy")
-        verts = torch.empty((nv, 2), dtype=torch.float64).pin_memory()
-        verts.numpy()[:, 0] = ((1.0 / n) * ii).ravel(); verts.numpy()[:, 1] = ((1.0 / n) * jj).ravel()
-        q = (np.arange(n, dtype=np.int64)[None, :] + (n + 1) * np.arange(n, dtype=np.int64)[:, None]).ravel()
-        cells_h = torch.empty((2 * n * n, 3), dtype=torch.int32).pin_memory()
-        c = cells_h.numpy().view(np.uint32).reshape(n * n, 6)
-        c[:, 0] = q; c[:, 1] = q + 1; c[:, 2] = q + n + 2; c[:, 3] = q; c[:, 4] = q + n + 1; c[:, 5] = q + n + 2
-        x_host = torch.empty(nv, dtype=torch.float64).pin_memory()
-        del ii, jj, q
-        # release the resident objects: the e2e pass builds its own
-        solver.close(); b.close(); a.close(); space.close(); mesh.close()
+    e2e = e2e_poisson(ctx, n, world, rank, args, stream, barrier, all_max, args.e2e_steps) if args.e2e_steps > 0 else None
 
-        def e2e_step():
-            m2 = capi.Mesh.create(ctx, verts.numpy(), cells_h.numpy().view(np.uint32))
-            s2 = capi.Space(m2, "p1")
-            s2.add_dirichlet_boundary(0.0)
-            a2, b2 = make_forms(m2, s2)
-            a2.assemble("qf5pT", STIFFNESS)
-            b2.assemble("qf5pT", SOURCE)
-            sv = capi.Solver(ctx, method="cg", precond="jacobi", maxits=args.maxits, rtol=1e-8, check_every=args.check_every)
-            _, rep = a2.solve(b2, sv, out=x_host.numpy())
-            sv.close(); b2.close(); a2.close(); s2.close(); m2.close()
-            return rep
-
-        e2e_step()   # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        s_ev, e_ev = ev(), ev()
-        s_ev.record(stream)
-        for _ in range(args.e2e_steps):
-            rep = e2e_step()
-        e_ev.record(stream)
-        e_ev.synchronize()
-        barrier()
-        wall = time.perf_counter() - t0
-        te = torch.tensor([max(wall, s_ev.elapsed_time(e_ev) * 1e-3)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": cells * args.e2e_steps / float(te.item()), "unit": "cells/s",
-               "h2d_bytes_per_step": int(verts.numel() * 8 + cells_h.numel() * 4), "d2h_bytes_per_step": int(x_host.numel() * 8),
-               "s_per_step": float(te.item()) / args.e2e_steps, "steps": args.e2e_steps,
-               "includes": "mesh upload, DOF numbering, boundary + Dirichlet set, CSR pattern, assembly of A and b, CG solve, "
-                           "solution download", "max_u": float(x_host.max())}
+    like, other = None, None
+    if world == 1 and not args.no_extras:
+        # ---- the same step at the mesh size of the reference arm -------------------------------------------------
+        try:
+            s2 = PoissonSession(ctx, args.ref_n, 1, 0, args, stream)
+            ms2, _ = timed_steps(s2, 2, 5, barrier, all_max)
+            like = {"n": args.ref_n, "cells": s2.cells, "steps": 5, "warmup": 2, "value": s2.cells * 5 / (ms2 * 1e-3),
+                    "unit": "cells/s", "ms_per_step": ms2 / 5, "cg_iterations": int(np.mean(s2.its)),
+                    "assembly_ms": float(np.mean(s2.asm_ms)), "solve_s": float(np.mean(s2.solve_ms)) * 1e-3}
+            s2.close()
+            like["e2e"] = e2e_poisson(ctx, args.ref_n, 1, 0, args, stream, barrier, all_max, 2)
+            like["note"] = "compare with `--impl reference` (same n): value / reference value, e2e.value / reference value"
+        except Exception as ex:   # noqa: BLE001 -- never lose the main line to an extra
+            like = {"error": repr(ex)}
+        other = {}
+        for name, fn in (("c3", lambda: config_c3(ctx, stream, args.c3_n)),
+                         ("c4", lambda: config_c4(ctx, stream, args.c4_assembly_n, args.c4_solve_n, args.ilufill)),
+                         ("c5", lambda: config_c5(args.c5_n, args.c5_steps))):
+            try:
+                other[name] = fn()
+            except Exception as ex:   # noqa: BLE001
+                other[name] = {"error": repr(ex)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "configs[1]: 2D Poisson P1 on %dx%d square mesh, qf5pT, f=1, CG + Jacobi to rtol 1e-8"
-                                       % (n, n), "n": n, "cells": cells, "dofs": a.n_rows, "rows_rank0": N, "nnz_rank0": nnz,
-                           "l2": "inputs larger than L2 (CSR 1.5 GB, mesh 0.67 GB per pass vs 126 MB)",
-                           "parallelism": ("%d horizontal strips of rows (reference numbering); halo exchange + reductions over %s"
-                                           % (world, "peer-mapped memory (CUDA IPC, NVLink)" if ctx.p2p else "NCCL send/recv + allreduce"))
-                           if world > 1 else "single GPU",
-                           "structure_build_s": t_structure},
+                "config": workload_config(n), "setup": setup,
                 "assembly": assembly, "solve": solve, "roofline": roofline, "clocks": clocks,
                 "e2e": e2e, "gpu_launches": int(launches)}
+        if parity is not None:
+            line["parity"] = parity
+        if like is not None:
+            line["like_for_like"] = like
+        if other is not None:
+            line["other_configs"] = other
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args.ref_n)
+            line["cpu_baseline"] = cpu_baseline(args.cpu_n)
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -376,6 +638,15 @@ def main():
     ap.add_argument("--profile-every", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip like_for_like and other_configs")
+    ap.add_argument("--cpu-n", type=int, default=512, help="mesh size of the bounded cpu_baseline sample of the own arm")
+    ap.add_argument("--config", default="c1", choices=["c1", "c3", "c4", "c5"])
+    ap.add_argument("--c3-n", type=int, default=142)
+    ap.add_argument("--c4-assembly-n", type=int, default=2048)
+    ap.add_argument("--c4-solve-n", type=int, default=256)
+    ap.add_argument("--ilufill", type=int, default=2)
+    ap.add_argument("--c5-n", type=int, default=128)
+    ap.add_argument("--c5-steps", type=int, default=3)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

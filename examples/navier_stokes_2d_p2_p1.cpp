@@ -1,8 +1,11 @@
 // test/navier_stokes_2d_p2_p1.cpp:236-448 of the reference (`navier_stokes(n)`) on the CUDA path: P2-P2-P1 composite
 // space, regularised lid-driven cavity data (:22-28), implicit Euler + Newton iteration with a NEW bilinear_form and
 // solver per Newton step, stopping on the relative L2 norm of the velocity step (rank-0 integrate). Differences from the
-// reference program: solver::cuda::gmres_ilu0 instead of solver::petsc::gmres_ilu, "atol" (the reference's "abstol"
-// makes its own solver constructor throw), the number of time steps is an argument, no EnSight export.
+// reference program: solver::cuda::gmres_ilu (GMRES(restart) + ILU(ilufill), same dictionary) instead of
+// solver::petsc::gmres_ilu, "atol" (the reference's "abstol" makes its own solver constructor throw), the
+// number of time steps is an argument, no EnSight export. The constructor of the per-Newton-step bilinear_form and the
+// solver set-up are timed as well: after the first Newton step both find their structure (CSR pattern, slot map, SpMV plan,
+// ILU symbolic phase) parked by the objects of the previous step.
 //   navier_stokes_2d_p2_p1 n [time_steps [solution.bin]]
 #include <tfel/tfel.hpp>
 
@@ -63,7 +66,10 @@ int main(int argc, char* argv[]) {
 
     double bilinear_form_elapsed_time(0.0), linear_form_elapsed_time(0.0), linear_solve_elapsed_time(0.0);
     double total_bilinear(0.0), total_linear(0.0), total_solve(0.0);
-    std::size_t newton_steps(0), krylov_its(0);
+    double total_ctor(0.0), total_setup(0.0), total_symbolic(0.0), total_krylov(0.0);
+    double first_ctor(0.0), first_setup(0.0), first_symbolic(0.0);
+    std::size_t newton_steps(0), krylov_its(0), not_converged(0);
+    const timer whole_run;
 
     double time(0.0);
     for (std::size_t k(0); k < end_time_step; ++k) {
@@ -78,7 +84,10 @@ int main(int argc, char* argv[]) {
         auto v0(make_expr<u_fe_type>(v0_h));
         auto v1(make_expr<u_fe_type>(v1_h));
 
-        bilinear_form<fes_type, fes_type> a(fes, fes); {
+        const timer t_ctor;
+        bilinear_form<fes_type, fes_type> a(fes, fes);
+        tfelcu_ctx_synchronize(tfel_cuda::context());
+        const double form_ctor_elapsed_time(t_ctor.tic()); {
           timer t;
 
           auto w0(a.get_test_function<0>());
@@ -145,14 +154,16 @@ int main(int argc, char* argv[]) {
                          .set("atol",    1.e-50)
                          .set("dtol",    1.e20)
                          .set("ilufill", 2u));
-        solver::cuda::gmres_ilu0 s(param);
+        solver::cuda::gmres_ilu s(param);
 
         timer t;
         dictionary report;
         auto xpp(a.solve(f, s, &report));
         linear_solve_elapsed_time = t.tic();
         krylov_its += report.get<unsigned>("its");
-        if (not report.get<bool>("converged")) std::cout << "warning: linear solve did not converge" << std::endl;
+        if (not report.get<bool>("converged")) { ++not_converged; std::cout << "warning: linear solve did not converge" << std::endl; }
+        const double setup_ms(1e3 * report.get<double>("t_setup_s")), symbolic_ms(1e3 * report.get<double>("t_symbolic_s")),
+                     krylov_ms(1e3 * report.get<double>("t_solve_s"));
 
         auto vn0_h(xpp.template get_component<0>());
         auto vn1_h(xpp.template get_component<1>());
@@ -174,13 +185,18 @@ int main(int argc, char* argv[]) {
         std::cout << "newton step #" << j << ": relative step norm (" << newton_relative_step_0_norm << ", "
                   << newton_relative_step_1_norm << "), elapsed ms (bilinear, linear, solve): ("
                   << bilinear_form_elapsed_time << ", " << linear_form_elapsed_time << ", " << linear_solve_elapsed_time
-                  << "), krylov its " << report.get<unsigned>("its") << std::endl;
+                  << "), krylov its " << report.get<unsigned>("its") << "; form constructor " << form_ctor_elapsed_time
+                  << " ms, solver set-up " << setup_ms << " ms (ILU symbolic " << symbolic_ms << " ms), GMRES " << krylov_ms
+                  << " ms" << std::endl;
 
         newton_done = (newton_relative_step_0_norm < newton_rtol and
                        newton_relative_step_1_norm < newton_rtol);
 
         xp = xpp;
         total_bilinear += bilinear_form_elapsed_time; total_linear += linear_form_elapsed_time; total_solve += linear_solve_elapsed_time;
+        if (newton_steps == 0) { first_ctor = form_ctor_elapsed_time; first_setup = setup_ms; first_symbolic = symbolic_ms; }
+        else { total_ctor += form_ctor_elapsed_time; total_setup += setup_ms; total_symbolic += symbolic_ms; }
+        total_krylov += krylov_ms;
         ++newton_steps;
       }
 
@@ -190,6 +206,22 @@ int main(int argc, char* argv[]) {
               << " time_steps " << end_time_step << " newton_steps " << newton_steps << " krylov_its " << krylov_its
               << " ms_per_newton_step (bilinear, linear, solve) (" << total_bilinear / newton_steps << ", "
               << total_linear / newton_steps << ", " << total_solve / newton_steps << ")" << std::endl;
+    {
+      const double run_ms(whole_run.tic());
+      const double later(newton_steps > 1 ? double(newton_steps - 1) : 1.0);
+      std::cout.precision(6);
+      std::cout << "json: {\"n\": " << n << ", \"cells\": " << m.get_cell_number() << ", \"dofs\": " << fes.get_total_dof_number()
+                << ", \"time_steps\": " << end_time_step << ", \"newton_steps\": " << newton_steps << ", \"krylov_its\": " << krylov_its
+                << ", \"linear_solves_not_converged\": " << not_converged
+                << ", \"ms_per_time_step\": " << run_ms / end_time_step
+                << ", \"cells_per_s_whole_run\": " << double(m.get_cell_number()) * newton_steps / (run_ms * 1e-3)
+                << ", \"per_newton_step_ms\": {\"bilinear_assembly\": " << total_bilinear / newton_steps
+                << ", \"linear_assembly\": " << total_linear / newton_steps << ", \"solve_call\": " << total_solve / newton_steps
+                << ", \"gmres\": " << total_krylov / newton_steps << "}"
+                << ", \"structure_ms\": {\"first_step\": {\"form_constructor\": " << first_ctor << ", \"solver_setup\": " << first_setup
+                << ", \"ilu_symbolic\": " << first_symbolic << "}, \"later_steps_mean\": {\"form_constructor\": " << total_ctor / later
+                << ", \"solver_setup\": " << total_setup / later << ", \"ilu_symbolic\": " << total_symbolic / later << "}}}" << std::endl;
+    }
     if (argc > 3) {
       std::ofstream out(argv[3], std::ios::binary);
       out.write(reinterpret_cast<const char*>(xp.get_coefficients().get_data()), sizeof(double) * xp.get_coefficients().get_size(0));

@@ -66,7 +66,7 @@ int main(int argc, char* argv[]) {
                      .set("atol",    1.e-50)
                      .set("dtol",    1.e20)
                      .set("ilufill", 2u));
-    solver::cuda::gmres_ilu0 s(param);
+    solver::cuda::gmres_ilu s(param);   // ILU(ilufill = 2), like solver::petsc::gmres_ilu (solver.hpp:162-163)
     dictionary report;
     const fes_type::element x(a.solve(f, s, &report));
 

@@ -160,6 +160,14 @@ def test_reference_navier_stokes_program():
     last = [float(line.split("(")[1].split(",")[0]) for line in steps]
     assert min(last) < 1e-8
     assert "summary:" in r.stdout
+    # the configured solver is the reference's: GMRES(1000) + ILU(ilufill = 2); after the first Newton step the per-step
+    # bilinear_form and solver find their structure parked (pattern, slot map, SpMV plan, ILU symbolic phase)
+    import json
+    js = [json.loads(line[6:]) for line in r.stdout.splitlines() if line.startswith("json: ")]
+    assert len(js) == 1 and js[0]["linear_solves_not_converged"] == 0
+    st = js[0]["structure_ms"]
+    assert st["first_step"]["ilu_symbolic"] > 0.0 and st["later_steps_mean"]["ilu_symbolic"] == 0.0, st
+    assert st["later_steps_mean"]["form_constructor"] < 0.5 * st["first_step"]["form_constructor"] + 0.5, st
 
 
 @pytest.mark.gpu
