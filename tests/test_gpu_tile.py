@@ -1,0 +1,137 @@
+"""GPU: the tile assembly (tfel_b200/csrc/tile.cu) -- cell-centric, graph colouring inside shared-memory tiles, A and b
+in one pass -- against the oracle, against the owner-computes rows, and against itself (bitwise reproducible)."""
+import numpy as np
+import pytest
+
+import cuda_runner
+import oracle as orc
+import oracle_runner
+import problems
+from parity import assert_int_equal, assert_values_close, matrix_entries_close
+
+pytestmark = pytest.mark.gpu
+
+STIFF = [dict(test=(0, 1), trial=(0, 1)), dict(test=(0, 2), trial=(0, 2))]
+MASS = [dict(test=(0, 0), trial=(0, 0), c=0.75)]
+MIXED = STIFF + MASS + [dict(test=(0, 1), trial=(0, 0), c=0.3), dict(test=(0, 0), trial=(0, 2), c=-0.2),
+                        dict(test=(0, 1), trial=(0, 2), c=0.1)]
+SRC = [dict(test=(0, 0), c=1.0)]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from tfel_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 57, 130, 257])
+def test_tile_matches_oracle(ctx, n):
+    """configs[0] / [1] shape at sizes around the tile edges (16 x 16 vertices per tile): structure bit-exact, values and
+    the fused right-hand side to 1e-12"""
+    p = problems.poisson("p1", n)
+    ref = oracle_runner.run(p)
+    got = cuda_runner.run(ctx, p, scatter="tile")
+    try:
+        for key in ("csr_rowptr", "csr_colind"):
+            assert_int_equal(got[key], ref[key], key)
+        matrix_entries_close(ref["csr_rowptr"], got["csr_val"], ref["csr_val"], 1e-12)
+        assert_values_close(got["linear_form"], ref["linear_form"], 1e-12, "linear_form")
+        assert_values_close(got["rhs"], ref["rhs"], 1e-12, "rhs")
+    finally:
+        cuda_runner.close(got["_built"])
+
+
+def _forms(ctx, n, scatter, jitter=0.0, dirichlet=True):
+    from tfel_b200 import capi
+    v, c = orc.gen_square_mesh(1.0, 1.0, n, n)
+    if jitter:
+        rs = np.random.RandomState(5)
+        inner = (v[:, 0] > 1e-9) & (v[:, 0] < 1 - 1e-9) & (v[:, 1] > 1e-9) & (v[:, 1] < 1 - 1e-9)
+        v = v.copy(); v[inner] += (rs.rand(int(inner.sum()), 2) - 0.5) * (jitter / n)
+    m = capi.Mesh.create(ctx, v, c)
+    sp = capi.Space(m, "p1")
+    if dirichlet:
+        sp.add_dirichlet_boundary(0.0)
+    return m, sp, capi.Matrix(sp, sp, scatter=scatter), capi.Vector(sp)
+
+
+@pytest.mark.parametrize("terms", [STIFF, MASS, MIXED], ids=["stiffness", "mass", "all_tensor_blocks"])
+@pytest.mark.parametrize("dirichlet", [True, False])
+def test_tile_equals_rows_on_a_distorted_mesh(ctx, terms, dirichlet):
+    """general triangles (jittered vertices), every block of the constant-coefficient tensor (value x value, value x
+    gradient, gradient x value, gradient x gradient): tile == owner-computes rows up to the order of the additions"""
+    out = {}
+    for scatter in ("rows", "tile"):
+        m, sp, A, b = _forms(ctx, 75, scatter, jitter=0.6, dirichlet=dirichlet)
+        A.assemble("qf5pT", terms)
+        b.assemble("qf5pT", SRC)
+        out[scatter] = (A.csr()[2], b.download())
+        b.close(); A.close(); sp.close(); m.close()
+    scale = np.abs(out["rows"][0]).max()
+    assert np.abs(out["tile"][0] - out["rows"][0]).max() <= 2e-14 * scale
+    assert np.abs(out["tile"][1] - out["rows"][1]).max() <= 2e-14 * np.abs(out["rows"][1]).max()
+
+
+def test_tile_is_bitwise_reproducible_and_auto_picks_it(ctx):
+    runs = []
+    for scatter in ("tile", "tile", None):
+        m, sp, A, b = _forms(ctx, 200, scatter, jitter=0.4)
+        A.assemble("qf5pT", MIXED)
+        b.assemble("qf5pT", SRC)
+        runs.append((A.csr()[2].copy(), b.download().copy()))
+        b.close(); A.close(); sp.close(); m.close()
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    assert np.array_equal(runs[0][0], runs[2][0]) and np.array_equal(runs[0][1], runs[2][1])   # AUTO == TILE here
+
+
+def test_fused_linear_form_equals_separate_pass(ctx):
+    """b += ... right after a += ... rides along in the tile pass; looking at the matrix in between launches the += on
+    its own and the linear form takes its usual kernel: same vector up to the order of the additions"""
+    m, sp, A, b = _forms(ctx, 90, "tile", jitter=0.5)
+    A.assemble("qf5pT", STIFF)
+    b.assemble("qf5pT", [dict(test=(0, 0), c=2.5)])
+    fused = b.download()
+    v_fused = A.csr()[2]
+    A.clear(); b.clear()
+    A.assemble("qf5pT", STIFF)
+    v_alone = A.csr()[2]                      # flushes the deferred +=
+    b.assemble("qf5pT", [dict(test=(0, 0), c=2.5)])
+    alone = b.download()
+    assert np.array_equal(v_fused, v_alone)
+    assert np.abs(fused - alone).max() <= 2e-14 * np.abs(alone).max()
+    # a linear form with a derivative does not ride along but is still right
+    A.clear(); b.clear()
+    A.assemble("qf5pT", STIFF)
+    b.assemble("qf5pT", [dict(test=(0, 1), c=1.0)])
+    assert np.array_equal(A.csr()[2], v_alone)
+    b.close(); A.close(); sp.close(); m.close()
+
+
+def test_tile_accumulate_twice_and_clear(ctx):
+    m, sp, A, b = _forms(ctx, 40, "tile")
+    A.assemble("qf5pT", STIFF)
+    rp, ci, v1 = A.csr()
+    A.assemble("qf5pT", STIFF)
+    A.assemble("qf5pT", STIFF)               # two deferred += in a row: the first is launched by the second
+    v3 = A.csr()[2]
+    dofs, _ = sp.dirichlet()
+    is_dir = np.zeros(v1.shape[0], dtype=bool); is_dir[rp[dofs]] = True
+    assert np.array_equal(v3[~is_dir], 3.0 * v1[~is_dir]) and np.all(v3[is_dir] == 1.0)
+    A.assemble("qf5pT", STIFF)
+    A.clear()                                # a += x; clear(): x is gone
+    v0 = A.csr()[2]
+    assert np.all(v0[is_dir] == 1.0) and np.all(v0[~is_dir] == 0.0)
+    b.close(); A.close(); sp.close(); m.close()
+
+
+def test_variable_coefficients_fall_back(ctx):
+    p = problems.poissong("p1", 33)
+    ref = oracle_runner.run(p)
+    got = cuda_runner.run(ctx, p)            # AUTO: the tile path refuses coefficient factors, rows take over
+    try:
+        matrix_entries_close(ref["csr_rowptr"], got["csr_val"], ref["csr_val"], 1e-12)
+        assert_values_close(got["linear_form"], ref["linear_form"], 1e-12, "linear_form")
+    finally:
+        cuda_runner.close(got["_built"])

@@ -20,7 +20,7 @@ QUAD = {"qf1pT": 1, "qf2pT": 2, "qf5pT": 3, "qf1pTlump": 4,
 FACTOR_FIELD, FACTOR_TABLE, FACTOR_PROGRAM = 1, 2, 3
 METHOD = {"cg": 1, "gmres": 2}
 PRECOND = {"none": 0, "jacobi": 1, "block_jacobi": 2, "ilu0": 3, "ilu": 3}
-SCATTER = {"rows": 0, "colored": 1, "patch": 2, "auto": 3}
+SCATTER = {"rows": 0, "colored": 1, "patch": 2, "auto": 3, "tile": 4}
 SPMV = {"auto": 0, "vector": 1, "stream": 2}
 
 

@@ -499,6 +499,7 @@ static void matrix_create_impl(tfelcu_ctx* ctx, int n_test, tfelcu_fes* const* t
     if (!same) continue;
     ctx->matrix_pool.erase(ctx->matrix_pool.begin() + i);
     P->val_valid = false; P->pristine = true;
+    if (P->pending) { tfelcu::form_build_free(P->pending); P->pending = nullptr; }
     P->scatter = TFELCU_SCATTER_AUTO; P->patch_refused = false;
     *m = P;
     return;
@@ -530,6 +531,8 @@ int tfelcu_matrix_destroy(tfelcu_matrix* m) {
   return guarded([&] {
     if (!m) return;
     use_device(m->ctx); m->ctx->sync();
+    if (m->pending) { tfelcu::form_build_free(m->pending); m->pending = nullptr; }   // a += nobody looked at
+    if (m->ctx->pending_matrix == m) m->ctx->pending_matrix = nullptr;
     auto& pool = m->ctx->matrix_pool;
     bool spaces_alive = true;
     auto alive = [&](const tfelcu_fes* f) {
@@ -557,6 +560,8 @@ int tfelcu_matrix_clear(tfelcu_matrix* m) {
       tfelcu::matrix_snapshot_dirichlet(m);
       tfelcu::matrix_build_pattern(m);
     }
+    if (m->pending) { tfelcu::form_build_free(m->pending); m->pending = nullptr; }   // a += x; clear(): x is gone
+    if (m->ctx->pending_matrix == m) m->ctx->pending_matrix = nullptr;
     m->val_valid = false;
     m->pristine = true;
   });
@@ -574,7 +579,7 @@ int tfelcu_matrix_info(const tfelcu_matrix* m, size_t* n_rows, size_t* n_cols, s
 int tfelcu_matrix_set_scatter(tfelcu_matrix* m, int scatter) {
   return guarded([&] {
     TFELCU_REQUIRE(m != nullptr, "null matrix");
-    TFELCU_REQUIRE(scatter >= TFELCU_SCATTER_ROW_GATHER && scatter <= TFELCU_SCATTER_AUTO, "unknown scatter strategy");
+    TFELCU_REQUIRE(scatter >= TFELCU_SCATTER_ROW_GATHER && scatter <= TFELCU_SCATTER_TILE, "unknown scatter strategy");
     m->scatter = scatter;
     m->patch_refused = false;
   });
@@ -651,9 +656,9 @@ int tfelcu_vector_size(const tfelcu_vector* v, size_t* n) {
 int tfelcu_vector_set_scatter(tfelcu_vector* v, int scatter) {
   return guarded([&] {
     TFELCU_REQUIRE(v != nullptr, "null vector");
-    TFELCU_REQUIRE(scatter == TFELCU_SCATTER_ROW_GATHER || scatter == TFELCU_SCATTER_PATCH || scatter == TFELCU_SCATTER_AUTO,
-                   "unknown scatter strategy for a linear form");
-    v->scatter = scatter;
+    TFELCU_REQUIRE(scatter == TFELCU_SCATTER_ROW_GATHER || scatter == TFELCU_SCATTER_PATCH || scatter == TFELCU_SCATTER_AUTO ||
+                   scatter == TFELCU_SCATTER_TILE, "unknown scatter strategy for a linear form");
+    v->scatter = scatter == TFELCU_SCATTER_TILE ? TFELCU_SCATTER_AUTO : scatter;   // a linear form rides along with a tile += (AUTO)
     v->patch_refused = false;
   });
 }

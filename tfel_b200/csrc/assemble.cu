@@ -505,6 +505,7 @@ static void assemble_bilinear_dim(tfelcu_matrix* m, int quad, const tfelcu_facto
 int resolve_scatter(int requested, bool single_block, int nd_te, int nd_tr) {
   if (requested != TFELCU_SCATTER_AUTO) return requested;
   if (const char* e = std::getenv("TFELCU_SCATTER")) {
+    if (!std::strcmp(e, "tile")) return TFELCU_SCATTER_TILE;
     if (!std::strcmp(e, "rows")) return TFELCU_SCATTER_ROW_GATHER;
     if (!std::strcmp(e, "patch")) return TFELCU_SCATTER_PATCH;
     if (!std::strcmp(e, "colored")) return TFELCU_SCATTER_COLORED;
@@ -514,17 +515,66 @@ int resolve_scatter(int requested, bool single_block, int nd_te, int nd_tr) {
   return (single_block && nd_te * nd_tr <= max_nn) ? TFELCU_SCATTER_PATCH : TFELCU_SCATTER_ROW_GATHER;
 }
 
+void form_build_free(FormBuild* p) { delete p; }
+
+// launch a += that was accepted but deferred (tile path): on its own, no linear form rode along
+void matrix_flush_pending(tfelcu_matrix* m) {
+  if (!m->pending) return;
+  std::unique_ptr<FormBuild> fb(m->pending);
+  m->pending = nullptr;
+  if (m->ctx->pending_matrix == m) m->ctx->pending_matrix = nullptr;
+  TFELCU_REQUIRE(assemble_tiles(m, *fb, nullptr, nullptr), "tile assembly: the plan of a deferred += is gone");
+  m->pristine = false;
+}
+
+// TILE (explicit, or AUTO where it applies): constant-coefficient forms on vertex-based P1 triangles. The launch is
+// deferred: a constant-coefficient linear form on the same space that follows is assembled in the same pass (tile.cu).
+static bool try_tile(tfelcu_matrix* m, int quad, const tfelcu_factor* factors, int n_factors, const tfelcu_term* terms,
+                     int n_terms, bool explicit_request) {
+  if (!tile_applicable(m)) { if (explicit_request) refuse("tile assembly: needs one scalar P1 space on triangles with every vertex used"); return false; }
+  for (int t = 0; t < n_terms; ++t) if (terms[t].n_factors != 0) { if (explicit_request) refuse("tile assembly: constant coefficients only"); return false; }
+  std::unique_ptr<FormBuild> fb(new FormBuild());
+  tfelcu_fes* te = m->test.fes[0];
+  build_form(m->ctx, m->mesh, quad, factors, n_factors, terms, n_terms, 0, te->fe, 0, te->fe, *fb);
+  if (fb->F.n_terms == 0) return true;   // only (already stored) zeros
+  if (!fb->const_coef) return false;
+  if (!matrix_tile_plan_ready(m)) { if (explicit_request) refuse("tile assembly: a tile of this mesh exceeds the capacities of the plan"); return false; }
+  // own copy of the tables: the shared scratch is overwritten by the next form that is lowered
+  if (m->pending_tables_host != fb->tables) {
+    m->ctx->sync();   // an earlier launch may still read the old tables
+    if (m->pending_tables.n < fb->tables.size()) m->pending_tables.alloc(fb->tables.size());
+    TFELCU_CK(cudaMemcpyAsync(m->pending_tables.p, fb->tables.data(), fb->tables.size() * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
+    m->ctx->sync();
+    m->pending_tables_host = fb->tables;
+  }
+  fb->F.tables = m->pending_tables.p;
+  Ctx* ctx = m->ctx;
+  if (ctx->pending_matrix && ctx->pending_matrix != m) matrix_flush_pending(ctx->pending_matrix);
+  m->pending = fb.release();
+  ctx->pending_matrix = m;
+  if (std::getenv("TFELCU_NO_DEFER")) matrix_flush_pending(m);
+  return true;
+}
+
 void assemble_bilinear(tfelcu_matrix* m, int quad, const tfelcu_factor* factors, int n_factors,
                        const tfelcu_term* terms, int n_terms) {
   for (int t = 0; t < n_terms; ++t) {
     TFELCU_REQUIRE(terms[t].test_comp >= 0 && terms[t].test_comp < m->test.n, "test component out of range");
     TFELCU_REQUIRE(terms[t].trial_comp >= 0 && terms[t].trial_comp < m->trial.n, "trial component out of range");
   }
+  if (m->pending) matrix_flush_pending(m);   // a second += on the same form: the first one goes first
   const bool single_block = (m->test.n == 1 && m->trial.n == 1);
   const int requested = m->scatter;
+  {
+    const int want = resolve_scatter(requested, single_block, m->test.fes[0]->nd, m->trial.fes[0]->nd);
+    const bool auto_tile = requested == TFELCU_SCATTER_AUTO && want == TFELCU_SCATTER_ROW_GATHER && !std::getenv("TFELCU_NO_TILE");
+    if (want == TFELCU_SCATTER_TILE || auto_tile)
+      if (try_tile(m, quad, factors, n_factors, terms, n_terms, want == TFELCU_SCATTER_TILE && requested == TFELCU_SCATTER_TILE)) return;
+  }
   int mode = (requested == TFELCU_SCATTER_AUTO && m->patch_refused)
                  ? TFELCU_SCATTER_ROW_GATHER
                  : resolve_scatter(requested, single_block, m->test.fes[0]->nd, m->trial.fes[0]->nd);
+  if (mode == TFELCU_SCATTER_TILE) mode = TFELCU_SCATTER_ROW_GATHER;   // did not apply (AUTO / environment)
   if (mode == TFELCU_SCATTER_PATCH) {
     if (requested == TFELCU_SCATTER_PATCH) { assemble_bilinear_patch(m, quad, factors, n_factors, terms, n_terms); return; }
     try { assemble_bilinear_patch(m, quad, factors, n_factors, terms, n_terms); return; }
@@ -564,10 +614,33 @@ static void assemble_linear_dim(tfelcu_vector* v, int quad, const tfelcu_factor*
   }
 }
 
+// b += (constant-coefficient linear form without derivatives) on the space of a form whose += is still pending: both in
+// one pass over the mesh
+static bool try_ride_along(tfelcu_vector* v, int quad, const tfelcu_factor* factors, int n_factors,
+                           const tfelcu_term* terms, int n_terms) {
+  Ctx* ctx = v->ctx;
+  tfelcu_matrix* m = ctx->pending_matrix;
+  if (!m || !m->pending || v->space.n != 1 || v->space.fes[0] != m->test.fes[0] || v->rows.n != 1) return false;
+  if (v->rows.g_begin[0] != m->rows.g_begin[0] || v->rows.g_end[0] != m->rows.g_end[0]) return false;
+  if (v->scatter != TFELCU_SCATTER_AUTO) return false;
+  for (int t = 0; t < n_terms; ++t) if (terms[t].n_factors != 0 || terms[t].test_d != 0) return false;
+  FormBuild fbv;
+  tfelcu_fes* te = v->space.fes[0];
+  build_form(ctx, te->mesh, quad, factors, n_factors, terms, n_terms, 0, te->fe, -1, 0, fbv);
+  if (fbv.F.n_terms == 0) return true;
+  if (!fbv.const_coef) return false;
+  std::unique_ptr<FormBuild> fb(m->pending);
+  m->pending = nullptr; ctx->pending_matrix = nullptr;
+  TFELCU_REQUIRE(assemble_tiles(m, *fb, v, &fbv), "tile assembly: the plan of a deferred += is gone");
+  m->pristine = false;
+  return true;
+}
+
 void assemble_linear(tfelcu_vector* v, int quad, const tfelcu_factor* factors, int n_factors,
                      const tfelcu_term* terms, int n_terms) {
   for (int t = 0; t < n_terms; ++t)
     TFELCU_REQUIRE(terms[t].test_comp >= 0 && terms[t].test_comp < v->space.n, "test component out of range");
+  if (try_ride_along(v, quad, factors, n_factors, terms, n_terms)) return;
   const int requested = v->scatter;
   const int nd = v->space.fes[0]->nd;
   int mode = (requested == TFELCU_SCATTER_AUTO && v->patch_refused) ? TFELCU_SCATTER_ROW_GATHER

@@ -107,6 +107,7 @@ struct Ctx {
   // forms and solvers are parked here (a few of each) and handed out again when a form on the same spaces with the same
   // Dirichlet sets / a solver with the same parameters is created, so that the CSR pattern, slot map, colouring, SpMV plan
   // and the symbolic phase of ILU(k) are built once. TFELCU_NO_POOL=1 disables it.
+  struct ::tfelcu_matrix* pending_matrix = nullptr;   // the form whose += is deferred (at most one per context)
   std::vector<const void*> live_fes;   // spaces alive in this context (a form is parked only while its spaces are)
   std::vector<struct ::tfelcu_matrix*> matrix_pool;
   std::vector<struct ::tfelcu_solver*> solver_pool;

@@ -163,6 +163,7 @@ void matrix_build_pattern(tfelcu_matrix* m) {
   m->patch_stage_off.clear();
   m->has_recs = false;
   m->recs.clear();
+  m->tile_refused = false;
   static uint64_t next_pattern_id = 0;   // one host thread drives a context (API not re-entrant)
   m->pattern_id = ++next_pattern_id;
 }
@@ -269,6 +270,7 @@ __global__ void k_clear_values(const int32_t* __restrict__ rowptr, const int32_t
 }
 
 void matrix_ensure_cleared(tfelcu_matrix* m) {
+  if (m->pending) matrix_flush_pending(m);
   if (m->val_valid) return;
   Ctx* ctx = m->ctx;
   if (m->rows.n_local()) {

@@ -33,6 +33,11 @@ struct PatchPlan {
   size_t max_cells = 0;                // largest patch, in cells
 };
 
+struct TilePlan;                         // tile.cu
+struct FormBuild;                        // element.cuh
+void tile_plan_free(TilePlan* p);
+void form_build_free(FormBuild* p);
+
 }  // namespace tfelcu
 
 struct tfelcu_mesh {
@@ -188,6 +193,15 @@ struct tfelcu_matrix {
   tfelcu::PatchPlan* patch_plan[tfelcu::kMaxSeg] = {nullptr};
   std::vector<tfelcu::DevBuf<uint32_t>> patch_stage_off;
   size_t patch_max_stage[tfelcu::kMaxSeg] = {0};
+  // tile assembly (TFELCU_SCATTER_TILE, tile.cu): one blob per tile of rows; built once per pattern
+  tfelcu::TilePlan* tile_plan = nullptr;
+  bool tile_refused = false;            // a tile exceeded a capacity of the plan once: stay on another strategy
+  // a += (constant-coefficient form) that has been accepted but not launched yet: a linear form on the same space that
+  // follows rides along in the same pass over the mesh (tile.cu); every other use of the matrix launches it first
+  tfelcu::FormBuild* pending = nullptr;
+  tfelcu::DevBuf<double> pending_tables;
+  std::vector<double> pending_tables_host;   // what pending_tables holds (an unchanged form is not uploaded again)
+  ~tfelcu_matrix() { if (tile_plan) tfelcu::tile_plan_free(tile_plan); if (pending) tfelcu::form_build_free(pending); }
   // cell colouring (TFELCU_SCATTER_COLORED): cells sorted by colour
   bool has_colors = false;
   int n_colors = 0;
@@ -223,6 +237,11 @@ void matrix_snapshot_dirichlet(tfelcu_matrix* m);
 void matrix_build_pattern(tfelcu_matrix* m);
 void matrix_build_colors(tfelcu_matrix* m);
 void matrix_ensure_cleared(tfelcu_matrix* m);
+// ---- tile.cu
+bool tile_applicable(const tfelcu_matrix* m);
+bool matrix_tile_plan_ready(tfelcu_matrix* m);
+bool assemble_tiles(tfelcu_matrix* m, const FormBuild& fb, tfelcu_vector* v, const FormBuild* fbv);
+void matrix_flush_pending(tfelcu_matrix* m);     // assemble.cu: launch an accepted-but-deferred +=
 void matrix_build_slots(tfelcu_matrix* m);
 void matrix_build_recs(tfelcu_matrix* m);
 void fes_transpose(tfelcu_fes* f);

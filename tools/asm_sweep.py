@@ -16,7 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=4096)
 ap.add_argument("--fe", default="p1")
 ap.add_argument("--reps", type=int, default=5)
-ap.add_argument("--configs", nargs="*", default=["rows", "patch:256:256", "patch:256:128", "patch:512:256", "patch:128:128"])
+ap.add_argument("--configs", nargs="*", default=["rows", "tile", "auto"])
 a = ap.parse_args()
 
 torch.cuda.set_device(0)
@@ -47,8 +47,8 @@ for cfg in a.configs:
     ev = lambda: torch.cuda.Event(enable_timing=True)
     e0, e1 = ev(), ev()
     e0.record(stream)
-    A = capi.Matrix(space, space, scatter=scatter)
-    b = capi.Vector(space, scatter=scatter)
+    A = capi.Matrix(space, space, scatter=None if scatter == "auto" else scatter)
+    b = capi.Vector(space, scatter=None if scatter in ("auto", "tile") else scatter)
     tA, tb = [], []
     for rep in range(a.reps + 2):
         s0, s1, s2 = ev(), ev(), ev()
