@@ -1,5 +1,7 @@
-"""GPU: the tile assembly (tfel_b200/csrc/tile.cu) -- cell-centric, graph colouring inside shared-memory tiles, A and b
-in one pass -- against the oracle, against the owner-computes rows, and against itself (bitwise reproducible)."""
+"""GPU: the two fast paths for constant-coefficient forms on P1 triangles -- the closed-form rows of p1rows.cu (what AUTO
+picks: scatter=None) and the tiles of tile.cu (scatter="tile"), both with the linear form riding along in the same pass --
+against the oracle, against the generic owner-computes rows (scatter="rows"), and against themselves (bitwise
+reproducible)."""
 import numpy as np
 import pytest
 
@@ -26,13 +28,18 @@ def ctx():
     c.close()
 
 
+FAST = ["tile", None]
+FAST_IDS = ["tile", "auto_p1rows"]
+
+
+@pytest.mark.parametrize("scatter", FAST, ids=FAST_IDS)
 @pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 57, 130, 257])
-def test_tile_matches_oracle(ctx, n):
+def test_tile_matches_oracle(ctx, n, scatter):
     """configs[0] / [1] shape at sizes around the tile edges (16 x 16 vertices per tile): structure bit-exact, values and
     the fused right-hand side to 1e-12"""
     p = problems.poisson("p1", n)
     ref = oracle_runner.run(p)
-    got = cuda_runner.run(ctx, p, scatter="tile")
+    got = cuda_runner.run(ctx, p, scatter=scatter)
     try:
         for key in ("csr_rowptr", "csr_colind"):
             assert_int_equal(got[key], ref[key], key)
@@ -57,39 +64,41 @@ def _forms(ctx, n, scatter, jitter=0.0, dirichlet=True):
     return m, sp, capi.Matrix(sp, sp, scatter=scatter), capi.Vector(sp)
 
 
+@pytest.mark.parametrize("fast", FAST, ids=FAST_IDS)
 @pytest.mark.parametrize("terms", [STIFF, MASS, MIXED], ids=["stiffness", "mass", "all_tensor_blocks"])
 @pytest.mark.parametrize("dirichlet", [True, False])
-def test_tile_equals_rows_on_a_distorted_mesh(ctx, terms, dirichlet):
+def test_tile_equals_rows_on_a_distorted_mesh(ctx, terms, dirichlet, fast):
     """general triangles (jittered vertices), every block of the constant-coefficient tensor (value x value, value x
     gradient, gradient x value, gradient x gradient): tile == owner-computes rows up to the order of the additions"""
     out = {}
-    for scatter in ("rows", "tile"):
+    for key, scatter in (("rows", "rows"), ("fast", fast)):
         m, sp, A, b = _forms(ctx, 75, scatter, jitter=0.6, dirichlet=dirichlet)
         A.assemble("qf5pT", terms)
         b.assemble("qf5pT", SRC)
-        out[scatter] = (A.csr()[2], b.download())
+        out[key] = (A.csr()[2], b.download())
         b.close(); A.close(); sp.close(); m.close()
     scale = np.abs(out["rows"][0]).max()
-    assert np.abs(out["tile"][0] - out["rows"][0]).max() <= 2e-14 * scale
-    assert np.abs(out["tile"][1] - out["rows"][1]).max() <= 2e-14 * np.abs(out["rows"][1]).max()
+    assert np.abs(out["fast"][0] - out["rows"][0]).max() <= 2e-14 * scale
+    assert np.abs(out["fast"][1] - out["rows"][1]).max() <= 2e-14 * np.abs(out["rows"][1]).max()
 
 
-def test_tile_is_bitwise_reproducible_and_auto_picks_it(ctx):
+@pytest.mark.parametrize("scatter", FAST, ids=FAST_IDS)
+def test_fast_paths_are_bitwise_reproducible(ctx, scatter):
     runs = []
-    for scatter in ("tile", "tile", None):
+    for _ in range(2):
         m, sp, A, b = _forms(ctx, 200, scatter, jitter=0.4)
         A.assemble("qf5pT", MIXED)
         b.assemble("qf5pT", SRC)
         runs.append((A.csr()[2].copy(), b.download().copy()))
         b.close(); A.close(); sp.close(); m.close()
     assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
-    assert np.array_equal(runs[0][0], runs[2][0]) and np.array_equal(runs[0][1], runs[2][1])   # AUTO == TILE here
 
 
-def test_fused_linear_form_equals_separate_pass(ctx):
-    """b += ... right after a += ... rides along in the tile pass; looking at the matrix in between launches the += on
+@pytest.mark.parametrize("scatter", FAST, ids=FAST_IDS)
+def test_fused_linear_form_equals_separate_pass(ctx, scatter):
+    """b += ... right after a += ... rides along in the same pass; looking at the matrix in between launches the += on
     its own and the linear form takes its usual kernel: same vector up to the order of the additions"""
-    m, sp, A, b = _forms(ctx, 90, "tile", jitter=0.5)
+    m, sp, A, b = _forms(ctx, 90, scatter, jitter=0.5)
     A.assemble("qf5pT", STIFF)
     b.assemble("qf5pT", [dict(test=(0, 0), c=2.5)])
     fused = b.download()
@@ -109,8 +118,9 @@ def test_fused_linear_form_equals_separate_pass(ctx):
     b.close(); A.close(); sp.close(); m.close()
 
 
-def test_tile_accumulate_twice_and_clear(ctx):
-    m, sp, A, b = _forms(ctx, 40, "tile")
+@pytest.mark.parametrize("scatter", FAST, ids=FAST_IDS)
+def test_tile_accumulate_twice_and_clear(ctx, scatter):
+    m, sp, A, b = _forms(ctx, 40, scatter)
     A.assemble("qf5pT", STIFF)
     rp, ci, v1 = A.csr()
     A.assemble("qf5pT", STIFF)

@@ -411,6 +411,12 @@ class _Integrand:
         self.n_factors = len(factors)
 
 
+def integrand(terms, fields=None):
+    """An integrand lowered once to the C structs of the ABI, for `+=` calls that repeat (time / Newton loops, bench.py):
+    Matrix.assemble / Vector.assemble accept it in place of the list of terms."""
+    return _Integrand(terms, fields)
+
+
 class Matrix:
     """bilinear_form<te, tr> and its sparse_matrix (bilinear_form.hpp:9-19, solver.hpp:236-283)."""
 
@@ -444,13 +450,14 @@ class Matrix:
             lib().tfelcu_matrix_destroy(self.h)
             self.h = C.c_void_p()
 
-    def clear(self):
+    def clear(self, refresh_info=True):
         _ck(lib().tfelcu_matrix_clear(self.h))
-        self._info()
+        if refresh_info:      # the pattern (nnz) changes with the Dirichlet sets of the test spaces
+            self._info()
 
     def assemble(self, quad, terms, fields=None):
-        """a += integrate<quad>(expr, mesh)"""
-        ig = _Integrand(terms, fields)
+        """a += integrate<quad>(expr, mesh); terms: list of term dicts or a prepared capi.integrand(...)"""
+        ig = terms if isinstance(terms, _Integrand) else _Integrand(terms, fields)
         _ck(lib().tfelcu_matrix_assemble(self.h, QUAD[quad], ig.factors, ig.n_factors, ig.terms, ig.n_terms))
 
     def csr(self, values=True):
@@ -506,7 +513,7 @@ class Vector:
         _ck(lib().tfelcu_vector_clear(self.h))
 
     def assemble(self, quad, terms, fields=None):
-        ig = _Integrand(terms, fields)
+        ig = terms if isinstance(terms, _Integrand) else _Integrand(terms, fields)
         _ck(lib().tfelcu_vector_assemble(self.h, QUAD[quad], ig.factors, ig.n_factors, ig.terms, ig.n_terms))
 
     def download(self):

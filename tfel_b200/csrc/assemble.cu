@@ -523,34 +523,34 @@ void matrix_flush_pending(tfelcu_matrix* m) {
   std::unique_ptr<FormBuild> fb(m->pending);
   m->pending = nullptr;
   if (m->ctx->pending_matrix == m) m->ctx->pending_matrix = nullptr;
-  TFELCU_REQUIRE(assemble_tiles(m, *fb, nullptr, nullptr), "tile assembly: the plan of a deferred += is gone");
+  const bool ok = m->pending_mode == 1 ? assemble_tiles(m, *fb, nullptr, nullptr) : assemble_p1_rows(m, *fb, nullptr, nullptr);
+  TFELCU_REQUIRE(ok, "assembly: the plan of a deferred += is gone");
   m->pristine = false;
 }
 
-// TILE (explicit, or AUTO where it applies): constant-coefficient forms on vertex-based P1 triangles. The launch is
-// deferred: a constant-coefficient linear form on the same space that follows is assembled in the same pass (tile.cu).
-static bool try_tile(tfelcu_matrix* m, int quad, const tfelcu_factor* factors, int n_factors, const tfelcu_term* terms,
-                     int n_terms, bool explicit_request) {
-  if (!tile_applicable(m)) { if (explicit_request) refuse("tile assembly: needs one scalar P1 space on triangles with every vertex used"); return false; }
+// Constant-coefficient forms on P1 triangles: the closed-form row kernel of p1rows.cu (AUTO) or the tiles of tile.cu
+// (TFELCU_SCATTER_TILE). The launch is deferred: a constant-coefficient linear form on the same space that follows is
+// assembled in the same pass.
+static bool try_p1_fast(tfelcu_matrix* m, int quad, const tfelcu_factor* factors, int n_factors, const tfelcu_term* terms,
+                        int n_terms, bool tile, bool explicit_request) {
+  if (tile ? !tile_applicable(m) : !p1rows_applicable(m)) {
+    if (explicit_request) refuse("tile assembly: needs one scalar P1 space on triangles with every vertex used");
+    return false;
+  }
   for (int t = 0; t < n_terms; ++t) if (terms[t].n_factors != 0) { if (explicit_request) refuse("tile assembly: constant coefficients only"); return false; }
   std::unique_ptr<FormBuild> fb(new FormBuild());
   tfelcu_fes* te = m->test.fes[0];
   build_form(m->ctx, m->mesh, quad, factors, n_factors, terms, n_terms, 0, te->fe, 0, te->fe, *fb);
   if (fb->F.n_terms == 0) return true;   // only (already stored) zeros
   if (!fb->const_coef) return false;
-  if (!matrix_tile_plan_ready(m)) { if (explicit_request) refuse("tile assembly: a tile of this mesh exceeds the capacities of the plan"); return false; }
-  // own copy of the tables: the shared scratch is overwritten by the next form that is lowered
-  if (m->pending_tables_host != fb->tables) {
-    m->ctx->sync();   // an earlier launch may still read the old tables
-    if (m->pending_tables.n < fb->tables.size()) m->pending_tables.alloc(fb->tables.size());
-    TFELCU_CK(cudaMemcpyAsync(m->pending_tables.p, fb->tables.data(), fb->tables.size() * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
-    m->ctx->sync();
-    m->pending_tables_host = fb->tables;
-  }
-  fb->F.tables = m->pending_tables.p;
+  if (tile) {
+    if (!matrix_tile_plan_ready(m)) { if (explicit_request) refuse("tile assembly: a tile of this mesh exceeds the capacities of the plan"); return false; }
+  } else if (m->rows_per_cta != 128 || m->max_block_nnz * sizeof(double) > 200 * 1024 || !matrix_ell_ready(m)) return false;
+  // the tile kernel takes the form by value (tile.cu: TileForm): nothing of it lives in the shared table scratch
   Ctx* ctx = m->ctx;
   if (ctx->pending_matrix && ctx->pending_matrix != m) matrix_flush_pending(ctx->pending_matrix);
   m->pending = fb.release();
+  m->pending_mode = tile ? 1 : 0;
   ctx->pending_matrix = m;
   if (std::getenv("TFELCU_NO_DEFER")) matrix_flush_pending(m);
   return true;
@@ -567,9 +567,11 @@ void assemble_bilinear(tfelcu_matrix* m, int quad, const tfelcu_factor* factors,
   const int requested = m->scatter;
   {
     const int want = resolve_scatter(requested, single_block, m->test.fes[0]->nd, m->trial.fes[0]->nd);
-    const bool auto_tile = requested == TFELCU_SCATTER_AUTO && want == TFELCU_SCATTER_ROW_GATHER && !std::getenv("TFELCU_NO_TILE");
-    if (want == TFELCU_SCATTER_TILE || auto_tile)
-      if (try_tile(m, quad, factors, n_factors, terms, n_terms, want == TFELCU_SCATTER_TILE && requested == TFELCU_SCATTER_TILE)) return;
+    // AUTO: the closed-form P1 rows where they apply (TFELCU_NO_P1ROWS=1: the generic kernels only)
+    const bool auto_p1 = requested == TFELCU_SCATTER_AUTO && want == TFELCU_SCATTER_ROW_GATHER && !std::getenv("TFELCU_NO_P1ROWS");
+    if (want == TFELCU_SCATTER_TILE || auto_p1)
+      if (try_p1_fast(m, quad, factors, n_factors, terms, n_terms, want == TFELCU_SCATTER_TILE,
+                      want == TFELCU_SCATTER_TILE && requested == TFELCU_SCATTER_TILE)) return;
   }
   int mode = (requested == TFELCU_SCATTER_AUTO && m->patch_refused)
                  ? TFELCU_SCATTER_ROW_GATHER
@@ -631,7 +633,8 @@ static bool try_ride_along(tfelcu_vector* v, int quad, const tfelcu_factor* fact
   if (!fbv.const_coef) return false;
   std::unique_ptr<FormBuild> fb(m->pending);
   m->pending = nullptr; ctx->pending_matrix = nullptr;
-  TFELCU_REQUIRE(assemble_tiles(m, *fb, v, &fbv), "tile assembly: the plan of a deferred += is gone");
+  const bool ok = m->pending_mode == 1 ? assemble_tiles(m, *fb, v, &fbv) : assemble_p1_rows(m, *fb, v, &fbv);
+  TFELCU_REQUIRE(ok, "assembly: the plan of a deferred += is gone");
   m->pristine = false;
   return true;
 }
@@ -641,6 +644,7 @@ void assemble_linear(tfelcu_vector* v, int quad, const tfelcu_factor* factors, i
   for (int t = 0; t < n_terms; ++t)
     TFELCU_REQUIRE(terms[t].test_comp >= 0 && terms[t].test_comp < v->space.n, "test component out of range");
   if (try_ride_along(v, quad, factors, n_factors, terms, n_terms)) return;
+  v->ensure_cleared();
   const int requested = v->scatter;
   const int nd = v->space.fes[0]->nd;
   int mode = (requested == TFELCU_SCATTER_AUTO && v->patch_refused) ? TFELCU_SCATTER_ROW_GATHER

@@ -157,6 +157,12 @@ struct tfelcu_vector {
   tfelcu::DevBuf<double> data;
   int scatter = TFELCU_SCATTER_AUTO;
   bool patch_refused = false;
+  bool zero_pending = false;            // clear() is pending: the next writer starts from zero, every other user zeroes first
+  void ensure_cleared() {
+    if (!zero_pending) return;
+    zero_pending = false;
+    ctx->zero(data.p, data.n);
+  }
 };
 
 struct tfelcu_matrix {
@@ -199,8 +205,11 @@ struct tfelcu_matrix {
   // a += (constant-coefficient form) that has been accepted but not launched yet: a linear form on the same space that
   // follows rides along in the same pass over the mesh (tile.cu); every other use of the matrix launches it first
   tfelcu::FormBuild* pending = nullptr;
-  tfelcu::DevBuf<double> pending_tables;
-  std::vector<double> pending_tables_host;   // what pending_tables holds (an unchanged form is not uploaded again)
+  int pending_mode = 0;                 // 0: P1 rows (p1rows.cu), 1: tiles (tile.cu)
+  // P1 x P1 triangle forms with constant coefficients (p1rows.cu): the packed records in a blocked ELL layout
+  bool has_ell = false, ell_compact = false;   // compact: 8-byte records (vertex offsets from the row's own vertex)
+  tfelcu::DevBuf<uint32_t> ell;         // uint4 records [ell_ptr[block] + k][128 rows of the block]
+  tfelcu::DevBuf<unsigned int> ell_ptr, ell_deg;
   ~tfelcu_matrix() { if (tile_plan) tfelcu::tile_plan_free(tile_plan); if (pending) tfelcu::form_build_free(pending); }
   // cell colouring (TFELCU_SCATTER_COLORED): cells sorted by colour
   bool has_colors = false;
@@ -240,6 +249,10 @@ void matrix_ensure_cleared(tfelcu_matrix* m);
 // ---- tile.cu
 bool tile_applicable(const tfelcu_matrix* m);
 bool matrix_tile_plan_ready(tfelcu_matrix* m);
+// ---- p1rows.cu
+bool p1rows_applicable(const tfelcu_matrix* m);
+bool matrix_ell_ready(tfelcu_matrix* m);
+bool assemble_p1_rows(tfelcu_matrix* m, const FormBuild& fb, tfelcu_vector* v, const FormBuild* fbv);
 bool assemble_tiles(tfelcu_matrix* m, const FormBuild& fb, tfelcu_vector* v, const FormBuild* fbv);
 void matrix_flush_pending(tfelcu_matrix* m);     // assemble.cu: launch an accepted-but-deferred +=
 void matrix_build_slots(tfelcu_matrix* m);

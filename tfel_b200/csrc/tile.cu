@@ -1,21 +1,25 @@
 // Tile assembly: bilinear_form::operator+= (src/core/bilinear_form.hpp:23-110) and linear_form::operator+=
-// (linear_form.hpp:20-142) for vertex-based (P1) spaces, cell-centric with graph colouring inside shared-memory tiles --
-// the scatter north_star names ("graph coloring, not atomics, so the result is deterministic"), arranged so that every
-// cell, every vertex coordinate and every stored value crosses HBM once.
+// (linear_form.hpp:20-142) for vertex-based (P1) spaces on triangles, cell-centric inside shared-memory tiles, so that
+// every cell, every vertex coordinate and every stored value crosses HBM once and every element matrix is computed once.
 //
 // The owner-computes rows of assemble.cu recompute the geometry of every cell once per incident row (dim + 1 times) and
 // stream a 16-byte record per (row, cell): 2.5 GB of traffic for 1.6 GB of algorithmic bytes on configs[1]. Here the rows
 // are grouped into compact tiles of the mesh (the quadtree / octree leaves of patch.cu: 16 x 16 vertices on a uniform
 // grid) and ONE contiguous blob per tile, built once per pattern, holds everything a CTA needs:
-//     header | coordinates of the tile's vertices (owned + rim) | per-vertex stage offsets | per-row CSR positions |
-//     one 8-byte record per cell: three tile-local vertex indices (9 bits each) + nine 4-bit slots
-// The cells of a tile are sorted by COLOUR (no two cells of a colour share a vertex; Jones-Plassmann rounds with fixed
-// hashed priorities in shared memory, deterministic). A CTA computes each element matrix once, in registers, and adds it
-// colour by colour into the shared-memory image of its CSR rows: race-free without atomics, the order of the additions to
-// an entry is the colour order -- bitwise reproducible. Rows are then written run by run, coalesced, each stored value
-// exactly once. Cells on the rim of a tile are recomputed by the neighbouring tile (~13 %). A constant-coefficient linear
-// form on the same space can ride along (one pass over the mesh for A and b).
-#include "element.cuh"
+//     header | coordinates of the tile's vertices (owned + rim) | per-vertex row info | per-row CSR positions |
+//     one 12-byte record per cell: three tile-local vertex indices (9 bits each), nine 4-bit slots (position of column
+//     dof(k, j) in row dof(k, i)) and, for each of its three rows, the RANK of the cell among the cells of that row
+// Phase 1: one thread per cell computes the element matrix (closed form for P1: the gradients are constant on a cell) and
+// stores row i of it at [row of vertex i][rank] in shared memory -- a private location, no atomics, no colours.
+// Phase 2: one thread per row adds its contributions in rank order = ascending cell order = the order of the reference's
+// cell loop (the same sums as the owner-computes rows, bit for bit when the quadrature weights sum to exactly 1) into the
+// shared-memory image of its CSR row. Rows are then written run by run, coalesced, each stored value exactly once.
+// Cells on the rim of a tile are recomputed by the neighbouring tile (~13 %). A constant-coefficient linear form on the
+// same space rides along as a fourth value per contribution (one pass over the mesh for A and b).
+// (A first version accumulated colour by colour -- Jones-Plassmann colours inside the tile, one CTA barrier per colour --
+// and was slower than the rows: 1700 instructions per warp and tile, a third of the stall samples on those barriers;
+// profiles/r02_ncu_tile_assembly.md.)
+#include "p1form.cuh"
 #include "sortutil.cuh"
 
 #include <cstdlib>
@@ -26,30 +30,30 @@ namespace {
 
 constexpr int kTileThreads = 256;
 constexpr int kTileMaxRefs = 4096;     // (dim + 1) x cells of a tile, padded to a power of two
-constexpr int kTileMaxVerts = 511;     // 9-bit local vertex indices, 0x1ff never used
-constexpr int kTileMaxColors = 24;
+constexpr int kTileMaxVerts = 511;     // 9-bit local vertex indices
+constexpr int kTileMaxDeg = 15;        // cells per row: 4-bit ranks
 constexpr int kTileRows = 256;
 
-struct alignas(16) TileHeader {        // 80 bytes
-  uint16_t n_rows, n_verts, n_cells, n_colors;
-  uint32_t stage_len, pad;
-  uint16_t color_off[kTileMaxColors + 2];   // cells of colour c: [color_off[c], color_off[c + 1]) in record order
-  uint16_t pad2[6];
+struct alignas(16) TileHeader {        // 32 bytes
+  uint16_t n_rows, n_verts, n_cells, max_deg;
+  uint32_t stage_len, pad[5];
 };
-static_assert(sizeof(TileHeader) == 80, "tile header layout");
+static_assert(sizeof(TileHeader) == 32, "tile header layout");
 
 __host__ __device__ inline size_t pad16(size_t b) { return (b + 15) & ~(size_t)15; }
 
 // byte offsets of the sections of a blob
 struct TileLayout {
-  size_t coords, vinfo, rows, rowmeta, records, total;
+  size_t coords, vinfo, rows, rowmeta, rec0, rec1, rec2, total;
   __host__ __device__ TileLayout(int R, int V, int C) {
     coords = sizeof(TileHeader);
     vinfo = coords + (size_t)V * 16;
     rows = vinfo + pad16((size_t)V * 4);
     rowmeta = rows + pad16((size_t)R * 8);
-    records = rowmeta + pad16((size_t)R * 4);
-    total = records + pad16((size_t)C * 8);
+    rec0 = rowmeta + pad16((size_t)R * 4);
+    rec1 = rec0 + pad16((size_t)C * 4);
+    rec2 = rec1 + pad16((size_t)C * 4);
+    total = rec2 + pad16((size_t)C * 4);
   }
 };
 
@@ -99,11 +103,6 @@ __device__ __forceinline__ int lower_bound_u32(const uint32_t* a, int n, uint32_
   return lo;
 }
 
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {
-  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-  return x;
-}
-
 struct TileBuildArgs {
   const uint32_t* patch_row_ptr; const uint32_t* patch_rows; const uint32_t* patch_cell_ptr; const uint32_t* patch_cells;
   const uint32_t* cells; const double* vertices;
@@ -111,37 +110,34 @@ struct TileBuildArgs {
   uint32_t off_te; size_t to_local;          // global row = off_te + dof; local row = dof + to_local
   unsigned long long* sizes;                 // PASS 0: bytes of every blob
   const unsigned long long* blob_ptr; unsigned char* blob;   // PASS 1
-  int* status;                               // 1: a tile exceeds a capacity (vertices, colours, row length, stage)
-  unsigned int* maxima;                      // [0] rows, [1] vertices, [2] stage entries, [3] colours
+  int* status;                               // 1: a tile exceeds a capacity (vertices, cells per row, row length, stage)
+  unsigned int* maxima;                      // [0] rows, [1] vertices, [2] stage entries, [3] cells per row
 };
 
-// One CTA per tile. DIM = 2 (triangles). PASS 0 sizes the blob, PASS 1 writes it.
+// One CTA per tile (triangles). PASS 0 sizes the blob, PASS 1 writes it.
 template <int PASS>
 __global__ void __launch_bounds__(kTileThreads) k_tile_build(const TileBuildArgs A) {
   constexpr int NV = 3;
   extern __shared__ unsigned char tb_sm[];
   uint32_t* sorted = reinterpret_cast<uint32_t*>(tb_sm);                 // [kTileMaxRefs]
   uint32_t* uvert = sorted + kTileMaxRefs;                               // [512]
-  uint32_t* vinfo = uvert + 512;                                         // [512]
+  uint32_t* vinfo = uvert + 512;                                         // [512] owned ordinal or kNoRow
   int* vlen = reinterpret_cast<int*>(vinfo + 512);                       // [512] row length of owned vertices -> stage offsets
-  uint32_t* vmax = reinterpret_cast<uint32_t*>(vlen + 512);              // [512]
-  uint32_t* used = vmax + 512;                                           // [512]
-  int* scratch = reinterpret_cast<int*>(used + 512);                     // [kTileThreads + 1] + flags
+  int* vdeg = vlen + 512;                                                // [512] cells of the tile at the vertex
+  int* scratch = vdeg + 512;                                             // [kTileThreads + 8]
   int* head = scratch + kTileThreads + 8;                                // [kTileMaxRefs] unique flags / offsets
   uint16_t* clv = reinterpret_cast<uint16_t*>(head + kTileMaxRefs);      // [kTileMaxRefs] local vertex of every cell ref
-  uint8_t* color = reinterpret_cast<uint8_t*>(clv + kTileMaxRefs);       // [kTileMaxRefs / 3 + 1]
-  uint16_t* order = reinterpret_cast<uint16_t*>(color + 1376);           // [1376] cells sorted by colour
-  uint8_t* vdir = reinterpret_cast<uint8_t*>(order + 1376);              // [512] owned Dirichlet rows (identity rows)
-  __shared__ int s_ncolors, s_left, s_bad;
-  __shared__ int ccount[kTileMaxColors + 2];
+  uint8_t* rank = reinterpret_cast<uint8_t*>(clv + kTileMaxRefs);        // [kTileMaxRefs] rank of the cell at that vertex
+  uint8_t* vdir = rank + kTileMaxRefs;                                   // [512] owned Dirichlet rows (identity rows)
+  __shared__ int s_bad, s_maxdeg;
 
   const size_t tile = blockIdx.x;
   const uint32_t r_begin = A.patch_row_ptr[tile], r_end = A.patch_row_ptr[tile + 1];
   const uint32_t c_begin = A.patch_cell_ptr[tile], c_end = A.patch_cell_ptr[tile + 1];
   const int R = (int)(r_end - r_begin), C = (int)(c_end - c_begin);
-  if (threadIdx.x == 0) { s_bad = 0; s_ncolors = 0; }
+  if (threadIdx.x == 0) { s_bad = 0; s_maxdeg = 0; }
   __syncthreads();
-  if (C * NV > kTileMaxRefs || R > kTileRows * 2 || C > 1365) {
+  if (C * NV > kTileMaxRefs || R > 511 || C > 1365) {
     if (threadIdx.x == 0) { atomicExch(A.status, 1); if (PASS == 0) A.sizes[tile] = 0; }
     return;
   }
@@ -175,7 +171,7 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_build(const TileBuildArgs
     int len = 0;
     if (owned) { const size_t lrow = (size_t)v + A.to_local; len = A.rowptr[lrow + 1] - A.rowptr[lrow]; }
     vlen[lv] = len;
-    vinfo[lv] = owned ? (uint32_t)t : kNoRow;      // owned ordinal for now
+    vinfo[lv] = owned ? (uint32_t)t : kNoRow;
     vdir[lv] = (owned && A.dir_row[(size_t)A.off_te + v] != 0) ? 1 : 0;
     if (owned && len > 16) atomicExch(&s_bad, 1);  // 4-bit slots
   }
@@ -185,98 +181,60 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_build(const TileBuildArgs
     if (threadIdx.x == 0) { atomicExch(A.status, 1); if (PASS == 0) A.sizes[tile] = 0; }
     return;
   }
-  // 4. local vertex of every cell reference (cells in the plan's order: ascending cell id)
-  for (int t = threadIdx.x; t < C * NV; t += kTileThreads) {
-    const uint32_t v = A.cells[(size_t)A.patch_cells[c_begin + t / NV] * NV + t % NV];
-    clv[t] = (uint16_t)lower_bound_u32(uvert, V, v);
+  // 4. local vertex of every cell reference (cells in the plan's order: ascending cell id) and the rank of the cell among
+  //    the cells of the tile at that vertex: sort (vertex, cell, i) keys, rank = position inside the vertex's run
+  for (int t = threadIdx.x; t < P; t += kTileThreads) {
+    uint32_t key = 0xffffffffu;
+    if (t < C * NV) {
+      const uint32_t v = A.cells[(size_t)A.patch_cells[c_begin + t / NV] * NV + t % NV];
+      const int lv = lower_bound_u32(uvert, V, v);
+      clv[t] = (uint16_t)lv;
+      key = ((uint32_t)lv << 13) | (uint32_t)t;      // t = cell * 3 + i < 4096 = 2^12
+    }
+    sorted[t] = key;
   }
-  // 5. colouring: rounds of "local maxima of the hashed priority take the smallest colour free at their vertices"
-  for (int lv = threadIdx.x; lv < V; lv += kTileThreads) { vmax[lv] = 0u; used[lv] = 0u; }
-  for (int c = threadIdx.x; c < C; c += kTileThreads) color[c] = 0xff;
-  if (threadIdx.x == 0) s_left = C;
   __syncthreads();
-  for (int round = 0; round < 64; ++round) {
-    if (s_left == 0) break;
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += kTileThreads) {
-      if (color[c] != 0xff) continue;
-      const uint32_t pr = (mix32(A.patch_cells[c_begin + c]) & 0xfffff000u) | (uint32_t)(c + 1);   // distinct inside a tile
-#pragma unroll
-      for (int v = 0; v < NV; ++v) atomicMax(&vmax[clv[c * NV + v]], pr);
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += kTileThreads) {
-      if (color[c] != 0xff) continue;
-      const uint32_t pr = (mix32(A.patch_cells[c_begin + c]) & 0xfffff000u) | (uint32_t)(c + 1);
-      bool top = true;
-      uint32_t busy = 0u;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) { const int lv = clv[c * NV + v]; top = top && vmax[lv] == pr; busy |= used[lv]; }
-      if (!top) continue;
-      const int col = __ffs(~busy) - 1;     // smallest colour not used at any of its vertices
-      if (col < 0 || col >= kTileMaxColors) { atomicExch(&s_bad, 1); color[c] = 0; }
-      else {
-        color[c] = (uint8_t)col;
-        // the winners of a round share no vertex (each vertex has one maximum): plain ORs would race only with other
-        // winners of OTHER vertices of the same word -- use the atomic form
-#pragma unroll
-        for (int v = 0; v < NV; ++v) atomicOr(&used[clv[c * NV + v]], 1u << col);
-        atomicMax(&s_ncolors, col + 1);
-      }
-      atomicSub(&s_left, 1);
-    }
-    __syncthreads();
-    for (int lv = threadIdx.x; lv < V; lv += kTileThreads) vmax[lv] = 0u;
-    __syncthreads();
+  block_bitonic_sort(sorted, P);
+  for (int t = threadIdx.x; t < C * NV; t += kTileThreads) {
+    const uint32_t key = sorted[t];
+    const uint32_t lv = key >> 13;
+    const int first = lower_bound_u32(sorted, C * NV, lv << 13);
+    const int rk = t - first;
+    if (rk > kTileMaxDeg) atomicExch(&s_bad, 1);
+    rank[key & 0x1fffu] = (uint8_t)rk;
+    const bool last = (t + 1 == C * NV) || (sorted[t + 1] >> 13) != lv;
+    if (last) { vdeg[lv] = rk + 1; atomicMax(&s_maxdeg, rk + 1); }
   }
-  if (s_left != 0 || s_bad) {
+  __syncthreads();
+  if (s_bad) {
     if (threadIdx.x == 0) { atomicExch(A.status, 1); if (PASS == 0) A.sizes[tile] = 0; }
     return;
   }
-  const int NC = s_ncolors;
   if (PASS == 0) {
     if (threadIdx.x == 0) {
       A.sizes[tile] = TileLayout(R, V, C).total;
       atomicMax(A.maxima + 0, (unsigned)R); atomicMax(A.maxima + 1, (unsigned)V);
-      atomicMax(A.maxima + 2, (unsigned)S); atomicMax(A.maxima + 3, (unsigned)NC);
+      atomicMax(A.maxima + 2, (unsigned)S); atomicMax(A.maxima + 3, (unsigned)s_maxdeg);
     }
     return;
   }
-  // 6. cells sorted by colour (stable: ascending cell id inside a colour)
-  if (threadIdx.x <= kTileMaxColors) ccount[threadIdx.x] = 0;
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += kTileThreads) atomicAdd(&ccount[color[c]], 1);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int k = 0; k <= kTileMaxColors; ++k) { const int v = ccount[k]; ccount[k] = run; run += v; }
-  }
-  __syncthreads();
-  // rank of a cell inside its colour = cells of the same colour before it (C <= 1365: a scan per thread is fine)
-  for (int c = threadIdx.x; c < C; c += kTileThreads) {
-    const int col = color[c];
-    int rank = 0;
-    for (int d = 0; d < c; ++d) rank += (color[d] == col) ? 1 : 0;
-    order[ccount[col] + rank] = (uint16_t)c;
-  }
-  __syncthreads();
-  // 7. write the blob
+  // 5. write the blob
   unsigned char* out = A.blob + A.blob_ptr[tile];
   const TileLayout L(R, V, C);
   if (threadIdx.x == 0) {
     TileHeader H;
-    H.n_rows = (uint16_t)R; H.n_verts = (uint16_t)V; H.n_cells = (uint16_t)C; H.n_colors = (uint16_t)NC;
-    H.stage_len = (uint32_t)S; H.pad = 0;
-    for (int k = 0; k <= kTileMaxColors + 1; ++k) H.color_off[k] = (uint16_t)(k <= kTileMaxColors ? ccount[k] : C);
-    for (int k = NC; k <= kTileMaxColors + 1; ++k) H.color_off[k] = (uint16_t)C;
-    for (int k = 0; k < 6; ++k) H.pad2[k] = 0;
+    H.n_rows = (uint16_t)R; H.n_verts = (uint16_t)V; H.n_cells = (uint16_t)C; H.max_deg = (uint16_t)s_maxdeg;
+    H.stage_len = (uint32_t)S;
+    for (int k = 0; k < 5; ++k) H.pad[k] = 0;
     *reinterpret_cast<TileHeader*>(out) = H;
   }
   double2* o_coords = reinterpret_cast<double2*>(out + L.coords);
   uint32_t* o_vinfo = reinterpret_cast<uint32_t*>(out + L.vinfo);
   int2* o_rows = reinterpret_cast<int2*>(out + L.rows);
   uint32_t* o_meta = reinterpret_cast<uint32_t*>(out + L.rowmeta);
-  unsigned long long* o_rec = reinterpret_cast<unsigned long long*>(out + L.records);
+  uint32_t* o_rec0 = reinterpret_cast<uint32_t*>(out + L.rec0);
+  uint32_t* o_rec1 = reinterpret_cast<uint32_t*>(out + L.rec1);
+  uint32_t* o_rec2 = reinterpret_cast<uint32_t*>(out + L.rec2);
   for (int lv = threadIdx.x; lv < V; lv += kTileThreads) {
     const uint32_t v = uvert[lv];
     o_coords[lv] = reinterpret_cast<const double2*>(A.vertices)[v];
@@ -294,19 +252,22 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_build(const TileBuildArgs
         diag = lo - rs;
       }
       o_rows[t] = make_int2(rs, (int)lrow);
-      o_meta[t] = (uint32_t)vlen[lv] | ((uint32_t)len << 16) | ((uint32_t)diag << 24) | (dir ? 0x80000000u : 0u);
-      // stage offset | owned ordinal << 16 | owned | accumulates into A (identity rows take no contributions,
-      // bilinear_form.hpp:183-186; the linear form is not filtered, linear_form.hpp:55-63)
-      info = (uint32_t)vlen[lv] | (t << 16) | 0x40000000u | (dir ? 0u : 0x80000000u);
+      // stage offset (16) | row length (5) | cells at the row (4) | diagonal slot (4) | identity row
+      o_meta[t] = (uint32_t)vlen[lv] | ((uint32_t)len << 16) | ((uint32_t)vdeg[lv] << 21) | ((uint32_t)diag << 25) | (dir ? 0x80000000u : 0u);
+      info = t | 0x80000000u;     // owned ordinal | owned
     }
     o_vinfo[lv] = info;
   }
-  for (int e = threadIdx.x; e < C; e += kTileThreads) {
-    const int c = order[e];
-    unsigned long long rec = 0ull;
+  for (int c = threadIdx.x; c < C; c += kTileThreads) {
     uint32_t ids[NV];
+    unsigned long long slots = 0ull;
+    uint32_t w0 = 0u, ranks = 0u;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) { ids[v] = uvert[clv[c * NV + v]]; rec |= (unsigned long long)clv[c * NV + v] << (9 * v); }
+    for (int v = 0; v < NV; ++v) {
+      ids[v] = uvert[clv[c * NV + v]];
+      w0 |= (uint32_t)clv[c * NV + v] << (9 * v);
+      ranks |= (uint32_t)rank[c * NV + v] << (4 * v);
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int lv = clv[c * NV + i];
@@ -319,15 +280,20 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_build(const TileBuildArgs
         int lo = rs, hi = re;
         while (lo < hi) { const int mid = lo + ((hi - lo) >> 1); if (A.colind[mid] < gcol) lo = mid + 1; else hi = mid; }
         if (lo >= re || A.colind[lo] != gcol) atomicExch(A.status, 2);
-        rec |= (unsigned long long)((lo - rs) & 0xf) << (27 + 4 * (i * NV + j));
+        slots |= (unsigned long long)((lo - rs) & 0xf) << (4 * (i * NV + j));
       }
     }
-    o_rec[e] = rec;
+    // w0: three local vertices (27 bits) | rank at vertex 0 (4 bits); w1: slots of rows 0 and 1 (24 bits) | ranks at
+    // vertices 1 and 2 (8 bits); w2: slots of row 2 (12 bits)
+    o_rec0[c] = w0 | ((ranks & 0xfu) << 27);
+    o_rec1[c] = (uint32_t)(slots & 0xffffffull) | ((ranks >> 4) << 24);
+    o_rec2[c] = (uint32_t)(slots >> 24);
   }
 }
 
 size_t tile_build_smem() {
-  return (size_t)kTileMaxRefs * 4 + 512 * 4 * 5 + (kTileThreads + 8) * 4 + (size_t)kTileMaxRefs * 4 + (size_t)kTileMaxRefs * 2 + 1376 + 1376 * 2 + 512 + 64;
+  return (size_t)kTileMaxRefs * 4 + 512 * 4 * 4 + (kTileThreads + 8) * 4 + (size_t)kTileMaxRefs * 4 + (size_t)kTileMaxRefs * 2 +
+         (size_t)kTileMaxRefs + 512 + 64;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -337,102 +303,109 @@ size_t tile_build_smem() {
 struct TileAsm {
   const unsigned long long* blob_ptr; const unsigned char* blob;
   double* val; int init_mode;                  // 1: the values are uninitialised (pending clear()): write them fresh
-  double* b; int b_mode;                       // fused linear form: 0 none, 1 b += ..., (b is indexed by local row)
-  double b_c[3];                               // its reference weights: sum_t c_t mhat_i (constant coefficient, order 0)
+  double* b;                                   // fused linear form (indexed by local row), or nullptr
+  int b_init;                                  // 1: its clear() is pending: write the entries
+  int max_deg;                                 // capacity of the contribution lists (cells per row), over all tiles
 };
 
-// element matrix of a constant-coefficient form on a P1 triangle (without |K|): the W x W tensor
-// G = [c00, c0r^T Jmt; Jmt^T cr0, Jmt^T C Jmt] contracted with the pre-integrated reference tensor in shared memory
-__device__ __forceinline__ void tile_element(const FormDev& F, const double* sm_ref, const CellGeom<2>& g, double (&acc)[9]) {
-  element_matrix_const<2, 3, 3>(F, sm_ref - F.off_ref, g, acc);
-}
-
 template <bool FUSE_B>
-__global__ void __launch_bounds__(kTileThreads)
-k_assemble_tiles(const __grid_constant__ FormDev F, const TileAsm T) {
+__global__ void __launch_bounds__(kTileThreads, 3)
+k_assemble_tiles(const __grid_constant__ P1Form F, const TileAsm T) {
   extern __shared__ __align__(16) double tsm[];
   __shared__ TileHeader H;
   const unsigned char* blob = T.blob + T.blob_ptr[blockIdx.x];
   if (threadIdx.x < sizeof(TileHeader) / 4) reinterpret_cast<uint32_t*>(&H)[threadIdx.x] = reinterpret_cast<const uint32_t*>(blob)[threadIdx.x];
-  // reference tensor of the form (the last table)
-  const int n_ref = F.n_stage - F.off_ref;
-  double* s_ref = tsm;
-  for (int i = threadIdx.x; i < n_ref; i += kTileThreads) s_ref[i] = __ldg(F.tables + F.off_ref + i);
   __syncthreads();
-  const int R = H.n_rows, V = H.n_verts, C = H.n_cells, NC = H.n_colors, S = (int)H.stage_len;
+  const int R = H.n_rows, V = H.n_verts, C = H.n_cells, S = (int)H.stage_len;
+  const int D = T.max_deg;
   const TileLayout L(R, V, C);
-  double2* s_xy = reinterpret_cast<double2*>(s_ref + ((n_ref + 1) & ~1));
+  // shared memory: contributions [R][D] x 4 doubles (row i of an element matrix | its linear-form entry), coordinates,
+  // stage (image of the CSR rows), per-vertex row info, slots of every contribution
+  double4* s_con = reinterpret_cast<double4*>(tsm);
+  double2* s_xy = reinterpret_cast<double2*>(s_con + (size_t)R * D);
   double* s_stage = reinterpret_cast<double*>(s_xy + V);
-  double* s_b = s_stage + S;                                   // [R] when FUSE_B
-  uint32_t* s_vinfo = reinterpret_cast<uint32_t*>(s_b + (FUSE_B ? R : 0));
+  uint32_t* s_vinfo = reinterpret_cast<uint32_t*>(s_stage + S);
+  uint16_t* s_slot = reinterpret_cast<uint16_t*>(s_vinfo + V);
   const double2* g_xy = reinterpret_cast<const double2*>(blob + L.coords);
   const uint32_t* g_vinfo = reinterpret_cast<const uint32_t*>(blob + L.vinfo);
   const int2* g_rows = reinterpret_cast<const int2*>(blob + L.rows);
   const uint32_t* g_meta = reinterpret_cast<const uint32_t*>(blob + L.rowmeta);
-  const unsigned long long* g_rec = reinterpret_cast<const unsigned long long*>(blob + L.records);
+  const uint32_t* g_rec0 = reinterpret_cast<const uint32_t*>(blob + L.rec0);
+  const uint32_t* g_rec1 = reinterpret_cast<const uint32_t*>(blob + L.rec1);
+  const uint32_t* g_rec2 = reinterpret_cast<const uint32_t*>(blob + L.rec2);
   for (int i = threadIdx.x; i < V; i += kTileThreads) { s_xy[i] = __ldg(g_xy + i); s_vinfo[i] = __ldg(g_vinfo + i); }
-  for (int i = threadIdx.x; i < S; i += kTileThreads) s_stage[i] = 0.0;
-  if (FUSE_B) for (int i = threadIdx.x; i < R; i += kTileThreads) s_b[i] = 0.0;
-  __syncthreads();
-  if (T.init_mode)   // identity rows of the Dirichlet dofs
-    for (int t = threadIdx.x; t < R; t += kTileThreads) {
-      const uint32_t m = __ldg(g_meta + t);
-      if (m & 0x80000000u) s_stage[(m & 0xffffu) + ((m >> 24) & 0x7fu)] = 1.0;
-    }
-  // cells in record order (sorted by colour), one chunk of kTileThreads cells at a time
-  for (int c0 = 0; c0 < C; c0 += kTileThreads) {
-    const int c = c0 + threadIdx.x;
-    double acc[9];
-    double vol = 0.0;
-    uint32_t info[3] = {0u, 0u, 0u};
-    unsigned long long rec = 0ull;
-    int my_color = -1;
-    if (c < C) {
-      rec = __ldg(g_rec + c);
-      const int l0 = (int)(rec & 0x1ff), l1 = (int)((rec >> 9) & 0x1ff), l2 = (int)((rec >> 18) & 0x1ff);
-      const double2 p0 = s_xy[l0], p1 = s_xy[l1], p2 = s_xy[l2];
-      CellGeom<2> g;
-      g.v0[0] = p0.x; g.v0[1] = p0.y;
-      g.J[0][0] = p1.x - p0.x; g.J[1][0] = p1.y - p0.y;
-      g.J[0][1] = p2.x - p0.x; g.J[1][1] = p2.y - p0.y;
-      finish_cell_geometry<2>(g);
-      tile_element(F, s_ref, g, acc);
-      vol = g.vol;
-      info[0] = s_vinfo[l0]; info[1] = s_vinfo[l1]; info[2] = s_vinfo[l2];
-      my_color = 0;
-      while (c >= (int)H.color_off[my_color + 1]) ++my_color;
-    }
-    // colours present in this chunk
-    int first = 0;
-    while (c0 >= (int)H.color_off[first + 1]) ++first;
-    const int last_cell = min(c0 + kTileThreads, C) - 1;
-    int last = first;
-    while (last_cell >= (int)H.color_off[last + 1]) ++last;
-    for (int col = first; col <= last && col < NC; ++col) {
-      if (my_color == col) {
+  // the records of this thread's cells are requested before the barrier
+  uint32_t w0[2], w1[2], w2[2];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          if (info[i] & 0x80000000u) {
-            double* row = s_stage + (info[i] & 0xffffu);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) row[(rec >> (27 + 4 * (i * 3 + j))) & 0xf] += acc[i * 3 + j] * vol;
-          }
-          if (FUSE_B && (info[i] & 0x40000000u)) s_b[(info[i] >> 16) & 0x1ffu] += T.b_c[i] * vol;
-        }
-      }
-      __syncthreads();
-    }
+  for (int u = 0; u < 2; ++u) {
+    const int c = threadIdx.x + u * kTileThreads;
+    w0[u] = c < C ? __ldg(g_rec0 + c) : 0u; w1[u] = c < C ? __ldg(g_rec1 + c) : 0u; w2[u] = c < C ? __ldg(g_rec2 + c) : 0u;
   }
   __syncthreads();
-  // write-out: a warp takes 32 consecutive owned rows, splits them into runs of rows that are consecutive in the CSR
+  // ---- phase 1: element matrices, row i -> contribution list of the row of vertex i -----------------------------------
+  auto cell = [&](uint32_t r0, uint32_t r1, uint32_t r2) {
+    const int l0 = (int)(r0 & 0x1ff), l1 = (int)((r0 >> 9) & 0x1ff), l2 = (int)((r0 >> 18) & 0x1ff);
+    const double2 p0 = s_xy[l0], p1 = s_xy[l1], p2 = s_xy[l2];
+    const double J00 = p1.x - p0.x, J10 = p1.y - p0.y, J01 = p2.x - p0.x, J11 = p2.y - p0.y;
+    const double det = J00 * J11 - J10 * J01;
+    const double vol = 0.5 * fabs(det);
+    const double rdet = 1.0 / det;
+    double jmt[2][2];
+    jmt[0][0] = J11 * rdet; jmt[0][1] = -J10 * rdet; jmt[1][0] = -J01 * rdet; jmt[1][1] = J00 * rdet;
+    double K[9];
+    p1_element(F, jmt, K);
+    const uint32_t ranks = (r0 >> 27) | ((r1 >> 24) << 4);
+    const unsigned long long slots = (unsigned long long)(r1 & 0xffffffu) | ((unsigned long long)r2 << 24);
+    const uint32_t i0 = s_vinfo[l0], i1 = s_vinfo[l1], i2 = s_vinfo[l2];
+    if (i0 & 0x80000000u) {                                  // else: the row belongs to another tile
+      const int at = (int)(i0 & 0x1ffu) * D + (int)(ranks & 0xfu);
+      s_con[at] = make_double4(K[0] * vol, K[1] * vol, K[2] * vol, FUSE_B ? F.b_c[0] * vol : 0.0);
+      s_slot[at] = (uint16_t)(slots & 0xfffu);
+    }
+    if (i1 & 0x80000000u) {
+      const int at = (int)(i1 & 0x1ffu) * D + (int)((ranks >> 4) & 0xfu);
+      s_con[at] = make_double4(K[3] * vol, K[4] * vol, K[5] * vol, FUSE_B ? F.b_c[1] * vol : 0.0);
+      s_slot[at] = (uint16_t)((slots >> 12) & 0xfffu);
+    }
+    if (i2 & 0x80000000u) {
+      const int at = (int)(i2 & 0x1ffu) * D + (int)((ranks >> 8) & 0xfu);
+      s_con[at] = make_double4(K[6] * vol, K[7] * vol, K[8] * vol, FUSE_B ? F.b_c[2] * vol : 0.0);
+      s_slot[at] = (uint16_t)((slots >> 24) & 0xfffu);
+    }
+  };
+  if ((int)threadIdx.x < C) cell(w0[0], w1[0], w2[0]);
+  if ((int)threadIdx.x + kTileThreads < C) cell(w0[1], w1[1], w2[1]);
+  for (int c = threadIdx.x + 2 * kTileThreads; c < C; c += kTileThreads) cell(__ldg(g_rec0 + c), __ldg(g_rec1 + c), __ldg(g_rec2 + c));
+  __syncthreads();
+  // ---- phase 2: every row adds its contributions in rank order (ascending cell id) ----------------------------------
+  for (int t = threadIdx.x; t < R; t += kTileThreads) {
+    const uint32_t m = __ldg(g_meta + t);
+    const int off = (int)(m & 0xffffu), len = (int)((m >> 16) & 0x1fu), deg = (int)((m >> 21) & 0xfu);
+    const bool dir = (m & 0x80000000u) != 0u;
+    double* row = s_stage + off;
+    for (int e = 0; e < len; ++e) row[e] = 0.0;
+    if (dir && T.init_mode) row[(m >> 25) & 0xfu] = 1.0;   // identity rows of the Dirichlet dofs (clear())
+    double bsum = 0.0;
+    for (int k = 0; k < deg; ++k) {
+      const double4 v = s_con[t * D + k];
+      if (!dir) {
+        const uint32_t sl = s_slot[t * D + k];
+        row[sl & 0xfu] += v.x; row[(sl >> 4) & 0xfu] += v.y; row[(sl >> 8) & 0xfu] += v.z;
+      }
+      if (FUSE_B) bsum += v.w;
+    }
+    if (FUSE_B) { const int2 rr = __ldg(g_rows + t); T.b[rr.y] = T.b_init ? bsum : T.b[rr.y] + bsum; }
+  }
+  __syncthreads();
+  // ---- write-out: a warp takes 32 consecutive owned rows, splits them into runs of rows that are consecutive in the CSR
   // arrays and copies every run with coalesced stores
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int t0 = warp * 32; t0 < R; t0 += (kTileThreads / 32) * 32) {
+  for (int t0 = warp * 32; t0 < R; t0 += kTileThreads) {
     const int t = t0 + lane;
-    int rs = 0, len = 0, off = 0, lrow = 0;
+    int rs = 0, len = 0, off = 0;
     if (t < R) {
       const int2 rr = __ldg(g_rows + t); const uint32_t m = __ldg(g_meta + t);
-      rs = rr.x; lrow = rr.y; off = (int)(m & 0xffffu); len = (int)((m >> 16) & 0xffu);
+      rs = rr.x; off = (int)(m & 0xffffu); len = (int)((m >> 16) & 0x1fu);
     }
     const int prev_end = __shfl_up_sync(0xffffffffu, rs + len, 1);
     const bool start = (t < R) && (lane == 0 || prev_end != rs);
@@ -448,7 +421,6 @@ k_assemble_tiles(const __grid_constant__ FormDev F, const TileAsm T) {
       if (T.init_mode) for (int e = lane; e < n; e += 32) T.val[(size_t)run_rs + e] = s_stage[run_off + e];
       else for (int e = lane; e < n; e += 32) T.val[(size_t)run_rs + e] += s_stage[run_off + e];
     }
-    if (FUSE_B && t < R) T.b[lrow] += s_b[t];
   }
 }
 
@@ -462,7 +434,7 @@ struct TilePlan {
   size_t n_tile = 0;
   DevBuf<unsigned long long> blob_ptr;
   DevBuf<unsigned char> blob;
-  unsigned max_rows = 0, max_verts = 0, max_stage = 0, max_colors = 0;
+  unsigned max_rows = 0, max_verts = 0, max_stage = 0, max_deg = 0;
   uint64_t pattern_id = 0;
 };
 
@@ -509,7 +481,7 @@ TilePlan* matrix_tile_plan(tfelcu_matrix* m) {
   int h_status = 0; ctx->download(&h_status, status.p, 1);
   if (h_status) { m->tile_refused = true; return nullptr; }   // a tile exceeds a capacity: the caller stays on the rows
   unsigned h_max[4]; ctx->download(h_max, maxima.p, 4);
-  T->max_rows = h_max[0]; T->max_verts = h_max[1]; T->max_stage = h_max[2]; T->max_colors = h_max[3];
+  T->max_rows = h_max[0]; T->max_verts = h_max[1]; T->max_stage = h_max[2]; T->max_deg = h_max[3];
   T->blob_ptr.alloc(T->n_tile + 1);
   exclusive_sum<unsigned long long, unsigned long long>(ctx, sizes.p, T->blob_ptr.p, T->n_tile + 1);
   unsigned long long total = 0; ctx->download(&total, T->blob_ptr.p + T->n_tile, 1);
@@ -520,8 +492,8 @@ TilePlan* matrix_tile_plan(tfelcu_matrix* m) {
   ctx->download(&h_status, status.p, 1);
   TFELCU_REQUIRE(h_status == 0, "tile plan: a column of a cell is missing from the CSR pattern");
   if (std::getenv("TFELCU_TRACE"))
-    std::fprintf(stderr, "[tfelcu trace] tile plan: %zu tiles, %.1f MB, max rows %u verts %u stage %u colours %u\n", T->n_tile,
-                 (double)total / 1e6, T->max_rows, T->max_verts, T->max_stage, T->max_colors);
+    std::fprintf(stderr, "[tfelcu trace] tile plan: %zu tiles, %.1f MB, max rows %u verts %u stage %u cells per row %u\n", T->n_tile,
+                 (double)total / 1e6, T->max_rows, T->max_verts, T->max_stage, T->max_deg);
   m->tile_plan = T.release();
   return m->tile_plan;
 }
@@ -537,27 +509,23 @@ bool assemble_tiles(tfelcu_matrix* m, const FormBuild& fb, tfelcu_vector* v, con
   Ctx* ctx = m->ctx;
   TileAsm K;
   K.blob_ptr = T->blob_ptr.p; K.blob = T->blob.p; K.val = m->val.p; K.init_mode = m->val_valid ? 0 : 1;
-  K.b = nullptr; K.b_mode = 0; K.b_c[0] = K.b_c[1] = K.b_c[2] = 0.0;
-  if (v) {
-    // sum_t c_t D^0 psi_i integrated on the reference cell: mhat[0][i] of the linear form's reference table
-    const FormDev& G = fbv->F;
-    double c = 0.0;
-    for (int t = 0; t < G.n_terms; ++t) c += G.terms[t].c;
-    for (int i = 0; i < 3; ++i) K.b_c[i] = c * fbv->tables[(size_t)G.off_ref + i];
-    K.b = v->data.p; K.b_mode = 1;
-  }
+  K.b = nullptr; K.max_deg = (int)T->max_deg;
+  const P1Form F = make_p1_form(fb, v ? fbv : nullptr);
+  K.b_init = 0;
+  if (v) { K.b = v->data.p; K.b_init = v->zero_pending ? 1 : 0; }
   if (!T->n_tile) { m->val_valid = true; return true; }
-  const int n_ref = fb.F.n_stage - fb.F.off_ref;
-  const size_t smem = ((size_t)((n_ref + 1) & ~1) + 2 * (size_t)T->max_verts + T->max_stage + (v ? T->max_rows : 0)) * sizeof(double) +
-                      (size_t)T->max_verts * 4 + 16;
+  const size_t con = (size_t)T->max_rows * T->max_deg;
+  const size_t smem = con * 32 + (size_t)T->max_verts * 16 + (size_t)T->max_stage * 8 + (size_t)T->max_verts * 4 + con * 2 + 32;
+  TFELCU_REQUIRE(smem <= 200 * 1024, "tile assembly: a tile needs more shared memory than an SM has");
   if (v) {
     ensure_smem(k_assemble_tiles<true>, smem);
-    k_assemble_tiles<true><<<(unsigned)T->n_tile, kTileThreads, smem, ctx->stream>>>(fb.F, K);
+    k_assemble_tiles<true><<<(unsigned)T->n_tile, kTileThreads, smem, ctx->stream>>>(F, K);
   } else {
     ensure_smem(k_assemble_tiles<false>, smem);
-    k_assemble_tiles<false><<<(unsigned)T->n_tile, kTileThreads, smem, ctx->stream>>>(fb.F, K);
+    k_assemble_tiles<false><<<(unsigned)T->n_tile, kTileThreads, smem, ctx->stream>>>(F, K);
   }
   ctx->count(); TFELCU_LAUNCH_CHECK();
+  if (v) v->zero_pending = false;
   m->val_valid = true;
   return true;
 }
