@@ -64,8 +64,12 @@ def _forms(ctx, n, scatter, jitter=0.0, dirichlet=True):
     return m, sp, capi.Matrix(sp, sp, scatter=scatter), capi.Vector(sp)
 
 
+ANISO = [dict(test=(0, 1), trial=(0, 1), c=2.0), dict(test=(0, 2), trial=(0, 2), c=0.5), dict(test=(0, 1), trial=(0, 2), c=0.25)]
+
+
 @pytest.mark.parametrize("fast", FAST, ids=FAST_IDS)
-@pytest.mark.parametrize("terms", [STIFF, MASS, MIXED], ids=["stiffness", "mass", "all_tensor_blocks"])
+@pytest.mark.parametrize("terms", [STIFF, MASS, STIFF + MASS, ANISO, MIXED],
+                         ids=["stiffness", "mass", "stiffness_plus_mass", "anisotropic", "all_tensor_blocks"])
 @pytest.mark.parametrize("dirichlet", [True, False])
 def test_tile_equals_rows_on_a_distorted_mesh(ctx, terms, dirichlet, fast):
     """general triangles (jittered vertices), every block of the constant-coefficient tensor (value x value, value x

@@ -528,6 +528,14 @@ void matrix_flush_pending(tfelcu_matrix* m) {
   m->pristine = false;
 }
 
+// key of a constant-coefficient integrand: quadrature formula + the terms, byte for byte
+static std::vector<unsigned char> form_key(int quad, const tfelcu_term* terms, int n_terms) {
+  std::vector<unsigned char> k(sizeof(int) + (size_t)n_terms * sizeof(tfelcu_term));
+  std::memcpy(k.data(), &quad, sizeof(int));
+  if (n_terms) std::memcpy(k.data() + sizeof(int), terms, (size_t)n_terms * sizeof(tfelcu_term));
+  return k;
+}
+
 // Constant-coefficient forms on P1 triangles: the closed-form row kernel of p1rows.cu (AUTO) or the tiles of tile.cu
 // (TFELCU_SCATTER_TILE). The launch is deferred: a constant-coefficient linear form on the same space that follows is
 // assembled in the same pass.
@@ -540,7 +548,16 @@ static bool try_p1_fast(tfelcu_matrix* m, int quad, const tfelcu_factor* factors
   for (int t = 0; t < n_terms; ++t) if (terms[t].n_factors != 0) { if (explicit_request) refuse("tile assembly: constant coefficients only"); return false; }
   std::unique_ptr<FormBuild> fb(new FormBuild());
   tfelcu_fes* te = m->test.fes[0];
-  build_form(m->ctx, m->mesh, quad, factors, n_factors, terms, n_terms, 0, te->fe, 0, te->fe, *fb);
+  const std::vector<unsigned char> key = form_key(quad, terms, n_terms);
+  if (m->memo_form && m->memo_key == key) {
+    fb->F = m->memo_form->F; fb->tables = m->memo_form->tables; fb->const_coef = m->memo_form->const_coef;
+  } else {
+    build_form(m->ctx, m->mesh, quad, factors, n_factors, terms, n_terms, 0, te->fe, 0, te->fe, *fb);
+    if (m->memo_form) form_build_free(m->memo_form);
+    m->memo_form = new FormBuild();
+    m->memo_form->F = fb->F; m->memo_form->tables = fb->tables; m->memo_form->const_coef = fb->const_coef;
+    m->memo_key = key;
+  }
   if (fb->F.n_terms == 0) return true;   // only (already stored) zeros
   if (!fb->const_coef) return false;
   if (tile) {
@@ -628,7 +645,16 @@ static bool try_ride_along(tfelcu_vector* v, int quad, const tfelcu_factor* fact
   for (int t = 0; t < n_terms; ++t) if (terms[t].n_factors != 0 || terms[t].test_d != 0) return false;
   FormBuild fbv;
   tfelcu_fes* te = v->space.fes[0];
-  build_form(ctx, te->mesh, quad, factors, n_factors, terms, n_terms, 0, te->fe, -1, 0, fbv);
+  const std::vector<unsigned char> key = form_key(quad, terms, n_terms);
+  if (v->memo_form && v->memo_key == key) {
+    fbv.F = v->memo_form->F; fbv.tables = v->memo_form->tables; fbv.const_coef = v->memo_form->const_coef;
+  } else {
+    build_form(ctx, te->mesh, quad, factors, n_factors, terms, n_terms, 0, te->fe, -1, 0, fbv);
+    if (v->memo_form) form_build_free(v->memo_form);
+    v->memo_form = new FormBuild();
+    v->memo_form->F = fbv.F; v->memo_form->tables = fbv.tables; v->memo_form->const_coef = fbv.const_coef;
+    v->memo_key = key;
+  }
   if (fbv.F.n_terms == 0) return true;
   if (!fbv.const_coef) return false;
   std::unique_ptr<FormBuild> fb(m->pending);

@@ -18,6 +18,12 @@ struct P1Form {
   double mhat[3];       // sum_q w_q phi_i
   double Mhat[9];       // sum_q w_q phi_i phi_j
   double b_c[3];        // fused linear form: sum_t c_t mhat_i of ITS quadrature
+  // isotropic shape: C = c I (Laplacian-like) and, if there is a value x value term, a reference mass matrix with one
+  // diagonal and one off-diagonal value (any symmetric quadrature formula): K_ij = (c W / 4|K|) e_i . e_j + c00 |K| M_ij
+  // with e_i the edge opposite to vertex i -- no Jacobian inverse, nothing that depends on the local numbering
+  int iso;
+  double iso_k;         // 0.5 c W
+  double iso_md, iso_mo;   // c00 Mhat_ii, c00 Mhat_ij (i != j)
 };
 
 // fb: the bilinear form (constant coefficients, P1 x P1 on triangles); fbv: a constant-coefficient linear form without
@@ -33,6 +39,16 @@ inline P1Form make_p1_form(const FormBuild& fb, const FormBuild* fbv) {
   for (int e = 0; e < 9; ++e) F.Mhat[e] = ref[e];
   for (int i = 0; i < 3; ++i) F.mhat[i] = ref[((0 * 3 + 1) * 3 + i) * 3 + 1];   // mhat_i ghat_1[0], ghat_1 = (1, 0)
   F.wsum = ref[((1 * 3 + 1) * 3 + 1) * 3 + 1];                                 // ghat_1[0]^2 sum_q w_q
+  F.iso = 0; F.iso_k = 0.0; F.iso_md = 0.0; F.iso_mo = 0.0;
+  if (A.hasrr && !A.has0r && !A.hasr0 && A.C[0][0] == A.C[1][1] && A.C[0][1] == 0.0 && A.C[1][0] == 0.0) {
+    bool mass_ok = true;
+    if (A.has00) {
+      const double d = F.Mhat[0], o = F.Mhat[1];
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) mass_ok = mass_ok && F.Mhat[i * 3 + j] == (i == j ? d : o);
+      if (mass_ok) { F.iso_md = A.c00 * d; F.iso_mo = A.c00 * o; }
+    }
+    if (mass_ok) { F.iso = 1; F.iso_k = 0.5 * A.C[0][0] * F.wsum; }
+  }
   F.b_c[0] = F.b_c[1] = F.b_c[2] = 0.0;
   if (fbv) {
     const FormDev& G = fbv->F;   // sum_t c_t psi_i integrated on the reference cell: mhat[0][i] of its reference table

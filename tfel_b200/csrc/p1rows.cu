@@ -136,9 +136,11 @@ __device__ __forceinline__ void p1_row_from_corners(const P1Form& F, double2 p0,
   }
 }
 
-template <bool FUSE_B, bool STIFF, bool COMPACT>
+// SHAPE: 0 any constant-coefficient form, 1 gradient x gradient terms only, 2 isotropic (P1Form::iso; compact records)
+template <bool FUSE_B, int SHAPE, bool COMPACT>
 __global__ void __launch_bounds__(kEllRows)
 k_assemble_p1_ell(const __grid_constant__ P1Form F, const P1Rows B) {
+  constexpr bool STIFF = SHAPE == 1;
   extern __shared__ double stage[];
   const size_t r0 = B.row_begin + (size_t)blockIdx.x * kEllRows;
   size_t r1 = r0 + kEllRows; if (r1 > B.row_end) r1 = B.row_end;
@@ -157,16 +159,43 @@ k_assemble_p1_ell(const __grid_constant__ P1Form F, const P1Rows B) {
   double* row = stage + (rs - seg0);
   if (COMPACT) {
     const unsigned long long* rec = reinterpret_cast<const unsigned long long*>(B.ell) + (size_t)B.ell_ptr[blockIdx.x] * kEllRows + threadIdx.x;
-    unsigned long long q = D ? __ldg(rec) : 0ull;
-    const double2 pr = r < r1 ? __ldg(v2 + r) : make_double2(0.0, 0.0);   // the row's own vertex: once per row
+    // The record stream is the DRAM stream of this kernel: the first eight records of a row (all of them on every mesh
+    // seen so far) are requested up front, 64 bytes in flight per thread (with one record ahead the loop waited on the
+    // long scoreboard: 7.5 stall cycles per issue, 3.2 TB/s); the two corner gathers of cell k + 1 are in flight while
+    // cell k is computed.
+    const long long rc = (long long)(r < r1 ? r : r1 - 1);                   // rows past the end read a valid vertex
+    constexpr int kAhead = 8;
+    unsigned long long qa[kAhead];
+#pragma unroll
+    for (int k = 0; k < kAhead; ++k) qa[k] = (unsigned)k < D ? __ldg(rec + (size_t)k * kEllRows) : 0ull;
+    const double2 pr = __ldg(v2 + rc);                                       // the row's own vertex: once per row
+    auto off_a = [](unsigned long long c) { return ((long long)(c << 43)) >> 43; };   // sign-extended 21-bit fields
+    auto off_b = [](unsigned long long c) { return ((long long)(c << 22)) >> 43; };
+    double2 na = __ldg(v2 + rc + off_a(qa[0])), nb = __ldg(v2 + rc + off_b(qa[0]));
     __syncthreads();
-    for (unsigned k = 0; k < D; ++k) {
-      const unsigned long long cur = q;
-      if (k + 1 < D) q = __ldg(rec + (size_t)(k + 1) * kEllRows);   // next record in flight during the arithmetic
-      if (!(cur >> 63)) continue;
-      const long long da = ((long long)(cur << 43)) >> 43, db = ((long long)(cur << 22)) >> 43;   // sign-extended 21-bit fields
-      const double2 pa = __ldg(v2 + (long long)r + da), pb = __ldg(v2 + (long long)r + db);
+    auto step = [&](unsigned long long cur, unsigned long long nxt) {
+      const double2 pa = na, pb = nb;
+      na = __ldg(v2 + rc + off_a(nxt)); nb = __ldg(v2 + rc + off_b(nxt));   // padding records: offsets 0
+      if (!(cur >> 63)) return;
       const int i = (int)((cur >> 60) & 3u);
+      if (SHAPE == 2) {
+        // edges opposite to the row's vertex, to a and to b; K_ij = (c W / 4|K|) e_i . e_j + c00 |K| Mhat_ij
+        const double ox = pb.x - pa.x, oy = pb.y - pa.y, ax = pr.x - pb.x, ay = pr.y - pb.y, bx = pa.x - pr.x, by = pa.y - pr.y;
+        const double adet = fabs(bx * ay - by * ax);
+        const double vol = 0.5 * adet;
+        if (FUSE_B) bsum += (i == 0 ? bc0 : (i == 1 ? bc1 : bc2)) * vol;
+        if (dir) return;
+        const double sk = F.iso_k * fast_rcp(adet);
+        double k_own = sk * (ox * ox + oy * oy), k_a = sk * (ox * ax + oy * ay), k_b = sk * (ox * bx + oy * by);
+        if (F.has00) { k_own += F.iso_md * vol; k_a += F.iso_mo * vol; k_b += F.iso_mo * vol; }
+        // slots are stored in local order j = 0, 1, 2: own = i, a = the smaller of the other two, b = the larger
+        const unsigned sl = (unsigned)(cur >> 42) & 0x3ffffu;
+        const int s_own = 6 * i, s_a = i == 0 ? 6 : 0, s_b = i == 2 ? 6 : 12;
+        row[(sl >> s_own) & 0x3fu] += k_own;
+        row[(sl >> s_a) & 0x3fu] += k_a;
+        row[(sl >> s_b) & 0x3fu] += k_b;
+        return;
+      }
       // corners in local order: i = 0: (r, a, b), 1: (a, r, b), 2: (a, b, r)
       const double2 p0 = i == 0 ? pr : pa, p1 = i == 0 ? pa : (i == 1 ? pr : pb), p2 = i == 2 ? pr : pb;
       double vol, K[3];
@@ -175,14 +204,24 @@ k_assemble_p1_ell(const __grid_constant__ P1Form F, const P1Rows B) {
           const double det = (p1.x - p0.x) * (p2.y - p0.y) - (p1.y - p0.y) * (p2.x - p0.x);
           bsum += (i == 0 ? bc0 : (i == 1 ? bc1 : bc2)) * (0.5 * fabs(det));
         }
-        continue;
+        return;
       }
       p1_row_from_corners<STIFF>(F, p0, p1, p2, i, vol, K);
       if (FUSE_B) bsum += (i == 0 ? bc0 : (i == 1 ? bc1 : bc2)) * vol;
       row[(cur >> 42) & 0x3fu] += K[0];
       row[(cur >> 48) & 0x3fu] += K[1];
       row[(cur >> 54) & 0x3fu] += K[2];
+    };
+#pragma unroll
+    for (int k = 0; k < kAhead; ++k) {
+      if ((unsigned)k < D) {
+        const unsigned long long nxt = k + 1 < kAhead ? qa[k + 1 < kAhead ? k + 1 : 0]
+                                                      : ((unsigned)(k + 1) < D ? __ldg(rec + (size_t)(k + 1) * kEllRows) : 0ull);
+        step(qa[k], nxt);
+      }
     }
+    for (unsigned k = kAhead; k < D; ++k)
+      step(__ldg(rec + (size_t)k * kEllRows), k + 1 < D ? __ldg(rec + (size_t)(k + 1) * kEllRows) : 0ull);
   } else {
     const uint4* rec = reinterpret_cast<const uint4*>(B.ell) + (size_t)B.ell_ptr[blockIdx.x] * kEllRows + threadIdx.x;
     uint4 q = D ? __ldg(rec) : make_uint4(0u, 0u, 0u, 0xffffffffu);
@@ -304,17 +343,21 @@ bool assemble_p1_rows(tfelcu_matrix* m, const FormBuild& fb, tfelcu_vector* v, c
     if (v) v->zero_pending = false;
     const unsigned grid = grid_for(re - rb, kEllRows);
     const bool stiff = F.hasrr && !F.has00 && !F.has0r && !F.hasr0;
-#define TFELCU_P1(FB, ST, CP)                                                              \
+    const int shape = (F.iso && m->ell_compact && !std::getenv("TFELCU_NO_ISO")) ? 2 : (stiff ? 1 : 0);
+#define TFELCU_P1(FB, SH, CP)                                                              \
     do {                                                                                     \
-      ensure_smem(k_assemble_p1_ell<FB, ST, CP>, stage_bytes);                               \
-      k_assemble_p1_ell<FB, ST, CP><<<grid, kEllRows, stage_bytes, ctx->stream>>>(F, B);     \
+      ensure_smem(k_assemble_p1_ell<FB, SH, CP>, stage_bytes);                               \
+      k_assemble_p1_ell<FB, SH, CP><<<grid, kEllRows, stage_bytes, ctx->stream>>>(F, B);     \
     } while (0)
-    const int sel = (v ? 4 : 0) | (stiff ? 2 : 0) | (m->ell_compact ? 1 : 0);
+    const int sel = (v ? 8 : 0) | (shape << 1) | (m->ell_compact ? 1 : 0);
     switch (sel) {
-      case 0: TFELCU_P1(false, false, false); break; case 1: TFELCU_P1(false, false, true); break;
-      case 2: TFELCU_P1(false, true, false); break;  case 3: TFELCU_P1(false, true, true); break;
-      case 4: TFELCU_P1(true, false, false); break;  case 5: TFELCU_P1(true, false, true); break;
-      case 6: TFELCU_P1(true, true, false); break;   default: TFELCU_P1(true, true, true); break;
+      case 0: TFELCU_P1(false, 0, false); break; case 1: TFELCU_P1(false, 0, true); break;
+      case 2: TFELCU_P1(false, 1, false); break; case 3: TFELCU_P1(false, 1, true); break;
+      case 5: TFELCU_P1(false, 2, true); break;
+      case 8: TFELCU_P1(true, 0, false); break;  case 9: TFELCU_P1(true, 0, true); break;
+      case 10: TFELCU_P1(true, 1, false); break; case 11: TFELCU_P1(true, 1, true); break;
+      case 13: TFELCU_P1(true, 2, true); break;
+      default: fail("p1 rows: unexpected kernel selection");
     }
 #undef TFELCU_P1
     ctx->count(); TFELCU_LAUNCH_CHECK();

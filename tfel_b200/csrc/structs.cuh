@@ -157,6 +157,9 @@ struct tfelcu_vector {
   tfelcu::DevBuf<double> data;
   int scatter = TFELCU_SCATTER_AUTO;
   bool patch_refused = false;
+  tfelcu::FormBuild* memo_form = nullptr;   // like tfelcu_matrix::memo_form, for the linear form that rides along
+  std::vector<unsigned char> memo_key;
+  ~tfelcu_vector() { if (memo_form) tfelcu::form_build_free(memo_form); }
   bool zero_pending = false;            // clear() is pending: the next writer starts from zero, every other user zeroes first
   void ensure_cleared() {
     if (!zero_pending) return;
@@ -205,12 +208,18 @@ struct tfelcu_matrix {
   // a += (constant-coefficient form) that has been accepted but not launched yet: a linear form on the same space that
   // follows rides along in the same pass over the mesh (tile.cu); every other use of the matrix launches it first
   tfelcu::FormBuild* pending = nullptr;
+  tfelcu::FormBuild* memo_form = nullptr;   // the last constant-coefficient form lowered for this matrix and its key
+  std::vector<unsigned char> memo_key;      // (time / Newton loops repeat the same += : nothing is tabulated again)
   int pending_mode = 0;                 // 0: P1 rows (p1rows.cu), 1: tiles (tile.cu)
   // P1 x P1 triangle forms with constant coefficients (p1rows.cu): the packed records in a blocked ELL layout
   bool has_ell = false, ell_compact = false;   // compact: 8-byte records (vertex offsets from the row's own vertex)
   tfelcu::DevBuf<uint32_t> ell;         // uint4 records [ell_ptr[block] + k][128 rows of the block]
   tfelcu::DevBuf<unsigned int> ell_ptr, ell_deg;
-  ~tfelcu_matrix() { if (tile_plan) tfelcu::tile_plan_free(tile_plan); if (pending) tfelcu::form_build_free(pending); }
+  ~tfelcu_matrix() {
+    if (tile_plan) tfelcu::tile_plan_free(tile_plan);
+    if (pending) tfelcu::form_build_free(pending);
+    if (memo_form) tfelcu::form_build_free(memo_form);
+  }
   // cell colouring (TFELCU_SCATTER_COLORED): cells sorted by colour
   bool has_colors = false;
   int n_colors = 0;
