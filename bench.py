@@ -362,6 +362,7 @@ def parity_block(sess, dist, torch):
     r = rhs - A @ x
     acc = torch.tensor([float(val.sum()), float((val * val).sum()), float(r @ r), float(rhs @ rhs)], dtype=torch.float64, device=dev)
     dist.all_reduce(acc)
+    acc = acc.cpu().numpy()
     hs = torch.from_numpy(np.array([h_rp, h_ci], dtype=np.uint64).view(np.int64)).to(dev)
     dist.all_reduce(hs)      # int64 addition wraps: sums mod 2^64
     h_rp, h_ci = [int(v) for v in hs.cpu().numpy().view(np.uint64)]
@@ -571,7 +572,12 @@ def run_own(args):
              "parallelism": ("%d horizontal strips of rows (reference numbering); halo exchange + reductions over %s"
                              % (world, "peer-mapped memory (CUDA IPC, NVLink)" if ctx.p2p else "NCCL send/recv + allreduce"))
              if world > 1 else "single GPU"}
-    parity = parity_block(sess, dist, torch) if world > 1 else None
+    parity = None
+    if world > 1:
+        try:
+            parity = parity_block(sess, dist, torch)
+        except Exception as ex:   # noqa: BLE001 -- reported, never fatal for the line
+            parity = {"error": repr(ex), "ok": False}
     sess.close()
 
     # ---- e2e: host mesh arrays -> solution on the host, through the C ABI, everything timed -----------

@@ -9,7 +9,7 @@
 //                        ncclAllReduce), so that every rank takes the same branch of the stopping test
 //   dist_gather          owned entries -> full vector in reference numbering on every process
 // The reference has no distributed mode at all (sequential MATSEQAIJ, solver.hpp:139-143).
-#include "solver.cuh"
+#include "p2p.cuh"
 #include "sortutil.cuh"
 
 #include <algorithm>
@@ -37,7 +37,7 @@ __global__ void k_halo_keys(const int32_t* __restrict__ colind, size_t nnz, Rang
 }
 
 __global__ void k_localize_columns(const int32_t* __restrict__ colind, size_t nnz, RowMap R, const uint64_t* __restrict__ keys,
-                                   const uint64_t* __restrict__ halo, size_t n_halo, int32_t* __restrict__ out) {
+                                   const uint64_t* __restrict__ halo, size_t n_halo, size_t halo_base, int32_t* __restrict__ out) {
   const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (e >= nnz) return;
   const uint64_t key = keys[e];
@@ -47,7 +47,7 @@ __global__ void k_localize_columns(const int32_t* __restrict__ colind, size_t nn
     const size_t mid = lo + (hi - lo) / 2;
     if (halo[mid] < key) lo = mid + 1; else hi = mid;
   }
-  out[e] = (int32_t)(R.local_off[R.n] + lo);
+  out[e] = (int32_t)(halo_base + lo);
 }
 
 __global__ void k_lower_bounds_u64(const uint64_t* __restrict__ sorted, size_t n, int n_targets, unsigned long long* __restrict__ out) {
@@ -77,8 +77,6 @@ __global__ void k_pack(const double* __restrict__ v, const uint32_t* __restrict_
   if (i < n) out[i] = v[idx[i]];
 }
 
-// block b: fixed-order sum of partial array b (one warp)
-struct ReduceArgs { const double* p[4]; int n[4]; };
 __global__ void k_reduce_many(ReduceArgs A, double* __restrict__ out) {
   const double* p = A.p[blockIdx.x];
   const int n = A.n[blockIdx.x];
@@ -93,109 +91,60 @@ __global__ void k_reduce_many(ReduceArgs A, double* __restrict__ out) {
 // peer-to-peer arena: remote stores + sequence flags over NVLink (one process per GPU, CUDA IPC)
 // ------------------------------------------------------------------------------------------
 
-constexpr size_t kArenaHaloCap = (size_t)1 << 20;   // doubles per parity
-constexpr long long kSpinLimit = 20000000000ll;     // clock64 ticks (~10 s): a lost peer must not hang the GPU
-
-struct Arena {
-  unsigned long long red_flag[2][16];   // [parity][source rank]: sequence number of the last complete contribution
-  double red_val[2][16][4];
-  unsigned long long halo_flag[16];     // [source rank]
-  unsigned long long pad[16];
-  double halo[2][kArenaHaloCap];        // landing zone of halo values, [parity]
-};
-
-struct Peers { Arena* a[16]; };
-
-__device__ __forceinline__ bool spin_until(const volatile unsigned long long* flag, unsigned long long seq) {
-  const long long t0 = clock64();
-  while (*flag < seq) {
-    if (clock64() - t0 > kSpinLimit) return false;
-    __nanosleep(40);
-  }
-  return true;
-}
-
-// warp w: fixed-order local sum of partial array w, contribution written into every rank's arena, flag, wait for
-// everybody's contribution, sum in rank order (every rank adds the same numbers in the same order)
+// stand-alone allreduce of k partial arrays (warp w: array w); see p2p_allreduce
 __global__ void k_p2p_allreduce(ReduceArgs A, int k, Peers peers, int me, int P, unsigned long long* __restrict__ seq_dev,
                                 double* __restrict__ out, KrylovScalars* __restrict__ S, int epilogue) {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned long long seq = seq_dev[0] + 1;   // every thread reads the counter before thread 0 advances it
-  __syncthreads();
-  const int par = (int)(seq & 1ull);
-  {
-    const double* p = A.p[w];
-    const int n = A.n[w];
-    double t = 0.0;
-    for (int i = lane; i < n; i += 32) t += p[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane < P) {
-      *reinterpret_cast<volatile double*>(&peers.a[lane]->red_val[par][me][w]) = t;
-      __threadfence_system();
-    }
-  }
-  __syncthreads();
-  if (w == 0 && lane < P) {
-    __threadfence_system();
-    *reinterpret_cast<volatile unsigned long long*>(&peers.a[lane]->red_flag[par][me]) = seq;
-  }
-  Arena* mine = peers.a[me];
-  double v = 0.0;
-  bool ok = true;
-  if (lane < P) {
-    ok = spin_until(&mine->red_flag[par][lane], seq);
-    __threadfence_system();
-    v = *reinterpret_cast<volatile double*>(&mine->red_val[par][lane][w]);
-  }
-  double t = 0.0;
-  for (int q = 0; q < P; ++q) t += __shfl_sync(0xffffffffu, v, q);
-  if (lane == 0) out[w] = t;
-  if (!__all_sync(0xffffffffu, ok) && lane == 0 && S) S->done = -3;
-  if (threadIdx.x == 0) seq_dev[0] = seq;
-  if (epilogue == 1) {   // single-reduction CG: (gamma, rr, delta) -> alpha, beta, stopping test, in the same launch
-    __syncthreads();
-    if (threadIdx.x == 0) cgs_scalar_step(S, out[0], out[1], k == 4 ? out[2] + out[3] : out[2]);
-  }
+  p2p_allreduce(A, k, peers, me, P, seq_dev, out, S, epilogue, (int)threadIdx.x, [] { __syncthreads(); });
 }
-
-struct HaloArgs {
-  unsigned long long send_off[17], recv_off[17], land_off[16];
-};
 
 // CTA q: my boundary values -> landing zone of rank q (+ flag); values of rank q -> halo entries of v
 __global__ void __launch_bounds__(256)
-k_p2p_halo(double* __restrict__ v, size_t n_local, const uint32_t* __restrict__ send_idx, HaloArgs H, Peers peers,
-           int me, unsigned long long* __restrict__ seq_dev, KrylovScalars* __restrict__ S) {
+k_p2p_halo(double* __restrict__ v, size_t halo_base, const uint32_t* __restrict__ send_idx, HaloArgs H, Peers peers,
+           int me, unsigned long long* __restrict__ seq_dev, KrylovScalars* __restrict__ S, int do_send, int do_recv) {
   if (S && S->done) return;
   const int q = blockIdx.x;
   if (q == me) return;
-  const unsigned long long seq = seq_dev[1 + q] + 1;
+  const unsigned long long seq_s = seq_dev[kSeqSend + q] + 1, seq_r = seq_dev[kSeqRecv + q] + 1;
   __syncthreads();
-  if (threadIdx.x == 0) seq_dev[1 + q] = seq;
-  const int par = (int)(seq & 1ull);
   const size_t sc = H.send_off[q + 1] - H.send_off[q], rc = H.recv_off[q + 1] - H.recv_off[q];
-  if (sc) {
+  if (sc && do_send) {
+    const int par = (int)(seq_s & 1ull);
     double* dst = peers.a[q]->halo[par] + H.land_off[q];
     const uint32_t* idx = send_idx + H.send_off[q];
-    for (size_t i = threadIdx.x; i < sc; i += blockDim.x) dst[i] = v[idx[i]];
+    for (size_t i0 = threadIdx.x; i0 < sc; i0 += (size_t)8 * blockDim.x) {   // see p2p_halo_send
+      uint32_t ix[8]; double val[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const size_t i = i0 + (size_t)u * blockDim.x; ix[u] = i < sc ? __ldg(idx + i) : 0u; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const size_t i = i0 + (size_t)u * blockDim.x; val[u] = i < sc ? v[ix[u]] : 0.0; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const size_t i = i0 + (size_t)u * blockDim.x; if (i < sc) dst[i] = val[u]; }
+    }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence_system();
-      *reinterpret_cast<volatile unsigned long long*>(&peers.a[q]->halo_flag[me]) = seq;
+      *reinterpret_cast<volatile unsigned long long*>(&peers.a[q]->halo_flag[me]) = seq_s;
+      seq_dev[kSeqSend + q] = seq_s;
     }
   }
-  if (rc) {
+  if (rc && do_recv) {
+    const int par = (int)(seq_r & 1ull);
     __shared__ int ok_s;
     Arena* mine = peers.a[me];
-    if (threadIdx.x == 0) ok_s = spin_until(&mine->halo_flag[q], seq) ? 1 : 0;
+    if (threadIdx.x == 0) { ok_s = spin_until(&mine->halo_flag[q], seq_r) ? 1 : 0; seq_dev[kSeqRecv + q] = seq_r; }
     __syncthreads();
     __threadfence_system();
     if (!ok_s) { if (threadIdx.x == 0 && S) S->done = -3; return; }
-    const volatile double* src = mine->halo[par] + H.recv_off[q];
-    double* dst = v + n_local + H.recv_off[q];
-    for (size_t i = threadIdx.x; i < rc; i += blockDim.x) dst[i] = src[i];
+    const double* src = mine->halo[par] + H.recv_off[q];
+    double* dst = v + halo_base + H.recv_off[q];
+    for (size_t i0 = threadIdx.x; i0 < rc; i0 += (size_t)8 * blockDim.x) {
+      double val[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const size_t i = i0 + (size_t)u * blockDim.x; val[u] = i < rc ? __ldcg(src + i) : 0.0; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const size_t i = i0 + (size_t)u * blockDim.x; if (i < rc) dst[i] = val[u]; }
+    }
   }
 }
 
@@ -216,10 +165,10 @@ void p2p_setup(Ctx* ctx) {
   cudaIpcMemHandle_t mine_h;
   std::memset(&mine_h, 0, sizeof(mine_h));
   if (cudaMalloc(&ctx->arena, sizeof(Arena)) != cudaSuccess) { ok = 0; ctx->arena = nullptr; cudaGetLastError(); }
-  if (ok && cudaMalloc(&ctx->seq_dev, 32 * sizeof(unsigned long long)) != cudaSuccess) { ok = 0; ctx->seq_dev = nullptr; cudaGetLastError(); }
+  if (ok && cudaMalloc(&ctx->seq_dev, 64 * sizeof(unsigned long long)) != cudaSuccess) { ok = 0; ctx->seq_dev = nullptr; cudaGetLastError(); }
   if (ok) {
     TFELCU_CK(cudaMemsetAsync(ctx->arena, 0, sizeof(Arena), ctx->stream));
-    TFELCU_CK(cudaMemsetAsync(ctx->seq_dev, 0, 32 * sizeof(unsigned long long), ctx->stream));
+    TFELCU_CK(cudaMemsetAsync(ctx->seq_dev, 0, 64 * sizeof(unsigned long long), ctx->stream));
     ctx->sync();
     if (cudaIpcGetMemHandle(&mine_h, ctx->arena) != cudaSuccess) { ok = 0; cudaGetLastError(); }
   }
@@ -337,11 +286,15 @@ void dist_setup(tfelcu_solver* s) {
     uint64_t last = 0; ctx->download(&last, halo.p + (n_halo - 1), 1);
     if (last == ~0ull) --n_halo;
   }
-  D.n_halo = n_halo;
-  TFELCU_REQUIRE(n_local + n_halo < 0x7fffffffull, "too many local columns");
+  // the halo entries of a vector start on a 128-byte line of their own: the product reads them through the read-only
+  // path after another CTA of the same launch has written them, which is only safe for lines no earlier read of the launch
+  // (of owned entries) can have brought into an L1
+  D.halo_base = (n_local + 15) & ~(size_t)15;
+  D.n_halo = (D.halo_base - n_local) + n_halo;      // what a vector holds behind its owned entries: padding + halo
+  TFELCU_REQUIRE(D.halo_base + n_halo < 0x7fffffffull, "too many local columns");
   D.colind_local.alloc(nnz);
   if (nnz) {
-    k_localize_columns<<<grid_for(nnz, 256), 256, 0, ctx->stream>>>(s->colind, nnz, R, keys.p, halo.p, n_halo, D.colind_local.p);
+    k_localize_columns<<<grid_for(nnz, 256), 256, 0, ctx->stream>>>(s->colind, nnz, R, keys.p, halo.p, n_halo, D.halo_base, D.colind_local.p);
     ctx->count(); TFELCU_LAUNCH_CHECK();
   }
   DevBuf<unsigned long long> bounds((size_t)P + 1);
@@ -398,7 +351,9 @@ void dist_setup(tfelcu_solver* s) {
 }
 
 // owned entries of v (length n_local + n_halo) -> halo entries of the neighbours' copies
-void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S, cudaStream_t stream) {
+// mode: 3 send + receive (default), 1 send only, 2 receive only (the fused loop of solver.cu opens with a send and, when it
+// stops at maxits, closes with a receive; peer-to-peer arena only)
+void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S, cudaStream_t stream, int mode) {
   Ctx* ctx = s->ctx;
   DistPlan& D = *s->dist;
   const int P = ctx->n_ranks, me = ctx->rank;
@@ -408,24 +363,45 @@ void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S, cud
     HaloArgs H;
     for (int q = 0; q <= P; ++q) { H.send_off[q] = D.send_off[q]; H.recv_off[q] = D.recv_off[q]; }
     for (int q = 0; q < P; ++q) H.land_off[q] = D.land_off[q];
-    k_p2p_halo<<<P, 256, 0, stream>>>(v, D.rows.n_local(), D.send_idx.p, H, peers_of(ctx), me, ctx->seq_dev,
-                                     const_cast<KrylovScalars*>(S));
+    k_p2p_halo<<<P, 256, 0, stream>>>(v, D.halo_base, D.send_idx.p, H, peers_of(ctx), me, ctx->seq_dev,
+                                     const_cast<KrylovScalars*>(S), mode & 1, (mode >> 1) & 1);
     ctx->count(); TFELCU_LAUNCH_CHECK();
     return;
   }
+  TFELCU_REQUIRE(mode == 3, "one-sided halo steps need the peer-to-peer arena");
   if (n_send) {
     k_pack<<<grid_for(n_send, 256), 256, 0, stream>>>(v, D.send_idx.p, n_send, D.send_buf.p, S);
     ctx->count(); TFELCU_LAUNCH_CHECK();
   }
-  const size_t n_local = D.rows.n_local();
   TFELCU_NCCL(ncclGroupStart());
   for (int q = 0; q < P; ++q) {
     if (q == me) continue;
     const size_t rc = D.recv_off[q + 1] - D.recv_off[q], sc = D.send_off[q + 1] - D.send_off[q];
     if (sc) TFELCU_NCCL(ncclSend(D.send_buf.p + D.send_off[q], sc, ncclDouble, q, ctx->comm, stream));
-    if (rc) TFELCU_NCCL(ncclRecv(v + n_local + D.recv_off[q], rc, ncclDouble, q, ctx->comm, stream));
+    if (rc) TFELCU_NCCL(ncclRecv(v + D.halo_base + D.recv_off[q], rc, ncclDouble, q, ctx->comm, stream));
   }
   TFELCU_NCCL(ncclGroupEnd());
+}
+
+// what the fused loop of the distributed single-reduction CG hands to its two kernels (p2p.cuh: DistFuse)
+void dist_fuse_args(tfelcu_solver* s, DistFuse* out) {
+  Ctx* ctx = s->ctx;
+  DistPlan& D = *s->dist;
+  const int P = ctx->n_ranks;
+  DistFuse F;
+  std::memset(&F, 0, sizeof(F));
+  F.enabled = 1; F.me = ctx->rank; F.P = P;
+  F.peers = peers_of(ctx);
+  F.seq_dev = ctx->seq_dev;
+  if (!D.fuse_ctr.p) { D.fuse_ctr.alloc(8); ctx->zero(D.fuse_ctr.p, 8); }
+  F.ctr = D.fuse_ctr.p;
+  for (int q = 0; q <= P; ++q) { F.H.send_off[q] = D.send_off[q]; F.H.recv_off[q] = D.recv_off[q]; }
+  for (int q = 0; q < P; ++q) F.H.land_off[q] = D.land_off[q];
+  F.send_idx = D.send_idx.p;
+  F.halo_base = D.halo_base;
+  F.n_interior = s->plan.n_interior;
+  F.S = s->scal.p;
+  *out = F;
 }
 
 // out_slot .. out_slot + k - 1 of the reduction buffer <- global sums of k partial arrays; returns the device address

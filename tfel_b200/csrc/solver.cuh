@@ -46,6 +46,7 @@ struct SpmvPlan {
   DevBuf<int16_t> delta16;               // column - row of every stored entry, when all fit 16 bits
   bool use_delta16 = false;
   int tile_nnz = 0, tile_rows = 0;
+  struct DistFuse* fuse = nullptr;       // set around one launch by spmv_launch (fused distributed CG)
 };
 
 // consecutive levels [l0, l1) of a level schedule launched together: one CTA walking several small levels
@@ -88,7 +89,10 @@ struct Ilu0 {
 struct DistPlan {
   RowMap rows;                           // rows of this rank
   std::vector<RowMap> all_rows;          // rows of every rank
-  size_t n_halo = 0;                     // columns owned by other ranks, stored after the owned entries of a vector
+  size_t n_halo = 0;                     // what a vector holds behind its owned entries: padding up to halo_base, then one
+                                         // entry per column owned by another rank
+  size_t halo_base = 0;                  // index of the first halo entry (owned entries rounded up to a 128-byte line)
+  DevBuf<unsigned int> fuse_ctr;         // counters of the fused loop (p2p.cuh: DistFuse::ctr)
   DevBuf<int32_t> colind_local;          // column indices in [owned | halo] numbering
   DevBuf<uint32_t> send_idx;             // owned entries to send, grouped by destination rank
   DevBuf<double> send_buf;
@@ -141,7 +145,9 @@ void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep);
 void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep);
 void spmv_plan(tfelcu_solver* s);
 // y = A x; when dot_partial != nullptr also writes per-CTA partial sums of x . y and returns their number
-int spmv_launch(tfelcu_solver* s, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal);
+struct DistFuse;
+int spmv_launch(tfelcu_solver* s, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal,
+                DistFuse* fuse = nullptr);
 int spmv_partial_count(tfelcu_solver* s);
 int spmv_launch_part(tfelcu_solver* s, int part, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal);
 void spmv_split_boundary(tfelcu_solver* s, size_t n_local);
@@ -155,7 +161,8 @@ void block_jacobi_setup(tfelcu_solver* s);
 void block_jacobi_apply(tfelcu_solver* s, const double* d_in, double* d_out);
 // ---- dist.cu
 void dist_setup(tfelcu_solver* s);
-void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S, cudaStream_t stream = nullptr);
+void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S, cudaStream_t stream = nullptr, int mode = 3);
+void dist_fuse_args(tfelcu_solver* s, DistFuse* out);
 // epilogue == 1: the reducing kernel also performs the scalar step of the single-reduction CG (k_cgs_scalars)
 const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const int* n, int k, int out_slot, int epilogue = 0);
 void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep);

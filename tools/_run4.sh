@@ -1,11 +1,7 @@
 cd $GRAFT_REPO_ROOT
-nvidia-smi -L
-timeout 900 python -m pytest tests/test_dist.py -m gpu -v 2>&1 | tail -15 | tee gpurun_out/r2_dist_tests_n2.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29700 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r2_bench_n2_a.json 2> gpurun_out/r2_bench_n2_a.err
-tail -c 400 gpurun_out/r2_bench_n2_a.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r2_bench_n2_a.json').read().strip().splitlines()[-1])
-for k in ('value','ms_per_step','assembly','solve','parity','e2e'):
-    print(k, json.dumps(d.get(k))[:900])
-PY
+nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv
+for mode in 0 1; do
+TFELCU_TRACE=1 TFELCU_FUSED_DIST=$mode timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2970$mode bench.py --gpus 2 --steps 1 --warmup 3 --e2e-steps 0 > gpurun_out/r2_bench_n2_fused$mode.json 2> gpurun_out/r2_bench_n2_fused$mode.err &
+sleep 45; nvidia-smi --query-gpu=index,clocks.sm,power.draw --format=csv,noheader; wait
+grep "tfelcu trace\] rank" gpurun_out/r2_bench_n2_fused$mode.err | tail -2
+done
