@@ -100,6 +100,8 @@ struct Ctx {
   void* peer_arena[16] = {nullptr};
   cudaStream_t side_stream = nullptr;      // halo exchange overlapped with the interior SpMV
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int* p2p_err = nullptr;                  // device flag: a peer did not answer within the spin limit
+  bool p2p_failed = false;                 // ... seen by the host: distributed solves on this context are refused from then on
   unsigned long long* seq_dev = nullptr;   // [0]: reductions done, [1 + q]: halo exchanges done with rank q (device counters,
                                            // advanced by the kernels themselves so that the loop can live in a CUDA graph)
   DevBuf<double> table_scratch;   // reference-element tables of the form being assembled (stream ordered reuse)

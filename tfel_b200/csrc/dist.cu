@@ -93,14 +93,16 @@ __global__ void k_reduce_many(ReduceArgs A, double* __restrict__ out) {
 
 // stand-alone allreduce of k partial arrays (warp w: array w); see p2p_allreduce
 __global__ void k_p2p_allreduce(ReduceArgs A, int k, Peers peers, int me, int P, unsigned long long* __restrict__ seq_dev,
-                                double* __restrict__ out, KrylovScalars* __restrict__ S, int epilogue) {
-  p2p_allreduce(A, k, peers, me, P, seq_dev, out, S, epilogue, (int)threadIdx.x, [] { __syncthreads(); });
+                                double* __restrict__ out, KrylovScalars* __restrict__ S, int epilogue, int* __restrict__ err) {
+  p2p_allreduce(A, k, peers, me, P, seq_dev, out, S, epilogue, (int)threadIdx.x, [] { __syncthreads(); }, err);
 }
 
-// CTA q: my boundary values -> landing zone of rank q (+ flag); values of rank q -> halo entries of v
+// CTA q: my boundary values -> landing zone of rank q; values of rank q -> halo entries of v (words that carry their own
+// sequence number: p2p.cuh)
 __global__ void __launch_bounds__(256)
 k_p2p_halo(double* __restrict__ v, size_t halo_base, const uint32_t* __restrict__ send_idx, HaloArgs H, Peers peers,
-           int me, unsigned long long* __restrict__ seq_dev, KrylovScalars* __restrict__ S, int do_send, int do_recv) {
+           int me, unsigned long long* __restrict__ seq_dev, KrylovScalars* __restrict__ S, int do_send, int do_recv,
+           int* __restrict__ err) {
   if (S && S->done) return;
   const int q = blockIdx.x;
   if (q == me) return;
@@ -109,7 +111,7 @@ k_p2p_halo(double* __restrict__ v, size_t halo_base, const uint32_t* __restrict_
   const size_t sc = H.send_off[q + 1] - H.send_off[q], rc = H.recv_off[q + 1] - H.recv_off[q];
   if (sc && do_send) {
     const int par = (int)(seq_s & 1ull);
-    double* dst = peers.a[q]->halo[par] + H.land_off[q];
+    unsigned long long* dst = peers.a[q]->halo[par] + 2 * H.land_off[q];
     const uint32_t* idx = send_idx + H.send_off[q];
     for (size_t i0 = threadIdx.x; i0 < sc; i0 += (size_t)8 * blockDim.x) {   // see p2p_halo_send
       uint32_t ix[8]; double val[8];
@@ -118,33 +120,22 @@ k_p2p_halo(double* __restrict__ v, size_t halo_base, const uint32_t* __restrict_
 #pragma unroll
       for (int u = 0; u < 8; ++u) { const size_t i = i0 + (size_t)u * blockDim.x; val[u] = i < sc ? v[ix[u]] : 0.0; }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { const size_t i = i0 + (size_t)u * blockDim.x; if (i < sc) dst[i] = val[u]; }
+      for (int u = 0; u < 8; ++u) { const size_t i = i0 + (size_t)u * blockDim.x; if (i < sc) ll_store(dst + 2 * i, val[u], (unsigned int)seq_s); }
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence_system();
-      *reinterpret_cast<volatile unsigned long long*>(&peers.a[q]->halo_flag[me]) = seq_s;
-      seq_dev[kSeqSend + q] = seq_s;
-    }
+    if (threadIdx.x == 0) seq_dev[kSeqSend + q] = seq_s;
   }
   if (rc && do_recv) {
     const int par = (int)(seq_r & 1ull);
-    __shared__ int ok_s;
-    Arena* mine = peers.a[me];
-    if (threadIdx.x == 0) { ok_s = spin_until(&mine->halo_flag[q], seq_r) ? 1 : 0; seq_dev[kSeqRecv + q] = seq_r; }
-    __syncthreads();
-    __threadfence_system();
-    if (!ok_s) { if (threadIdx.x == 0 && S) S->done = -3; return; }
-    const double* src = mine->halo[par] + H.recv_off[q];
+    const unsigned long long* src = peers.a[me]->halo[par] + 2 * H.recv_off[q];
     double* dst = v + halo_base + H.recv_off[q];
+    bool ok = true;
     for (size_t i0 = threadIdx.x; i0 < rc; i0 += (size_t)8 * blockDim.x) {
-      double val[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { const size_t i = i0 + (size_t)u * blockDim.x; val[u] = i < rc ? __ldcg(src + i) : 0.0; }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { const size_t i = i0 + (size_t)u * blockDim.x; if (i < rc) dst[i] = val[u]; }
+      const size_t left = (rc - i0 + blockDim.x - 1) / blockDim.x;
+      ok = ll_load_batch(src + 2 * i0, (size_t)blockDim.x, left < 8 ? (int)left : 8, (unsigned int)seq_r,
+                         [&](int u, double val) { dst[i0 + (size_t)u * blockDim.x] = val; }) && ok;
     }
+    if (!ok) { atomicExch(err, 1); if (S) S->done = -3; }   // the counters advance all the same: the ranks stay in step
+    if (threadIdx.x == 0) seq_dev[kSeqRecv + q] = seq_r;
   }
 }
 
@@ -153,7 +144,8 @@ void p2p_teardown(Ctx* ctx) {
     if (ctx->peer_arena[q] && q != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_arena[q]);
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->seq_dev) cudaFree(ctx->seq_dev);
-  ctx->arena = nullptr; ctx->seq_dev = nullptr; ctx->p2p = false;
+  if (ctx->p2p_err) cudaFree(ctx->p2p_err);
+  ctx->arena = nullptr; ctx->seq_dev = nullptr; ctx->p2p_err = nullptr; ctx->p2p = false;
   for (int q = 0; q < 16; ++q) ctx->peer_arena[q] = nullptr;
   cudaGetLastError();
 }
@@ -166,7 +158,9 @@ void p2p_setup(Ctx* ctx) {
   std::memset(&mine_h, 0, sizeof(mine_h));
   if (cudaMalloc(&ctx->arena, sizeof(Arena)) != cudaSuccess) { ok = 0; ctx->arena = nullptr; cudaGetLastError(); }
   if (ok && cudaMalloc(&ctx->seq_dev, 64 * sizeof(unsigned long long)) != cudaSuccess) { ok = 0; ctx->seq_dev = nullptr; cudaGetLastError(); }
+  if (ok && cudaMalloc(&ctx->p2p_err, sizeof(int)) != cudaSuccess) { ok = 0; ctx->p2p_err = nullptr; cudaGetLastError(); }
   if (ok) {
+    TFELCU_CK(cudaMemsetAsync(ctx->p2p_err, 0, sizeof(int), ctx->stream));
     TFELCU_CK(cudaMemsetAsync(ctx->arena, 0, sizeof(Arena), ctx->stream));
     TFELCU_CK(cudaMemsetAsync(ctx->seq_dev, 0, 64 * sizeof(unsigned long long), ctx->stream));
     ctx->sync();
@@ -213,10 +207,10 @@ double p2p_bench_allreduce(Ctx* ctx, int reps) {
   cudaEvent_t e0, e1;
   TFELCU_CK(cudaEventCreate(&e0)); TFELCU_CK(cudaEventCreate(&e1));
   for (int r = 0; r < 10; ++r)
-    k_p2p_allreduce<<<1, 64, 0, ctx->stream>>>(A, 2, peers_of(ctx), ctx->rank, ctx->n_ranks, ctx->seq_dev, out.p, nullptr, 0);
+    k_p2p_allreduce<<<1, 64, 0, ctx->stream>>>(A, 2, peers_of(ctx), ctx->rank, ctx->n_ranks, ctx->seq_dev, out.p, nullptr, 0, ctx->p2p_err);
   TFELCU_CK(cudaEventRecord(e0, ctx->stream));
   for (int r = 0; r < reps; ++r)
-    k_p2p_allreduce<<<1, 64, 0, ctx->stream>>>(A, 2, peers_of(ctx), ctx->rank, ctx->n_ranks, ctx->seq_dev, out.p, nullptr, 0);
+    k_p2p_allreduce<<<1, 64, 0, ctx->stream>>>(A, 2, peers_of(ctx), ctx->rank, ctx->n_ranks, ctx->seq_dev, out.p, nullptr, 0, ctx->p2p_err);
   TFELCU_CK(cudaEventRecord(e1, ctx->stream));
   TFELCU_CK(cudaEventSynchronize(e1));
   float ms = 0.f; TFELCU_CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -324,6 +318,18 @@ void dist_setup(tfelcu_solver* s) {
     }
     D.land_off[q] = off;
     if (total > kArenaHaloCap) D.p2p_halo = false;
+    // a parity buffer is reused every second exchange; what makes that safe is that every send to a rank is paired with
+    // a receive from it (the sender cannot run two exchanges ahead). One-directional couplings take the NCCL path.
+    const bool sends = h_cnt_all[(size_t)q * P + me] != 0, receives = h_cnt[q] != 0;
+    if (q != me && sends != receives) D.p2p_halo = false;
+  }
+  {   // every rank must take the same path
+    DevBuf<int> f(1);
+    int flag = D.p2p_halo ? 1 : 0;
+    ctx->upload(f.p, &flag, 1);
+    TFELCU_NCCL(ncclAllReduce(f.p, f.p, 1, ncclInt, ncclMin, ctx->comm, ctx->stream));
+    ctx->download(&flag, f.p, 1);
+    D.p2p_halo = flag != 0;
   }
   const size_t n_send = D.send_off[P];
   // 4. tell the owners which of their rows we need
@@ -364,7 +370,7 @@ void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S, cud
     for (int q = 0; q <= P; ++q) { H.send_off[q] = D.send_off[q]; H.recv_off[q] = D.recv_off[q]; }
     for (int q = 0; q < P; ++q) H.land_off[q] = D.land_off[q];
     k_p2p_halo<<<P, 256, 0, stream>>>(v, D.halo_base, D.send_idx.p, H, peers_of(ctx), me, ctx->seq_dev,
-                                     const_cast<KrylovScalars*>(S), mode & 1, (mode >> 1) & 1);
+                                     const_cast<KrylovScalars*>(S), mode & 1, (mode >> 1) & 1, ctx->p2p_err);
     ctx->count(); TFELCU_LAUNCH_CHECK();
     return;
   }
@@ -383,27 +389,6 @@ void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S, cud
   TFELCU_NCCL(ncclGroupEnd());
 }
 
-// what the fused loop of the distributed single-reduction CG hands to its two kernels (p2p.cuh: DistFuse)
-void dist_fuse_args(tfelcu_solver* s, DistFuse* out) {
-  Ctx* ctx = s->ctx;
-  DistPlan& D = *s->dist;
-  const int P = ctx->n_ranks;
-  DistFuse F;
-  std::memset(&F, 0, sizeof(F));
-  F.enabled = 1; F.me = ctx->rank; F.P = P;
-  F.peers = peers_of(ctx);
-  F.seq_dev = ctx->seq_dev;
-  if (!D.fuse_ctr.p) { D.fuse_ctr.alloc(8); ctx->zero(D.fuse_ctr.p, 8); }
-  F.ctr = D.fuse_ctr.p;
-  for (int q = 0; q <= P; ++q) { F.H.send_off[q] = D.send_off[q]; F.H.recv_off[q] = D.recv_off[q]; }
-  for (int q = 0; q < P; ++q) F.H.land_off[q] = D.land_off[q];
-  F.send_idx = D.send_idx.p;
-  F.halo_base = D.halo_base;
-  F.n_interior = s->plan.n_interior;
-  F.S = s->scal.p;
-  *out = F;
-}
-
 // out_slot .. out_slot + k - 1 of the reduction buffer <- global sums of k partial arrays; returns the device address
 __global__ void k_cgs_scalars_from(const double* __restrict__ v, int k, KrylovScalars* __restrict__ S) {
   if (threadIdx.x == 0 && blockIdx.x == 0) cgs_scalar_step(S, v[0], v[1], k == 4 ? v[2] + v[3] : v[2]);
@@ -417,7 +402,7 @@ const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const 
   double* out = D.red.p + out_slot;
   if (ctx->p2p) {
     k_p2p_allreduce<<<1, 32 * k, 0, ctx->stream>>>(A, k, peers_of(ctx), ctx->rank, ctx->n_ranks, ctx->seq_dev, out,
-                                                  s->scal.p, epilogue);
+                                                  s->scal.p, epilogue, ctx->p2p_err);
     ctx->count(); TFELCU_LAUNCH_CHECK();
     return out;
   }
@@ -429,6 +414,16 @@ const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const 
     ctx->count(); TFELCU_LAUNCH_CHECK();
   }
   return out;
+}
+
+// after a distributed solve: did a peer fail to answer? (the Krylov kernels stop at once when it happens: done = -3)
+bool dist_peer_failed(tfelcu_solver* s) {
+  Ctx* ctx = s->ctx;
+  if (!ctx->p2p_err) return false;
+  int h = 0;
+  ctx->download(&h, ctx->p2p_err, 1);
+  if (h) { ctx->p2p_failed = true; ctx->zero(ctx->p2p_err, 1); }
+  return h != 0;
 }
 
 // x_global (device, n_rows of the global system) <- owned entries of every rank, reference numbering

@@ -1,6 +1,9 @@
-// Peer-to-peer arena of the distributed Krylov loop (one process per GPU, CUDA IPC over NVLink): device-side pieces
-// shared by dist.cu (stand-alone halo / allreduce kernels), spmv.cu (halo receive before the boundary slabs, allreduce in
-// the tail of the product) and solver.cu (halo send in the tail of the fused vector update).
+// Peer-to-peer arena of the distributed Krylov loop (one process per GPU, CUDA IPC over NVLink): device-side pieces of
+// the halo exchange and allreduce kernels of dist.cu.
+// (Tried and removed: folding the halo receive and the allreduce into the product kernel and the halo send into the vector
+// update -- two launches per iteration instead of four. At 8 GPUs it was slower, 137 vs 112 us per iteration: the exposed
+// time is the latency of the peer-to-peer steps themselves, which the fused kernels serialise behind their last CTA, not
+// the launches. What did help is in this file: words that carry their own sequence number instead of value / fence / flag.)
 #pragma once
 
 #include "solver.cuh"
@@ -10,13 +13,66 @@ namespace tfelcu {
 constexpr size_t kArenaHaloCap = (size_t)1 << 20;   // doubles per parity
 constexpr long long kSpinLimit = 20000000000ll;     // clock64 ticks (~10 s): a lost peer must not hang the GPU
 
+// Every remote value travels as two 8-byte words (32 data bits | 32-bit sequence number): an aligned 8-byte store is
+// atomic, so a word whose sequence number matches carries valid data and no separate flag, no system-scope fence and no
+// second NVLink round trip are needed (the "LL" protocol of NCCL). Measured at 8 GPUs with value / fence / flag / fence:
+// 22 us per halo exchange and 25 us per reduction, most of it fence round trips.
 struct Arena {
-  unsigned long long red_flag[2][16];   // [parity][source rank]: sequence number of the last complete contribution
-  double red_val[2][16][4];
-  unsigned long long halo_flag[16];     // [source rank]
-  unsigned long long pad[16];
-  double halo[2][kArenaHaloCap];        // landing zone of halo values, [parity]
+  unsigned long long red[2][16][4][2];        // [parity][source rank][value][half]
+  unsigned long long halo[2][2 * kArenaHaloCap];   // landing zone of halo values, [parity][2 words per value]
 };
+
+__device__ __forceinline__ void ll_store(unsigned long long* dst, double v, unsigned int seq) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long lo = (b & 0xffffffffull) | ((unsigned long long)seq << 32);
+  const unsigned long long hi = (b >> 32) | ((unsigned long long)seq << 32);
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(lo), "l"(hi) : "memory");
+}
+
+// n (<= 8) values at src[2 * stride * u], u = 0 .. n - 1: all loads are issued before the first check (one exposed latency
+// per batch instead of one per value); words that are not there yet are re-read one by one
+template <typename Store>
+__device__ __forceinline__ bool ll_load_batch(const unsigned long long* src, size_t stride, int n, unsigned int seq, Store store) {
+  unsigned long long lo[8], hi[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    if (u < n) asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo[u]), "=l"(hi[u]) : "l"(src + 2 * stride * u) : "memory");
+  bool ok = true;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    if (u >= n) continue;
+    if ((unsigned int)(lo[u] >> 32) == seq && (unsigned int)(hi[u] >> 32) == seq) {
+      store(u, __longlong_as_double((long long)((lo[u] & 0xffffffffull) | (hi[u] << 32))));
+    } else {
+      const long long t0 = clock64();
+      int spins = 0;
+      unsigned long long a, b;
+      bool got = true;
+      while (true) {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(src + 2 * stride * u) : "memory");
+        if ((unsigned int)(a >> 32) == seq && (unsigned int)(b >> 32) == seq) break;
+        if ((++spins & 255) == 0 && clock64() - t0 > kSpinLimit) { got = false; break; }
+      }
+      ok = ok && got;
+      store(u, got ? __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32))) : 0.0);
+    }
+  }
+  return ok;
+}
+
+// both halves with sequence number seq -> value; false when they did not arrive in time
+__device__ __forceinline__ bool ll_load(const unsigned long long* src, unsigned int seq, double* out) {
+  unsigned long long lo, hi;
+  const long long t0 = clock64();
+  int spins = 0;
+  while (true) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+    if ((unsigned int)(lo >> 32) == seq && (unsigned int)(hi >> 32) == seq) break;
+    if ((++spins & 255) == 0 && clock64() - t0 > kSpinLimit) return false;
+  }
+  *out = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+  return true;
+}
 
 struct Peers { Arena* a[16]; };
 
@@ -28,107 +84,17 @@ struct HaloArgs {
 };
 
 // device counters (Ctx::seq_dev, 64 entries): advanced by the kernels themselves so that the loop can live in a CUDA graph
-//   [0] reductions done | [1 + q] halo sends to rank q | [17 + q] halo receives from rank q | [40] fused products launched
-constexpr int kSeqSend = 1, kSeqRecv = 17, kSeqLaunch = 40;
-
-__device__ __forceinline__ bool spin_until(const volatile unsigned long long* flag, unsigned long long seq) {
-  const long long t0 = clock64();
-  while (*flag < seq) {
-    if (clock64() - t0 > kSpinLimit) return false;
-    __nanosleep(40);
-  }
-  return true;
-}
-
-// everything the distributed single-reduction CG folds into its two kernels per iteration
-struct DistFuse {
-  int enabled;
-  int me, P;
-  Peers peers;
-  unsigned long long* seq_dev;
-  unsigned int* ctr;            // [0] CTAs of the product that are done, [1] halo of this launch unpacked (launch sequence),
-                                // [2] CTAs of the vector update that are done
-  HaloArgs H;
-  const uint32_t* send_idx;
-  double* x_rw;                 // the input vector of the product (its halo entries are written by the product itself)
-  size_t halo_base;             // first halo entry of a vector
-  int n_interior;               // slabs [0, n_interior) reference owned columns only
-  ReduceArgs A; int k;          // tail of the product: global sums of k partial arrays ...
-  double* red_out;              // ... written here, then the scalar step of the CG
-  KrylovScalars* S;
-};
-
-// One CTA: my boundary values of v -> landing zones of the neighbours (+ flags). All threads of the CTA (nt of them,
-// synchronised by `sync`) take part.
-template <typename Sync>
-__device__ __forceinline__ void p2p_halo_send(const double* v, const DistFuse& F, int tid, int nt, Sync sync) {
-  for (int q = 0; q < F.P; ++q) {
-    if (q == F.me) continue;
-    const size_t sc = F.H.send_off[q + 1] - F.H.send_off[q];
-    if (!sc) continue;
-    const unsigned long long seq = F.seq_dev[kSeqSend + q] + 1;
-    const int par = (int)(seq & 1ull);
-    double* dst = F.peers.a[q]->halo[par] + F.H.land_off[q];
-    const uint32_t* idx = F.send_idx + F.H.send_off[q];
-    // eight independent (index, value) loads in flight per thread before the first remote store: one element per trip
-    // costs two dependent L2 latencies each (measured: 18 us for 4097 values with 256 threads)
-    for (size_t i0 = tid; i0 < sc; i0 += (size_t)8 * nt) {
-      uint32_t ix[8]; double val[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { const size_t i = i0 + (size_t)u * nt; ix[u] = i < sc ? __ldg(idx + i) : 0u; }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { const size_t i = i0 + (size_t)u * nt; val[u] = i < sc ? __ldcg(v + ix[u]) : 0.0; }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { const size_t i = i0 + (size_t)u * nt; if (i < sc) dst[i] = val[u]; }
-    }
-    __threadfence_system();
-    sync();
-    if (tid == 0) {
-      __threadfence_system();
-      *reinterpret_cast<volatile unsigned long long*>(&F.peers.a[q]->halo_flag[F.me]) = seq;
-      F.seq_dev[kSeqSend + q] = seq;
-    }
-    sync();
-  }
-}
-
-// One CTA: values of the neighbours -> halo entries of v. Returns false when a peer did not answer in time.
-template <typename Sync>
-__device__ __forceinline__ bool p2p_halo_recv(double* v, const DistFuse& F, int tid, int nt, Sync sync, int* ok_s) {
-  Arena* mine = F.peers.a[F.me];
-  bool all_ok = true;
-  for (int q = 0; q < F.P; ++q) {
-    if (q == F.me) continue;
-    const size_t rc = F.H.recv_off[q + 1] - F.H.recv_off[q];
-    if (!rc) continue;
-    const unsigned long long seq = F.seq_dev[kSeqRecv + q] + 1;
-    const int par = (int)(seq & 1ull);
-    sync();
-    if (tid == 0) { *ok_s = spin_until(&mine->halo_flag[q], seq) ? 1 : 0; F.seq_dev[kSeqRecv + q] = seq; }
-    sync();
-    __threadfence_system();
-    if (!*ok_s) { all_ok = false; continue; }
-    const double* src = mine->halo[par] + F.H.recv_off[q];
-    double* dst = v + F.halo_base + F.H.recv_off[q];
-    for (size_t i0 = tid; i0 < rc; i0 += (size_t)8 * nt) {   // eight loads in flight per thread (L2: written by the peer)
-      double val[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { const size_t i = i0 + (size_t)u * nt; val[u] = i < rc ? __ldcg(src + i) : 0.0; }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { const size_t i = i0 + (size_t)u * nt; if (i < rc) dst[i] = val[u]; }
-    }
-  }
-  return all_ok;
-}
+//   [0] reductions done | [1 + q] halo sends to rank q | [17 + q] halo receives from rank q
+constexpr int kSeqSend = 1, kSeqRecv = 17;
 
 // Warps 0 .. k-1 of one CTA (lane = thread in warp): fixed-order local sum of partial array w, contribution written into
-// every rank's arena, flag, wait for everybody's contribution, sum in rank order (every rank adds the same numbers in the
-// same order: bitwise identical results, so every rank takes the same branch of the stopping test). epilogue == 1: the
-// scalar step of the single-reduction CG from (gamma, rr, delta) in the same launch.
+// every rank's arena, every rank's contribution awaited, sum in rank order (every rank adds the same numbers in the same
+// order: bitwise identical results, so every rank takes the same branch of the stopping test). epilogue == 1: the scalar
+// step of the single-reduction CG from (gamma, rr, delta) in the same launch.
 template <typename Sync>
 __device__ __forceinline__ void p2p_allreduce(const ReduceArgs& A, int k, const Peers& peers, int me, int P,
                                               unsigned long long* seq_dev, double* out, KrylovScalars* S, int epilogue,
-                                              int tid, Sync sync) {
+                                              int tid, Sync sync, int* err) {
   const int w = tid >> 5, lane = tid & 31;
   const unsigned long long seq = seq_dev[0] + 1;   // every thread reads the counter before thread 0 advances it
   sync();
@@ -146,29 +112,15 @@ __device__ __forceinline__ void p2p_allreduce(const ReduceArgs& A, int k, const 
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane < P) {
-      *reinterpret_cast<volatile double*>(&peers.a[lane]->red_val[par][me][w]) = t;
-      __threadfence_system();
-    }
-  }
-  sync();
-  if (w == 0 && lane < P) {
-    __threadfence_system();
-    *reinterpret_cast<volatile unsigned long long*>(&peers.a[lane]->red_flag[par][me]) = seq;
-  }
-  if (w < k) {
+    if (lane < P) ll_store(&peers.a[lane]->red[par][me][w][0], t, (unsigned int)seq);
     Arena* mine = peers.a[me];
     double v = 0.0;
     bool ok = true;
-    if (lane < P) {
-      ok = spin_until(&mine->red_flag[par][lane], seq);
-      __threadfence_system();
-      v = *reinterpret_cast<volatile double*>(&mine->red_val[par][lane][w]);
-    }
-    double t = 0.0;
-    for (int q = 0; q < P; ++q) t += __shfl_sync(0xffffffffu, v, q);
-    if (lane == 0) out[w] = t;
-    if (!__all_sync(0xffffffffu, ok) && lane == 0 && S) S->done = -3;
+    if (lane < P) ok = ll_load(&mine->red[par][lane][w][0], (unsigned int)seq, &v);
+    double sum = 0.0;
+    for (int q = 0; q < P; ++q) sum += __shfl_sync(0xffffffffu, v, q);
+    if (lane == 0) out[w] = sum;
+    if (!__all_sync(0xffffffffu, ok) && lane == 0) { atomicExch(err, 1); if (S) S->done = -3; }
   }
   if (tid == 0) seq_dev[0] = seq;
   if (epilogue == 1) {   // single-reduction CG: (gamma, rr, delta) -> alpha, beta, stopping test

@@ -9,7 +9,7 @@
 //
 // Convergence: ||r||_2 <= max(rtol ||b||_2, atol); divergence: ||r||_2 > dtol ||b||_2 (the dictionary keys of
 // solver.hpp:125-133). All reductions are per-CTA partial sums combined in a fixed order: bitwise reproducible.
-#include "p2p.cuh"
+#include "solver.cuh"
 
 #include <cstdlib>
 
@@ -431,10 +431,8 @@ __global__ void k_cgs_scalars(const double* __restrict__ pg, int ng, const doubl
 __global__ void __launch_bounds__(kVecThreads)
 k_cgs_fused(const double* __restrict__ w, const double* __restrict__ dinv, size_t n, double* __restrict__ u,
             double* __restrict__ p, double* __restrict__ sd, double* __restrict__ x, double* __restrict__ r,
-            double* __restrict__ partial_g, double* __restrict__ partial_rr, const KrylovScalars* __restrict__ S,
-            const __grid_constant__ DistFuse F) {
+            double* __restrict__ partial_g, double* __restrict__ partial_rr, const KrylovScalars* __restrict__ S) {
   __shared__ double red[kVecThreads / 32];
-  __shared__ int last_s;
   if (S->done) return;
   const double alpha = S->alpha, beta = S->beta;
   double g = 0.0, rr = 0.0;
@@ -471,19 +469,6 @@ k_cgs_fused(const double* __restrict__ w, const double* __restrict__ dinv, size_
   const double t0 = block_sum(g, red);
   const double t1 = block_sum(rr, red);
   if (threadIdx.x == 0) { partial_g[blockIdx.x] = t0; partial_rr[blockIdx.x] = t1; }
-  if (F.enabled) {
-    // distributed: the last CTA to finish sends the boundary entries of the new u to the neighbours (the product of the
-    // next iteration receives them while it multiplies its interior slabs)
-    // (the grid-barrier idiom: the CTA barrier orders every thread's stores before thread 0, whose fence is cumulative)
-    __syncthreads();
-    if (threadIdx.x == 0) { __threadfence(); last_s = atomicAdd(&F.ctr[2], 1u) == gridDim.x - 1 ? 1 : 0; }
-    __syncthreads();
-    if (last_s) {
-      __threadfence();
-      p2p_halo_send(u, F, (int)threadIdx.x, (int)blockDim.x, [] { __syncthreads(); });
-      if (threadIdx.x == 0) F.ctr[2] = 0u;
-    }
-  }
 }
 
 void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep) {
@@ -538,21 +523,7 @@ void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep) {
   // columns only) are multiplied; the boundary slabs follow once the halo has landed. Measured at n = 4096: 8 GPUs
   // 0.122 vs 0.129 ms per iteration, 2 GPUs 0.362 vs 0.313 ms (the extra launch and the cross-stream joins cost more
   // than the hidden latency), so it is off by default.
-  // Distributed default (TFELCU_FUSED_DIST=0 switches it off): TWO launches per iteration. The product receives the halo of
-  // u in its CTA 0 while every CTA multiplies its interior slabs and reduces (r.u, r.r, u.Au) over the ranks in its last CTA
-  // (+ the scalar step); the vector update sends the boundary entries of the new u from its last CTA. Before: four launches
-  // (halo exchange, product, reduction, update) with two exposed waits for the slowest rank per iteration.
-  const char* fenv = std::getenv("TFELCU_FUSED_DIST");
-  const bool fuse_on = dist && ctx->p2p && s->dist->p2p_halo && s->plan.kernel == TFELCU_SPMV_TMA_STREAM && s->plan.n_interior >= 0 &&
-                       !(fenv && fenv[0] == '0') && !std::getenv("TFELCU_OVERLAP");
-  DistFuse fuse, fuse_off;
-  std::memset(&fuse_off, 0, sizeof(fuse_off));
-  if (fuse_on) {
-    dist_fuse_args(s, &fuse);
-    fuse.A.p[0] = P_g; fuse.A.n[0] = vg; fuse.A.p[1] = P_rr; fuse.A.n[1] = vg; fuse.k = 3;
-    fuse.red_out = s->dist->red.p;
-  }
-  const bool overlap = !fuse_on && dist && s->plan.n_interior > 0 && s->plan.n_interior < s->plan.n_blocks && std::getenv("TFELCU_OVERLAP");
+  const bool overlap = dist && s->plan.n_interior > 0 && s->plan.n_interior < s->plan.n_blocks && std::getenv("TFELCU_OVERLAP");
   if (overlap && !ctx->side_stream) {
     TFELCU_CK(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
     TFELCU_CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -567,7 +538,7 @@ void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep) {
       TFELCU_CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
       dist_halo_exchange(s, u, S, ctx->side_stream);
       TFELCU_CK(cudaEventRecord(ctx->ev_join, ctx->side_stream));
-    } else if (dist && !fuse_on) dist_halo_exchange(s, u, S);
+    } else if (dist) dist_halo_exchange(s, u, S);
     mark(t_on);
     const bool sampled = may_sample && prof_every > 0 && (it == 0 || it >= last_sample + (uint32_t)prof_every) && prof.size() < 1024;
     if (sampled) {
@@ -581,13 +552,11 @@ void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep) {
       n_d = spmv_launch_part(s, 1, u, w, P_d, S);
       TFELCU_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
       n_d2 = spmv_launch_part(s, 2, u, w, P_d2, S);
-    } else n_d = spmv_launch(s, u, w, P_d, S, fuse_on ? &fuse : nullptr);
+    } else n_d = spmv_launch(s, u, w, P_d, S);
     ++n_spmv;
     if (sampled) TFELCU_CK(cudaEventRecord(prof.back(), ctx->stream));
     mark(t_on);
-    if (fuse_on) {
-      // reduced in the tail of the product
-    } else if (dist && n_d2 > 0) {
+    if (dist && n_d2 > 0) {
       const double* ptrs[4] = {P_g, P_rr, P_d, P_d2}; const int ns[4] = {vg, vg, n_d, n_d2};
       dist_reduce(s, ptrs, ns, 4, 0, 1);
     } else if (dist) {
@@ -598,12 +567,10 @@ void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep) {
       ctx->count(); TFELCU_LAUNCH_CHECK();
     }
     mark(t_on);
-    k_cgs_fused<<<vg, kVecThreads, 0, ctx->stream>>>(w, dinv, n, u, s->p.p, sd, s->x.p, s->r.p, P_g, P_rr, S,
-                                                    fuse_on ? fuse : fuse_off);
+    k_cgs_fused<<<vg, kVecThreads, 0, ctx->stream>>>(w, dinv, n, u, s->p.p, sd, s->x.p, s->r.p, P_g, P_rr, S);
     ctx->count(); TFELCU_LAUNCH_CHECK();
     mark(t_on);
   };
-  if (fuse_on) dist_halo_exchange(s, u, nullptr, nullptr, 1);   // the loop opens with the send of the first u
 
   int check = s->params.check_every > 0 ? s->params.check_every : 50;
   KrylovScalars h;
@@ -639,7 +606,6 @@ void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep) {
     ctx->download(&h, S, 1);
   }
   if (graph_exec) TFELCU_CK(cudaGraphExecDestroy(graph_exec));
-  if (fuse_on && !h.done) dist_halo_exchange(s, u, nullptr, nullptr, 2);   // never expected: take the last send off the wire
   if (!tr.empty()) {
     double acc[4] = {0, 0, 0, 0}; int cnt = 0;
     for (size_t e = 0; e + 4 < tr.size(); e += 5, ++cnt)
@@ -812,6 +778,7 @@ void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep) {
 void solver_solve(tfelcu_solver* s, const double* d_rhs, double* d_x, tfelcu_solver_report* rep) {
   Ctx* ctx = s->ctx;
   TFELCU_REQUIRE(s->rowptr != nullptr, "solver has no operator: call set_operator first");
+  TFELCU_REQUIRE(!(s->dist && ctx->p2p_failed), "a peer rank did not answer during an earlier distributed solve: recreate the contexts");
   TFELCU_REQUIRE(!s->borrowed || s->borrowed_live, "the solver only borrowed the arrays of a bilinear form during tfelcu_matrix_solve: call set_operator");
   std::memset(rep, 0, sizeof(*rep));
   cudaEvent_t e0, e1;
@@ -831,6 +798,7 @@ void solver_solve(tfelcu_solver* s, const double* d_rhs, double* d_x, tfelcu_sol
   TFELCU_CK(cudaEventRecord(e1, ctx->stream));
   TFELCU_CK(cudaEventSynchronize(e1));
   float ms = 0.f; TFELCU_CK(cudaEventElapsedTime(&ms, e0, e1));
+  if (s->dist && dist_peer_failed(s)) rep->converged = -3;   // also for GMRES, whose device state has no field for it
   rep->t_solve_s = ms * 1e-3;
   rep->t_setup_s = s->t_setup_s;
   rep->t_precond_setup_s = s->t_precond_s;

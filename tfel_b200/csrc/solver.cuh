@@ -46,7 +46,6 @@ struct SpmvPlan {
   DevBuf<int16_t> delta16;               // column - row of every stored entry, when all fit 16 bits
   bool use_delta16 = false;
   int tile_nnz = 0, tile_rows = 0;
-  struct DistFuse* fuse = nullptr;       // set around one launch by spmv_launch (fused distributed CG)
 };
 
 // consecutive levels [l0, l1) of a level schedule launched together: one CTA walking several small levels
@@ -92,7 +91,6 @@ struct DistPlan {
   size_t n_halo = 0;                     // what a vector holds behind its owned entries: padding up to halo_base, then one
                                          // entry per column owned by another rank
   size_t halo_base = 0;                  // index of the first halo entry (owned entries rounded up to a 128-byte line)
-  DevBuf<unsigned int> fuse_ctr;         // counters of the fused loop (p2p.cuh: DistFuse::ctr)
   DevBuf<int32_t> colind_local;          // column indices in [owned | halo] numbering
   DevBuf<uint32_t> send_idx;             // owned entries to send, grouped by destination rank
   DevBuf<double> send_buf;
@@ -145,9 +143,7 @@ void solve_cg(tfelcu_solver* s, tfelcu_solver_report* rep);
 void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep);
 void spmv_plan(tfelcu_solver* s);
 // y = A x; when dot_partial != nullptr also writes per-CTA partial sums of x . y and returns their number
-struct DistFuse;
-int spmv_launch(tfelcu_solver* s, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal,
-                DistFuse* fuse = nullptr);
+int spmv_launch(tfelcu_solver* s, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal);
 int spmv_partial_count(tfelcu_solver* s);
 int spmv_launch_part(tfelcu_solver* s, int part, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal);
 void spmv_split_boundary(tfelcu_solver* s, size_t n_local);
@@ -162,11 +158,11 @@ void block_jacobi_apply(tfelcu_solver* s, const double* d_in, double* d_out);
 // ---- dist.cu
 void dist_setup(tfelcu_solver* s);
 void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S, cudaStream_t stream = nullptr, int mode = 3);
-void dist_fuse_args(tfelcu_solver* s, DistFuse* out);
 // epilogue == 1: the reducing kernel also performs the scalar step of the single-reduction CG (k_cgs_scalars)
 const double* dist_reduce(tfelcu_solver* s, const double* const* partial, const int* n, int k, int out_slot, int epilogue = 0);
 void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep);
 void dist_gather(tfelcu_solver* s, const double* x_local, double* x_global);
+bool dist_peer_failed(tfelcu_solver* s);
 void p2p_setup(Ctx* ctx);      // collective over the communicator of ctx
 void p2p_teardown(Ctx* ctx);
 double p2p_bench_allreduce(Ctx* ctx, int reps);

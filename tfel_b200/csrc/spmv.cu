@@ -13,7 +13,7 @@
 // Both can fuse the dot product x . (A x) of conjugate gradients (per-CTA partial sums, fixed order).
 //
 // Algorithmic bytes per product: 12 nnz + 4 (n + 1) + 8 n (x once) + 8 n (y).
-#include "p2p.cuh"
+#include "solver.cuh"
 #include "sortutil.cuh"
 
 #include <cstdlib>
@@ -197,10 +197,8 @@ template <bool DOT, int LANES, int TILE_NNZ, int CONSUMERS, int STAGES, int CTAS
 __global__ void __launch_bounds__(CONSUMERS + 32, CTAS)
 k_spmv_stream(const int32_t* __restrict__ rowptr, const COL_T* __restrict__ colind, const double* __restrict__ val,
               const int4* __restrict__ desc, int n_blocks, const double* __restrict__ x,
-              double* __restrict__ y, double* __restrict__ dot_partial, const KrylovScalars* __restrict__ scal,
-              const __grid_constant__ DistFuse F) {
+              double* __restrict__ y, double* __restrict__ dot_partial, const KrylovScalars* __restrict__ scal) {
   extern __shared__ __align__(128) unsigned char raw[];
-  __shared__ int fuse_flag;
   using Smem = StreamSmem<TILE_NNZ, CONSUMERS, STAGES, COL_T>;
   constexpr bool kDelta = sizeof(COL_T) == 2;
   constexpr int kAlign = kDelta ? 8 : 4;   // entries per 16 bytes of the column stream
@@ -214,14 +212,8 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const COL_T* __restrict__ coli
     for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], CONSUMERS); }
     mbar_fence_init();
   }
-  // distributed single-reduction CG (p2p.cuh: DistFuse): the halo of x is received by the consumers of CTA 0 while every
-  // CTA multiplies its interior slabs, and the global sums are formed by the last CTA to finish
-  const bool fused = DOT && F.enabled;
-  unsigned int launch_seq = 0;
-  if (fused) launch_seq = (unsigned int)F.seq_dev[kSeqLaunch] + 1u;
   __syncthreads();
   const int first = blockIdx.x, step = gridDim.x;
-  auto consumer_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory"); };
 
   if (tid >= CONSUMERS) {
     // ---- producer warp: lane 0 issues, one slab descriptor prefetched ahead --------------------
@@ -252,32 +244,11 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const COL_T* __restrict__ coli
   }
 
   // ---- consumers: LANES threads per row ---------------------------------------------------------
-  bool halo_here = !fused;
-  if (fused && blockIdx.x == 0) {
-    const bool ok = p2p_halo_recv(F.x_rw, F, tid, CONSUMERS, consumer_sync, &fuse_flag);
-    __threadfence();
-    consumer_sync();
-    if (tid == 0) {
-      if (!ok) F.S->done = -3;
-      __threadfence();
-      *reinterpret_cast<volatile unsigned int*>(&F.ctr[1]) = launch_seq;
-    }
-    halo_here = true;
-  }
   double dot = 0.0;
   int it = 0;
   const int row_in_slab = tid / LANES, lane = tid % LANES;
   for (int b = first; b < n_blocks; b += step, ++it) {
     const int stage = it % STAGES;
-    if (!halo_here && b >= F.n_interior) {   // the first slab of this CTA that references halo columns
-      const long long t0 = clock64();
-      while (*reinterpret_cast<volatile unsigned int*>(&F.ctr[1]) != launch_seq) {
-        if (clock64() - t0 > kSpinLimit) break;
-        __nanosleep(60);
-      }
-      __threadfence();
-      halo_here = true;
-    }
     mbar_wait(&S.full[stage], (uint32_t)(it / STAGES) & 1u);
     const int32_t* m = S.meta[stage];
     const int r0 = m[0], r1 = m[1], a0 = m[2], r0a = m[3];
@@ -323,15 +294,6 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const COL_T* __restrict__ coli
       double t = 0.0;
       for (int w = 0; w < CONSUMERS / 32; ++w) t += S.red[w];
       dot_partial[blockIdx.x] = t;
-    }
-    if (fused) {
-      if (tid == 0) { __threadfence(); fuse_flag = atomicAdd(&F.ctr[0], 1u) == gridDim.x - 1 ? 1 : 0; }
-      consumer_sync();
-      if (fuse_flag) {   // every CTA has published its partial sums
-        __threadfence();
-        p2p_allreduce(F.A, F.k, F.peers, F.me, F.P, F.seq_dev, F.red_out, F.S, 1, tid, consumer_sync);
-        if (tid == 0) { F.ctr[0] = 0u; F.seq_dev[kSeqLaunch] = launch_seq; }
-      }
     }
   }
 }
@@ -399,12 +361,9 @@ static void launch_stream_t(tfelcu_solver* s, int grid, const COL_T* col, const 
     TFELCU_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return;
   }
-  DistFuse off;
-  off.enabled = 0;
   kern<<<grid, CONSUMERS + 32, smem, s->ctx->stream>>>(s->rowptr, col, s->val,
                                                       reinterpret_cast<const int4*>(s->plan.desc.p) + s->plan.part_begin,
-                                                      s->plan.part_count, d_x, d_y, dot_partial, scal,
-                                                      (DOT && s->plan.fuse) ? *s->plan.fuse : off);
+                                                      s->plan.part_count, d_x, d_y, dot_partial, scal);
 }
 
 template <bool DOT, int LANES, int TILE_NNZ, int CONSUMERS, int STAGES, int CTAS>
@@ -443,20 +402,12 @@ static void launch_stream_cfg(tfelcu_solver* s, int grid, const double* d_x, dou
 static void stream_dispatch(tfelcu_solver* s, int grid, const double* d_x, double* d_y, double* dot_partial,
                             const KrylovScalars* scal);
 
-int spmv_launch(tfelcu_solver* s, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal,
-                DistFuse* fuse) {
+int spmv_launch(tfelcu_solver* s, const double* d_x, double* d_y, double* dot_partial, const KrylovScalars* scal) {
   Ctx* ctx = s->ctx;
   if (s->plan.kernel == TFELCU_SPMV_TMA_STREAM) {
     const int grid = stream_grid(s);
     s->plan.part_begin = 0; s->plan.part_count = s->plan.n_blocks;
-    if (fuse) {   // the tail of the product reduces (r.u, r.r) of the caller and its own partials of u.Au
-      TFELCU_REQUIRE(dot_partial != nullptr && fuse->k >= 1 && fuse->k <= 4, "fused product: bad reduction arguments");
-      fuse->A.p[fuse->k - 1] = dot_partial; fuse->A.n[fuse->k - 1] = grid;
-      fuse->x_rw = const_cast<double*>(d_x);
-    }
-    s->plan.fuse = fuse;
     stream_dispatch(s, grid, d_x, d_y, dot_partial, scal);
-    s->plan.fuse = nullptr;
     ctx->count(); TFELCU_LAUNCH_CHECK();
     return grid;
   }

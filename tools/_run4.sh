@@ -1,7 +1,8 @@
 cd $GRAFT_REPO_ROOT
-nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv
-for mode in 0 1; do
-TFELCU_TRACE=1 TFELCU_FUSED_DIST=$mode timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2970$mode bench.py --gpus 2 --steps 1 --warmup 3 --e2e-steps 0 > gpurun_out/r2_bench_n2_fused$mode.json 2> gpurun_out/r2_bench_n2_fused$mode.err &
-sleep 45; nvidia-smi --query-gpu=index,clocks.sm,power.draw --format=csv,noheader; wait
-grep "tfelcu trace\] rank" gpurun_out/r2_bench_n2_fused$mode.err | tail -2
-done
+timeout 900 python -m pytest tests/test_dist.py -m gpu -v 2>&1 | tail -9 | tee gpurun_out/r2_dist_tests_n2.log
+TFELCU_TRACE=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29700 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r2_bench_n2_b.json 2> gpurun_out/r2_bench_n2_b.err
+grep "tfelcu trace\] rank" gpurun_out/r2_bench_n2_b.err | tail -2
+python -c "
+import json
+d=json.loads(open('gpurun_out/r2_bench_n2_b.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['solve'], d['parity'], d['e2e'])"
