@@ -149,6 +149,8 @@ uint64_t tfelcu_ctx_launch_count(const tfelcu_ctx* ctx);
 /* 1 when the distributed Krylov loop exchanges halos and reduction scalars through peer-mapped device memory
  * (CUDA IPC over NVLink), 0 when it uses NCCL send / recv / allreduce (TFELCU_NO_P2P=1, or IPC unavailable) */
 int tfelcu_ctx_p2p_enabled(const tfelcu_ctx* ctx);
+/* diagnostic: measured FP64 FMA throughput of the device in TFLOP/s (8 independent chains per thread, 8 CTAs per SM) */
+int tfelcu_ctx_fp64_peak(tfelcu_ctx* ctx, double* tflops);
 /* diagnostic (collective): average microseconds of one 2-value allreduce through the peer arenas */
 int tfelcu_ctx_p2p_bench(tfelcu_ctx* ctx, int reps, double* allreduce_us);
 

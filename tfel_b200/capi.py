@@ -77,7 +77,7 @@ class SolverReport(C.Structure):
 SYMBOLS = [
     "tfelcu_last_error", "tfelcu_version", "tfelcu_ctx_create", "tfelcu_nccl_unique_id",
     "tfelcu_ctx_create_distributed", "tfelcu_ctx_destroy", "tfelcu_ctx_set_stream", "tfelcu_ctx_stream",
-    "tfelcu_ctx_synchronize", "tfelcu_ctx_rank", "tfelcu_ctx_launch_count", "tfelcu_ctx_p2p_enabled", "tfelcu_ctx_p2p_bench",
+    "tfelcu_ctx_synchronize", "tfelcu_ctx_rank", "tfelcu_ctx_launch_count", "tfelcu_ctx_p2p_enabled", "tfelcu_ctx_p2p_bench", "tfelcu_ctx_fp64_peak",
     "tfelcu_mesh_create", "tfelcu_mesh_gen_square", "tfelcu_mesh_gen_cube", "tfelcu_mesh_destroy",
     "tfelcu_mesh_info", "tfelcu_mesh_download", "tfelcu_mesh_geometry", "tfelcu_mesh_boundary",
     "tfelcu_mesh_boundary_download", "tfelcu_mesh_neighbours",
@@ -179,6 +179,12 @@ class Context:
     @property
     def p2p(self):
         return bool(lib().tfelcu_ctx_p2p_enabled(self.h))
+
+    def fp64_peak(self):
+        """measured FP64 FMA throughput of the device, TFLOP/s"""
+        t = C.c_double()
+        _ck(lib().tfelcu_ctx_fp64_peak(self.h, C.byref(t)))
+        return t.value
 
     def p2p_bench(self, reps=1000):
         us = C.c_double()

@@ -4,6 +4,7 @@
 #include "structs.cuh"
 #include "solver.cuh"
 
+#include <algorithm>
 #include <exception>
 #include <new>
 
@@ -181,6 +182,46 @@ int tfelcu_ctx_p2p_bench(tfelcu_ctx* ctx, int reps, double* allreduce_us) {
     TFELCU_REQUIRE(ctx && allreduce_us && reps > 0, "bad arguments");
     use_device(ctx);
     *allreduce_us = tfelcu::p2p_bench_allreduce(ctx, reps);
+  });
+}
+
+// diagnostic: FP64 FMA throughput of the device (the denominator of the FP64-pipe figures in profiles/)
+namespace {
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+}  // namespace
+
+int tfelcu_ctx_fp64_peak(tfelcu_ctx* ctx, double* tflops) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx && tflops, "bad arguments");
+    use_device(ctx);
+    const int grid = ctx->sm_count * 8, iters = 4096;
+    DevBuf<double> out((size_t)grid * 256);
+    cudaEvent_t e0, e1;
+    TFELCU_CK(cudaEventCreate(&e0)); TFELCU_CK(cudaEventCreate(&e1));
+    k_dfma_peak<<<grid, 256, 0, ctx->stream>>>(out.p, 64, 0.999999, 1e-9);   // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+      TFELCU_CK(cudaEventRecord(e0, ctx->stream));
+      k_dfma_peak<<<grid, 256, 0, ctx->stream>>>(out.p, iters, 0.999999, 1e-9);
+      TFELCU_CK(cudaEventRecord(e1, ctx->stream));
+      TFELCU_CK(cudaEventSynchronize(e1));
+      float ms = 0.f; TFELCU_CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)grid * 256.0;
+      best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    ctx->count(6); TFELCU_LAUNCH_CHECK();
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops = best;
   });
 }
 

@@ -1,4 +1,4 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests/test_gpu_tile.py -x -q 2>&1 | tail -5 | tee gpurun_out/r2_tile_tests.log
-timeout 300 python tools/asm_sweep.py --n 4096 --configs rows auto 2>&1 | tail -5 | tee gpurun_out/r2_asm_sweep_tile.jsonl
-TFELCU_NO_ISO=1 timeout 300 python tools/asm_sweep.py --n 4096 --configs auto 2>&1 | tail -1 | sed 's/auto/auto-no-iso/' | tee -a gpurun_out/r2_asm_sweep_tile.jsonl
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 | tee gpurun_out/r2_gpu_tests_c.log
+timeout 900 python bench.py --steps 3 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r2_bench_n1_c.json 2> gpurun_out/r2_bench_n1_c.err; python -c "
+import json; d=json.loads(open('gpurun_out/r2_bench_n1_c.json').read().strip().splitlines()[-1]); print(d['value'], d['assembly']['ms'], d['solve'], d['roofline']['frac'], d['roofline']['moved_frac'], d.get('fp64_fma_peak_tflops'))"
