@@ -1,7 +1,8 @@
 // Coefficient functions as __device__ functors (include/tfel/tfel_device.cuh): the general Poisson problem of the parity
 // tests (-lap u + c(x) u = f(x), u = g on the boundary; source of examples/poisson.cpp:4-14 of the reference) assembled
-// twice -- with host callbacks (tabulated on the host, as the reference's free_function leaves are evaluated) and with
-// device functors instantiated in THIS translation unit -- and compared.
+// three times -- with host callbacks (tabulated on the host, the fallback that reports itself), with device functors
+// tabulated on the device (device_expr) and with device functors called by the assembly kernels themselves (dev(f): the
+// functor is device code of THIS translation unit, nothing is evaluated on the host) -- and compared.
 #include <tfel/tfel.hpp>
 #include <tfel/tfel_device.cuh>
 
@@ -25,6 +26,8 @@ struct src_dev {
 struct reac_dev {
   __device__ double operator()(const double* x) const { return 1.0 + x[0] * x[0] + 0.5 * x[1]; }
 };
+__device__ double reac_plain(const double* x) { return 1.0 + x[0] * x[0] + 0.5 * x[1]; }
+TFEL_DEVICE_FUNCTION(reac_plain);
 
 int main(int argc, char* argv[]) {
   try {
@@ -42,23 +45,32 @@ int main(int argc, char* argv[]) {
     dictionary param(dictionary().set("maxits", 20000u).set("restart", 1000u).set("rtol", 1.e-12)
                      .set("atol", 1.e-50).set("dtol", 1.e20).set("ilufill", 2u));
     std::vector<array<double>> sol;
-    for (int variant(0); variant < 2; ++variant) {
+    unsigned long long host_calls[3] = {0, 0, 0};
+    for (int variant(0); variant < 3; ++variant) {
+      const unsigned long long calls_before(tfel_cuda::host_callback_evaluations());
       bilinear_form<fes_type, fes_type> a(fes, fes);
       linear_form<fes_type> b(fes);
       auto u(a.get_trial_function()); auto v(a.get_test_function()); auto w(b.get_test_function());
       if (variant == 0) {
         a += integrate<quad_type>(d<1>(u) * d<1>(v) + d<2>(u) * d<2>(v) + reac_host * (u * v), m);
         b += integrate<quad_type>(src_host * w, m);
-      } else {
+      } else if (variant == 1) {
         a += integrate<quad_type>(d<1>(u) * d<1>(v) + d<2>(u) * d<2>(v) + device_expr<quad_type>(reac_dev(), m) * (u * v), m);
         b += integrate<quad_type>(device_expr<quad_type>(src_dev{0.1}, m) * w, m);
+      } else {
+        a += integrate<quad_type>(d<1>(u) * d<1>(v) + d<2>(u) * d<2>(v) + dev(reac_plain_functor()) * (u * v), m);
+        b += integrate<quad_type>(dev(src_dev{0.1}) * w, m);
       }
+      host_calls[variant] = tfel_cuda::host_callback_evaluations() - calls_before;
       solver::cuda::cg_jacobi s(param);
       sol.push_back(a.solve(b, s).get_coefficients());
     }
+    std::cout << "device_functor: host evaluations of integrand leaves: callbacks " << host_calls[0] << ", device_expr "
+              << host_calls[1] << ", dev " << host_calls[2] << std::endl;
+    if (host_calls[0] == 0 or host_calls[1] != 0 or host_calls[2] != 0) throw std::string("unexpected host evaluation counts");
     double diff(0.0), nrm(0.0);
     for (std::size_t i(0); i < fes.get_dof_number(); ++i) {
-      diff = std::max(diff, std::fabs(sol[0].at(i) - sol[1].at(i)));
+      diff = std::max(diff, std::max(std::fabs(sol[0].at(i) - sol[1].at(i)), std::fabs(sol[0].at(i) - sol[2].at(i))));
       nrm = std::max(nrm, std::fabs(sol[0].at(i)));
     }
     std::cout << "device_functor: dofs " << fes.get_dof_number() << " max |u_host_callback - u_device_functor| " << diff

@@ -509,7 +509,25 @@ struct factor_desc {
   std::shared_ptr<std::vector<double>> data;         // FIELD coefficients
   std::function<double(const double*)> fn;           // host callback (free_function / std_function)
   std::vector<tfelcu_op> prog;                       // PROGRAM
+  const void* device_fn = nullptr;                   // FUNCTION: device code instantiated in the user's nvcc translation unit
+  std::shared_ptr<void> device_closure;              // FUNCTION: the functor object in device memory (tfel_device.cuh)
 };
+
+// Host callbacks are the FALLBACK for integrands: a free_function leaf compiled by a host compiler cannot run on the GPU,
+// so it is evaluated here at every quadrature point of every cell and uploaded (expression.hpp:31-58 evaluates it in the
+// cell loop). It reports itself: the counter below, and once per process a note on stderr. Device alternatives without
+// any host evaluation: __device__ functors (tfel_device.cuh: dev(f) * v, compiled by nvcc) or xfun expressions.
+inline unsigned long long& host_callback_evaluations() { static unsigned long long n(0); return n; }
+inline void note_host_callbacks(unsigned long long n) {
+  host_callback_evaluations() += n;
+  static bool said(false);
+  if (not said and not std::getenv("TFEL_CUDA_QUIET")) {
+    said = true;
+    std::cerr << "tfel_cuda: an integrand contains a host function (free_function): " << n << " evaluations on the host for this "
+                 "integral; use a __device__ functor (tfel/tfel_device.cuh) or xfun for device-side evaluation" << std::endl;
+  }
+}
+
 
 struct monomial {
   double c = 1.0;
@@ -723,6 +741,7 @@ public:
         bool same(f.kind == g.kind and f.d == g.d);
         if (same and f.kind == TFELCU_FACTOR_FIELD) same = f.fes == g.fes and f.data.get() == g.data.get();
         else if (same and f.kind == TFELCU_FACTOR_TABLE) same = f.device_table.get() == g.device_table.get();
+        else if (same and f.kind == TFELCU_FACTOR_FUNCTION) same = f.device_fn == g.device_fn and f.device_closure.get() == g.device_closure.get();
         else if (same and f.kind == TFELCU_FACTOR_PROGRAM) {
           same = f.prog.size() == g.prog.size();
           for (std::size_t t(0); same and t < f.prog.size(); ++t) same = f.prog[t].op == g.prog[t].op and f.prog[t].imm == g.prog[t].imm;
@@ -740,7 +759,9 @@ public:
       const factor_desc& f(e.factors[kept[i]]);
       tfelcu_factor& o(factors[i]);
       o.kind = f.kind; o.d = f.d; o.fes = f.fes; o.data = nullptr; o.ops = nullptr; o.n_ops = 0; o.pad = 0;
+      o.fn = nullptr; o.closure = nullptr;
       if (f.kind == TFELCU_FACTOR_FIELD) o.data = f.data->data();
+      else if (f.kind == TFELCU_FACTOR_FUNCTION) { o.fn = f.device_fn; o.closure = f.device_closure.get(); }
       else if (f.kind == TFELCU_FACTOR_PROGRAM) { o.ops = f.prog.data(); o.n_ops = static_cast<int>(f.prog.size()); }
       else if (f.kind == TFELCU_FACTOR_TABLE) {   // evaluated on the device by a user functor (tfel_device.cuh)
         if (f.table_quad != quad_id) throw std::string("integrate: a device function was tabulated for another quadrature formula");
@@ -756,6 +777,7 @@ public:
         tables.emplace_back(K * nq);
         std::vector<double>& t(tables.back());
         for (std::size_t p(0); p < K * nq; ++p) t[p] = f.fn(&xq[p * dim]);
+        note_host_callbacks(K * nq);
         o.kind = TFELCU_FACTOR_TABLE; o.data = t.data();
       }
     }

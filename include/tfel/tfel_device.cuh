@@ -4,11 +4,17 @@
 // path a function of x can instead be any copyable type with   __device__ double operator()(const double* x) const:
 //
 //   struct gaussian { double sigma; __device__ double operator()(const double* x) const { ... } };
-//   b += integrate<quad_type>(device_expr<quad_type>(gaussian{0.1}, m) * v, m);
+//   b += integrate<quad_type>(dev(gaussian{0.1}) * v, m);
 //
-// device_expr instantiates the functor in a kernel of the USER's translation unit, evaluates it at the quadrature
-// points of every cell (cell.hpp:456-468) on the device, and hands the device-resident table to the assembly kernels
-// (TFELCU_FACTOR_TABLE): no host evaluation, no host <-> device copy. Include after <tfel/tfel.hpp>; compile with nvcc.
+// dev(f) instantiates the functor as DEVICE CODE in the user's translation unit -- a __device__ trampoline
+// double (const void* closure, const double* x) whose address crosses the C ABI (TFELCU_FACTOR_FUNCTION) together with a
+// device copy of the functor object -- and the assembly kernels of libtfel_cuda call it at the quadrature points of every
+// cell, inside the element loop, exactly where the reference evaluates its free_function leaves (expression.hpp:46-48):
+// no table, no host evaluation, no host <-> device copy. TFEL_DEVICE_FUNCTION(name) wraps a plain
+// __device__ double name(const double*) the same way.
+// device_expr<quad>(f, mesh) is the older variant: it evaluates the functor at every quadrature point into a
+// device-resident table first (TFELCU_FACTOR_TABLE).
+// Include after <tfel/tfel.hpp>; compile with nvcc.
 #ifndef TFEL_TFEL_DEVICE_CUH
 #define TFEL_TFEL_DEVICE_CUH
 
@@ -28,7 +34,51 @@ inline void cuda_ck(cudaError_t e) {
   if (e != cudaSuccess) throw std::string("tfel_device: ") + cudaGetErrorString(e);
 }
 
+// the device code the library calls: one instance per functor type, in the user's translation unit
+template <typename F>
+__device__ double functor_trampoline(const void* closure, const double* x) { return (*static_cast<const F*>(closure))(x); }
+
+template <typename F>
+__global__ void k_trampoline_address(const void** out) { *out = reinterpret_cast<const void*>(&functor_trampoline<F>); }
+
+template <typename F>
+const void* trampoline_address() {
+  static const void* address(nullptr);   // one query per functor type and process
+  if (address) return address;
+  const void** d(nullptr);
+  cuda_ck(cudaMalloc(&d, sizeof(void*)));
+  cudaStream_t stream(static_cast<cudaStream_t>(tfelcu_ctx_stream(context())));
+  k_trampoline_address<F><<<1, 1, 0, stream>>>(d);
+  cuda_ck(cudaGetLastError());
+  cuda_ck(cudaMemcpyAsync(&address, d, sizeof(void*), cudaMemcpyDeviceToHost, stream));
+  cuda_ck(cudaStreamSynchronize(stream));
+  cudaFree(d);
+  return address;
+}
+
 }  // namespace tfel_cuda
+
+// rank-0 expression whose value at a point x is f(x), evaluated by the assembly kernels themselves
+template <typename F>
+expression<false> dev(const F& f) {
+  static_assert(std::is_trivially_copyable<F>::value, "a device functor is copied to the GPU byte for byte");
+  void* closure(nullptr);
+  tfel_cuda::cuda_ck(cudaMalloc(&closure, sizeof(F)));
+  std::shared_ptr<void> owner(closure, [](void* p) { cudaFree(p); });
+  cudaStream_t stream(static_cast<cudaStream_t>(tfelcu_ctx_stream(tfel_cuda::context())));
+  tfel_cuda::cuda_ck(cudaMemcpyAsync(closure, &f, sizeof(F), cudaMemcpyHostToDevice, stream));
+  tfel_cuda::cuda_ck(cudaStreamSynchronize(stream));
+  expression<false> e;
+  tfel_cuda::factor_desc d;
+  d.kind = TFELCU_FACTOR_FUNCTION; d.device_fn = tfel_cuda::trampoline_address<F>(); d.device_closure = owner;
+  e.factors.push_back(d);
+  tfel_cuda::monomial mono; mono.factors.push_back(0); e.terms.push_back(mono);
+  return e;
+}
+
+// a plain  __device__ double name(const double* x)  as a functor type name##_functor (dev(name##_functor()) * v)
+#define TFEL_DEVICE_FUNCTION(name) \
+  struct name##_functor { __device__ double operator()(const double* x) const { return name(x); } }
 
 // rank-0 expression whose value at a quadrature point is f(x_q), evaluated on the device
 template <typename quad_t, typename F, typename mesh_t>

@@ -47,7 +47,11 @@ enum {
   TFELCU_FACTOR_FIELD = 1,    /* finite_element_function<fe, d>, expression.hpp:89-139 */
   TFELCU_FACTOR_TABLE = 2,    /* free_function / std_function tabulated at the quadrature points
                                  (expression.hpp:31-87): double[K][nq], host or device */
-  TFELCU_FACTOR_PROGRAM = 3   /* function of x evaluated on device (postfix program) */
+  TFELCU_FACTOR_PROGRAM = 3,  /* function of x evaluated on device (postfix program) */
+  TFELCU_FACTOR_FUNCTION = 4  /* function of x as DEVICE CODE of the caller: a __device__ function
+                                 double fn(const void* closure, const double* x) compiled by nvcc in the user's translation unit
+                                 (include/tfel/tfel_device.cuh instantiates it from any functor type) and called by the
+                                 assembly kernels at every quadrature point -- no table, no host evaluation */
 };
 
 /* postfix opcodes of TFELCU_FACTOR_PROGRAM */
@@ -67,6 +71,8 @@ typedef struct {
   const tfelcu_op* ops;       /* PROGRAM: host array */
   int32_t n_ops;
   int32_t pad;
+  const void* fn;             /* FUNCTION: device address of double (*)(const void* closure, const double* x) */
+  const void* closure;        /* FUNCTION: device memory handed to fn (the functor object), may be NULL */
 } tfelcu_factor;
 
 /* One monomial  c * prod(factors) * D^{test_d} psi^{test_comp}_i * D^{trial_d} phi^{trial_comp}_j  of an

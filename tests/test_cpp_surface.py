@@ -17,7 +17,7 @@ def build():
 
 def test_reference_programs_compile_against_the_cuda_headers():
     build()
-    for name in ("poisson", "stokes_2d_p2_p1", "navier_stokes_2d_p2_p1", "plugin_and_forms", "expression_algebra", "device_functor",
+    for name in ("poisson", "stokes_2d_p2_p1", "navier_stokes_2d_p2_p1", "plugin_and_forms", "expression_algebra", "device_functor", "poisson_device",
                  "export_ensight", "export_format_host", "laplacian_transient"):
         assert os.path.exists(os.path.join(BIN, name))
 
@@ -178,6 +178,27 @@ def test_device_functor_coefficients():
     r = subprocess.run([os.path.join(BIN, "device_functor"), "40"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "device_functor: ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_poisson_with_a_device_source_makes_no_host_callbacks(tmp_path):
+    """examples/poisson.cpp's Gaussian source as a __device__ functor called by the assembly kernels themselves
+    (TFELCU_FACTOR_FUNCTION): zero host evaluations of integrand leaves, and the linear form equals the oracle's with the
+    same source tabulated by numpy (1e-12)."""
+    import numpy as np
+    import oracle_runner
+    import problems
+    build()
+    n = 40
+    out = str(tmp_path / "b.bin")
+    r = subprocess.run([os.path.join(BIN, "poisson_device"), str(n), out], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "host evaluations of integrand leaves 0," in r.stdout
+    b = np.fromfile(out)
+    p = problems.poisson("p1", n)
+    p.linear = [dict(test=(0, 0), c=1.0, factors=[("x", problems.gaussian_src)])]
+    ref = oracle_runner.run(p)
+    assert np.abs(b - ref["linear_form"]).max() <= 1e-12 * np.abs(ref["linear_form"]).max()
 
 
 @pytest.mark.gpu

@@ -44,7 +44,7 @@ class Op(C.Structure):
 
 class Factor(C.Structure):
     _fields_ = [("kind", C.c_int32), ("d", C.c_int32), ("fes", C.c_void_p), ("data", C.c_void_p),
-                ("ops", C.POINTER(Op)), ("n_ops", C.c_int32), ("pad", C.c_int32)]
+                ("ops", C.POINTER(Op)), ("n_ops", C.c_int32), ("pad", C.c_int32), ("fn", C.c_void_p), ("closure", C.c_void_p)]
 
 
 class Term(C.Structure):

@@ -343,6 +343,10 @@ void build_form(Ctx* ctx, tfelcu_mesh* mesh, int quad, const tfelcu_factor* fact
       }
       TFELCU_REQUIRE(depth == 1, "malformed coefficient program");
       prog_at += s.n_ops;
+    } else if (s.kind == TFELCU_FACTOR_FUNCTION) {
+      TFELCU_REQUIRE(s.fn != nullptr, "function factor without device code");
+      TFELCU_REQUIRE(s.closure == nullptr || is_device_pointer(s.closure), "the closure of a function factor must live in device memory");
+      d.fn = s.fn; d.closure = s.closure;
     } else {
       fail("unknown coefficient factor kind");
     }
