@@ -57,6 +57,18 @@ inline tfelcu_ctx* context() {
   return h.c;
 }
 
+// a plain device array (tfelcu_array_*): coefficient vectors of discrete functions live here between a solve, the algebra
+// on elements and the next += that uses them as coefficient fields
+class device_array {
+public:
+  explicit device_array(std::size_t count) : n(count) { ck(tfelcu_array_create(context(), count, &p)); }
+  device_array(const device_array&) = delete;
+  device_array& operator=(const device_array&) = delete;
+  ~device_array() { if (p) tfelcu_array_destroy(context(), p); }
+  double* p = nullptr;
+  std::size_t n = 0;
+};
+
 }  // namespace tfel_cuda
 
 // ---- array<T> (thomashilke/spikes array.hpp subset: what crosses the solver plugin boundary) -------------
@@ -91,6 +103,55 @@ private:
   std::vector<std::size_t> size;
   std::vector<T> data;
 };
+
+namespace tfel_cuda {
+
+// Coefficients of a discrete function: on the device, on the host, or both (whichever side was asked for last is
+// fetched lazily). Device arrays are immutable once shared: arithmetic produces new ones.
+inline std::size_t& coefficient_transfers() { static std::size_t n(0); return n; }   // host <-> device copies so far
+
+class coefficients {
+public:
+  coefficients() {}
+  explicit coefficients(array<double> c) : host(std::move(c)), host_valid(true), count(host.get_element_number()) {}
+  explicit coefficients(std::shared_ptr<device_array> d) : dev(std::move(d)), count(dev ? dev->n : 0) {}
+  std::size_t size() const { return count; }
+  const array<double>& on_host() const {
+    if (not host_valid) {
+      host = array<double>{count};
+      if (count) ck(tfelcu_array_copy(context(), host.get_data(), dev->p, count));
+      host_valid = true; ++coefficient_transfers();
+    }
+    return host;
+  }
+  const std::shared_ptr<device_array>& on_device() const {
+    if (not dev) {
+      dev = std::make_shared<device_array>(count);
+      if (count) ck(tfelcu_array_copy(context(), dev->p, host.get_data(), count));
+      ++coefficient_transfers();
+    }
+    return dev;
+  }
+  // a x + b y on the device (y may be null)
+  static coefficients lincomb(double a, const coefficients& x, double b, const coefficients* y) {
+    std::shared_ptr<device_array> out(std::make_shared<device_array>(x.size()));
+    ck(tfelcu_array_lincomb(context(), x.size(), a, x.on_device()->p, b, y ? y->on_device()->p : nullptr, out->p));
+    return coefficients(out);
+  }
+  // [offset, offset + n) as a new device array
+  coefficients slice(std::size_t offset, std::size_t n) const {
+    std::shared_ptr<device_array> out(std::make_shared<device_array>(n));
+    if (n) ck(tfelcu_array_copy(context(), out->p, on_device()->p + offset, n));
+    return coefficients(out);
+  }
+private:
+  mutable array<double> host;
+  mutable bool host_valid = false;
+  mutable std::shared_ptr<device_array> dev;
+  std::size_t count = 0;
+};
+
+}  // namespace tfel_cuda
 
 // ---- dictionary (src/core/dictionary.hpp:8-94) --------------------------------------------------------------------------
 class dictionary {
@@ -289,31 +350,40 @@ public:
   using cell_type = typename fe_t::cell_type;
   static const std::size_t n_component = 1;
 
-  class element {   // fes.hpp:219-364 (coefficient vector of a discrete function)
+  // fes.hpp:219-364: coefficient vector of a discrete function. The coefficients stay on the device between a solve,
+  // the algebra below (fused vector kernels, tfelcu_array_lincomb) and their use as coefficient fields of the next +=
+  // (make_expr); get_coefficients() / evaluate() fetch a host copy on first use.
+  class element {
   public:
-    element(const finite_element_space& f, array<double> c) : fes(&f), coefficients(std::move(c)) {}
+    element(const finite_element_space& f, array<double> c) : fes(&f), coef(std::move(c)) {}
+    element(const finite_element_space& f, tfel_cuda::coefficients c) : fes(&f), coef(std::move(c)) {}
     const finite_element_space& get_finite_element_space() const { return *fes; }
-    const array<double>& get_coefficients() const { return coefficients; }
-    // coefficient-wise algebra of fes.hpp:314-359 (discrete functions of one space are a vector space)
+    const array<double>& get_coefficients() const { return coef.on_host(); }
+    const tfel_cuda::coefficients& get_storage() const { return coef; }
     // fes.hpp:247-255: sum_n coefficients[dof(k, n)] phi_n(x_hat) (the dof map is fetched from the device once per space)
     double evaluate(std::size_t k, const double* x_hat) const {
       const array<unsigned int>& dm(fes->cached_dof_map());
+      const array<double>& c(coef.on_host());
       double table[10 * 4];
       int nd(0);
       tfel_cuda::ck(tfelcu_fe_tabulate(cell_type::dim, fe_t::id, x_hat, table, &nd));
       double value(0.0);
-      for (int n(0); n < nd; ++n) value += coefficients.at(dm.at(k, n)) * table[n * (cell_type::dim + 1)];
+      for (int n(0); n < nd; ++n) value += c.at(dm.at(k, n)) * table[n * (cell_type::dim + 1)];
       return value;
     }
+    // an arbitrary host function of the coefficients (host round trip: the function is host code)
     element& transform(const std::function<double(double)>& f) {
-      for (std::size_t i(0); i < coefficients.get_element_number(); ++i) coefficients.at(i) = f(coefficients.at(i));
+      array<double> c(coef.on_host());
+      for (std::size_t i(0); i < c.get_element_number(); ++i) c.at(i) = f(c.at(i));
+      coef = tfel_cuda::coefficients(std::move(c));
       return *this;
     }
     element transformed(const std::function<double(double)>& f) const { element r(*this); r.transform(f); return r; }
-    element& operator*=(double s) { return transform([s](double c) { return c * s; }); }
-    element& operator/=(double s) { return transform([s](double c) { return c / s; }); }
-    element& operator+=(const element& o) { same_space(o); for (std::size_t i(0); i < size(); ++i) coefficients.at(i) += o.coefficients.at(i); return *this; }
-    element& operator-=(const element& o) { same_space(o); for (std::size_t i(0); i < size(); ++i) coefficients.at(i) -= o.coefficients.at(i); return *this; }
+    // coefficient-wise algebra of fes.hpp:314-359 (discrete functions of one space are a vector space), on the device
+    element& operator*=(double s) { coef = tfel_cuda::coefficients::lincomb(s, coef, 0.0, nullptr); return *this; }
+    element& operator/=(double s) { coef = tfel_cuda::coefficients::lincomb(1.0 / s, coef, 0.0, nullptr); return *this; }
+    element& operator+=(const element& o) { same_space(o); coef = tfel_cuda::coefficients::lincomb(1.0, coef, 1.0, &o.coef); return *this; }
+    element& operator-=(const element& o) { same_space(o); coef = tfel_cuda::coefficients::lincomb(1.0, coef, -1.0, &o.coef); return *this; }
     // fes.hpp:366-405 (hidden friends: the reference's free templates cannot deduce fe from a nested type)
     friend element operator+(element a, const element& b) { a += b; return a; }
     friend element operator-(element a, const element& b) { a -= b; return a; }
@@ -321,12 +391,11 @@ public:
     friend element operator*(element a, double s) { a *= s; return a; }
     friend element operator/(element a, double s) { a /= s; return a; }
   private:
-    std::size_t size() const { return coefficients.get_element_number(); }
     void same_space(const element& o) const {
       if (fes != o.fes) throw std::string("operations between elements of different finite element spaces are not supported.");
     }
     const finite_element_space* fes;
-    array<double> coefficients;
+    tfel_cuda::coefficients coef;
   };
 
   explicit finite_element_space(const fe_mesh<cell_type>& m) : msh(&m) {
@@ -422,36 +491,38 @@ public:
   template <std::size_t n>
   using component_space = finite_element_space<typename std::tuple_element<n, std::tuple<fe_pack...>>::type>;
 
-  class element {   // composite_fes.hpp:152-300
+  class element {   // composite_fes.hpp:152-300; coefficients [u0 | u1 | p] on the device like the scalar element's
   public:
-    element(const composite_finite_element_space& f, array<double> c) : fes(&f), coefficients(std::move(c)) {}
+    element(const composite_finite_element_space& f, array<double> c) : fes(&f), coef(std::move(c)) {}
+    element(const composite_finite_element_space& f, tfel_cuda::coefficients c) : fes(&f), coef(std::move(c)) {}
     // from one element per component (composite_fes.hpp:160-175)
     template <typename first_t, typename... rest_t,
-              typename = typename std::enable_if<!std::is_same<typename std::decay<first_t>::type, array<double>>::value>::type>
-    element(const composite_finite_element_space& f, const first_t& c0, const rest_t&... cs) : fes(&f), coefficients{f.get_total_dof_number()} {
+              typename = typename std::enable_if<!std::is_same<typename std::decay<first_t>::type, array<double>>::value and
+                                                 !std::is_same<typename std::decay<first_t>::type, tfel_cuda::coefficients>::value>::type>
+    element(const composite_finite_element_space& f, const first_t& c0, const rest_t&... cs) : fes(&f) {
+      std::shared_ptr<tfel_cuda::device_array> all(std::make_shared<tfel_cuda::device_array>(f.get_total_dof_number()));
       std::size_t at(0);
-      append(at, c0, cs...);
+      append(*all, at, c0, cs...);
+      coef = tfel_cuda::coefficients(all);
     }
-    const array<double>& get_coefficients() const { return coefficients; }
+    const array<double>& get_coefficients() const { return coef.on_host(); }
+    const tfel_cuda::coefficients& get_storage() const { return coef; }
     template <std::size_t n>
     typename component_space<n>::element get_component() const {
       const component_space<n>& sp(fes->template get_finite_element_space<n>());
-      array<double> c{sp.get_dof_number()};
-      const std::size_t off(fes->get_component_offset(n));
-      for (std::size_t i(0); i < c.get_size(0); ++i) c.at(i) = coefficients.at(off + i);
-      return typename component_space<n>::element(sp, std::move(c));
+      return typename component_space<n>::element(sp, coef.slice(fes->get_component_offset(n), sp.get_dof_number()));
     }
   private:
-    void append(std::size_t&) {}
+    void append(tfel_cuda::device_array&, std::size_t&) {}
     template <typename first_t, typename... rest_t>
-    void append(std::size_t& at, const first_t& c0, const rest_t&... cs) {
-      const array<double>& c(c0.get_coefficients());
-      for (std::size_t i(0); i < c.get_size(0); ++i) coefficients.at(at + i) = c.at(i);
-      at += c.get_size(0);
-      append(at, cs...);
+    void append(tfel_cuda::device_array& all, std::size_t& at, const first_t& c0, const rest_t&... cs) {
+      const tfel_cuda::coefficients& c(c0.get_storage());
+      if (c.size()) tfel_cuda::ck(tfelcu_array_copy(tfel_cuda::context(), all.p + at, c.on_device()->p, c.size()));
+      at += c.size();
+      append(all, at, cs...);
     }
     const composite_finite_element_space* fes;
-    array<double> coefficients;
+    tfel_cuda::coefficients coef;
   };
 
   explicit composite_finite_element_space(const fe_mesh<cell_type>& m)
@@ -506,7 +577,7 @@ struct factor_desc {
   std::shared_ptr<void> device_table;                // TABLE: double[K][nq] on the device (tfel_device.cuh functors)
   int table_quad = 0;                                // TABLE: quadrature formula the table was evaluated for
   const tfelcu_fes* fes = nullptr;                   // FIELD
-  std::shared_ptr<std::vector<double>> data;         // FIELD coefficients
+  coefficients data;                                 // FIELD coefficients (device resident)
   std::function<double(const double*)> fn;           // host callback (free_function / std_function)
   std::vector<tfelcu_op> prog;                       // PROGRAM
   const void* device_fn = nullptr;                   // FUNCTION: device code instantiated in the user's nvcc translation unit
@@ -569,11 +640,9 @@ inline expression<r> add(const expression<a>& x, const expression<b>& y, double 
     // like the reference does (no cancellation between expanded products in (u_h - v_h) * (u_h - v_h))
     const factor_desc& fx(x.factors[x.terms[0].factors[0]]);
     const factor_desc& fy(y.factors[y.terms[0].factors[0]]);
-    if (fx.fes == fy.fes and fx.d == fy.d and fx.data->size() == fy.data->size()) {
+    if (fx.fes == fy.fes and fx.d == fy.d and fx.data.size() == fy.data.size()) {
       factor_desc f(fx);
-      f.data = std::make_shared<std::vector<double>>(fx.data->size());
-      const double cx(x.terms[0].c), cy(sign * y.terms[0].c);
-      for (std::size_t i(0); i < f.data->size(); ++i) (*f.data)[i] = cx * (*fx.data)[i] + cy * (*fy.data)[i];
+      f.data = coefficients::lincomb(x.terms[0].c, fx.data, sign * y.terms[0].c, &fy.data);   // on the device
       out.factors.push_back(f);
       monomial m; m.factors.push_back(0); out.terms.push_back(m);
       return out;
@@ -636,8 +705,7 @@ expression<false> make_expr(const typename finite_element_space<fe_t>::element& 
   expression<false> e;
   tfel_cuda::factor_desc d;
   d.kind = TFELCU_FACTOR_FIELD; d.d = 0; d.fes = u.get_finite_element_space().handle();
-  const array<double>& c(u.get_coefficients());
-  d.data = std::make_shared<std::vector<double>>(c.get_data(), c.get_data() + c.get_element_number());
+  d.data = u.get_storage();   // shares the device array of the element
   e.factors.push_back(d);
   tfel_cuda::monomial m; m.factors.push_back(0); e.terms.push_back(m);
   return e;
@@ -739,7 +807,7 @@ public:
       for (std::size_t k(0); k < kept.size() and remap[i] < 0; ++k) {
         const factor_desc& g(e.factors[kept[k]]);
         bool same(f.kind == g.kind and f.d == g.d);
-        if (same and f.kind == TFELCU_FACTOR_FIELD) same = f.fes == g.fes and f.data.get() == g.data.get();
+        if (same and f.kind == TFELCU_FACTOR_FIELD) same = f.fes == g.fes and f.data.on_device().get() == g.data.on_device().get();
         else if (same and f.kind == TFELCU_FACTOR_TABLE) same = f.device_table.get() == g.device_table.get();
         else if (same and f.kind == TFELCU_FACTOR_FUNCTION) same = f.device_fn == g.device_fn and f.device_closure.get() == g.device_closure.get();
         else if (same and f.kind == TFELCU_FACTOR_PROGRAM) {
@@ -760,7 +828,7 @@ public:
       tfelcu_factor& o(factors[i]);
       o.kind = f.kind; o.d = f.d; o.fes = f.fes; o.data = nullptr; o.ops = nullptr; o.n_ops = 0; o.pad = 0;
       o.fn = nullptr; o.closure = nullptr;
-      if (f.kind == TFELCU_FACTOR_FIELD) o.data = f.data->data();
+      if (f.kind == TFELCU_FACTOR_FIELD) o.data = f.data.on_device()->p;   // a device pointer: nothing is uploaded
       else if (f.kind == TFELCU_FACTOR_FUNCTION) { o.fn = f.device_fn; o.closure = f.device_closure.get(); }
       else if (f.kind == TFELCU_FACTOR_PROGRAM) { o.ops = f.prog.data(); o.n_ops = static_cast<int>(f.prog.size()); }
       else if (f.kind == TFELCU_FACTOR_TABLE) {   // evaluated on the device by a user functor (tfel_device.cuh)
@@ -996,15 +1064,18 @@ public:
   typename trial_fes_t::element solve(const linear_form<test_fes_t>& form, solver::basic_solver& s, dictionary* report = nullptr) const {
     std::size_t n_row(0), n_col(0);
     tfel_cuda::ck(tfelcu_matrix_info(h, &n_row, &n_col, nullptr));
-    array<double> x{n_col};
     dictionary local;
     dictionary& rep(report ? *report : local);
     solver::cuda::krylov* device_solver(dynamic_cast<solver::cuda::krylov*>(&s));
-    if (device_solver) {   // everything stays on the device
+    if (device_solver) {   // everything stays on the device, the solution included
       tfelcu_solver_report r;
-      tfel_cuda::ck(tfelcu_matrix_solve(h, form.handle(), device_solver->handle(), x.get_data(), &r));
+      std::shared_ptr<tfel_cuda::device_array> xd(std::make_shared<tfel_cuda::device_array>(n_col));
+      tfel_cuda::ck(tfelcu_matrix_solve(h, form.handle(), device_solver->handle(), xd->p, &r));
       solver::cuda::krylov::fill(rep, r);
-    } else {               // any other plugin: the reference's host protocol
+      return typename trial_fes_t::element(*trial_fes, tfel_cuda::coefficients(xd));
+    }
+    array<double> x{n_col};
+    {                      // any other plugin: the reference's host protocol
       array<double> f{n_row};
       tfel_cuda::ck(tfelcu_matrix_make_rhs(h, form.handle(), f.get_data()));
       sparse_matrix m(get_matrix(true));

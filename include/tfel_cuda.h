@@ -268,6 +268,16 @@ int tfelcu_integrate(tfelcu_ctx* ctx, tfelcu_mesh* mesh, int quad, const tfelcu_
 int tfelcu_quadrature_size(int quad, int* n_points, int* dim);
 int tfelcu_mesh_quadrature_points(tfelcu_mesh* mesh, int quad, double* xq);
 
+/* ---- plain device arrays ------------------------------------------------------------------------
+ * Coefficient vectors of discrete functions (finite_element_space::element, fes.hpp:219-364) that stay on the device
+ * between a solve, the algebra on elements (fes.hpp:314-405) and the next += that uses them as coefficient fields.
+ * _copy takes host or device pointers on either side; _lincomb computes out = a x + b y (y may be NULL: out = a x) on
+ * device arrays, out may alias x or y. */
+int tfelcu_array_create(tfelcu_ctx* ctx, size_t n, double** out);
+int tfelcu_array_destroy(tfelcu_ctx* ctx, double* p);
+int tfelcu_array_copy(tfelcu_ctx* ctx, double* dst, const double* src, size_t n);
+int tfelcu_array_lincomb(tfelcu_ctx* ctx, size_t n, double a, const double* x, double b, const double* y, double* out);
+
 /* ---- solver plugin: solver::basic_solver, src/core/solver.hpp:29-40 ---------------------------- */
 
 int tfelcu_solver_create(tfelcu_ctx* ctx, const tfelcu_solver_params* params, tfelcu_solver** s);

@@ -17,7 +17,7 @@ def build():
 
 def test_reference_programs_compile_against_the_cuda_headers():
     build()
-    for name in ("poisson", "stokes_2d_p2_p1", "navier_stokes_2d_p2_p1", "plugin_and_forms", "expression_algebra", "device_functor", "poisson_device",
+    for name in ("poisson", "stokes_2d_p2_p1", "navier_stokes_2d_p2_p1", "plugin_and_forms", "expression_algebra", "device_functor", "poisson_device", "projectors",
                  "export_ensight", "export_format_host", "laplacian_transient"):
         assert os.path.exists(os.path.join(BIN, name))
 
@@ -213,3 +213,55 @@ def test_reference_transient_laplacian_program(tmp_path):
     assert "number of steps: 11" in case and "scalar per node: 1 c" in case
     assert os.path.exists(os.path.join(str(tmp_path), "solution.var.c.000010"))
     assert os.path.exists(os.path.join(str(tmp_path), "initial_condition.var.c_init"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [16, 40])
+def test_projectors_and_element_algebra_against_the_oracle(tmp_path, n):
+    """projector::lagrange / projector::l2 (projector.hpp:12-97) and the element algebra (fes.hpp:314-405) of
+    examples/projectors.cpp against the oracle: nodal values at the oracle's dof coordinates (exact), mass-matrix solves
+    of the oracle's own M and rhs (direct solve, 1e-6: the projector stops CG at rtol 1e-8), linear combinations to
+    rounding; the program itself checks that the coefficients never left the device on the solve -> algebra -> +=
+    -> solve chain."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    import oracle as orc
+    build()
+    r = subprocess.run([os.path.join(BIN, "projectors"), str(n)], capture_output=True, text=True, cwd=str(tmp_path), timeout=300)
+    assert r.returncode == 0 and "projectors: ok" in r.stdout, r.stdout + r.stderr
+    assert r.stdout.count("coefficient transfers on the device chain: 0") == 2
+    data = np.fromfile(os.path.join(str(tmp_path), "projectors.bin"))
+    vertices, cells = orc.gen_square_mesh(1.0, 1.0, n, n)
+    quad = "qf5pT"
+    xq = orc.quadrature_points(vertices, cells, quad)
+    wave = lambda x: np.sin(3.0 * x[..., 0]) * np.cos(2.0 * x[..., 1]) + 0.25
+    bump = lambda x: x[..., 0] * (1.0 - x[..., 0]) * x[..., 1] + 0.5 * x[..., 1] * x[..., 1]
+    at = 0
+    for fe_name in ("p1", "p2"):
+        fe = orc.FE_BY_NAME[fe_name]
+        dof_map, N, g2l = orc.fes_build(2, fe, cells)
+        got = [data[at + i * N: at + (i + 1) * N] for i in range(7)]
+        at += 7 * N
+        a, b, pa, pb, w, pw, mix = got
+        x = orc.dof_coordinates(2, fe, vertices, cells, g2l, np.arange(N, dtype=np.uint32))
+        assert np.array_equal(a, wave(x)) and np.array_equal(b, bump(x))
+        space = orc.Space(2, [(fe, dof_map, N)])
+        rowptr, colind = orc.pattern(cells.shape[0], space, space, None)
+        val = orc.assemble_bilinear(vertices, cells, space, space, quad, [dict(test=(0, 0), trial=(0, 0), c=1.0)], None, False, rowptr, colind)
+        M = sp.csr_matrix((val, colind, rowptr)).tocsc()
+        lu = spl.splu(M)
+
+        def l2(table):
+            return lu.solve(orc.assemble_linear(vertices, cells, space, quad, [dict(test=(0, 0), c=1.0, table=table)], False))
+
+        def close(u, v, tol):
+            return np.abs(u - v).max() <= tol * np.abs(v).max()
+        assert close(pa, l2(wave(xq)), 1e-6)
+        assert close(pb, l2(bump(xq)), 1e-6)
+        assert close(w, 2.0 * pa - pb / 3.0 + pa, 1e-14)
+        assert close(mix, 0.5 * a + b * 3.0 - a / 4.0, 1e-14)
+        # the next form takes w and d_x pb as coefficient fields (device arrays of the elements above)
+        table = (orc.field_at_quadrature(fe, vertices, cells, dof_map, w, 0, quad) +
+                 orc.field_at_quadrature(fe, vertices, cells, dof_map, pb, 1, quad))
+        assert close(pw, l2(table), 1e-6)
+    assert at == data.shape[0]

@@ -95,6 +95,7 @@ SYMBOLS = [
     "tfelcu_solver_set_operator_csr", "tfelcu_solver_solve", "tfelcu_matrix_solve", "tfelcu_matrix_make_rhs",
     "tfelcu_solver_gather", "tfelcu_solver_spmv", "tfelcu_solver_spmv_bench",
     "tfelcu_solver_ilu_info", "tfelcu_solver_ilu_download",
+    "tfelcu_array_create", "tfelcu_array_destroy", "tfelcu_array_copy", "tfelcu_array_lincomb",
 ]
 
 _lib = None

@@ -769,6 +769,56 @@ int tfelcu_mesh_quadrature_points(tfelcu_mesh* mesh, int quad, double* xq) {
   });
 }
 
+// ---- plain device arrays: coefficient vectors of discrete functions that stay on the device -------------------------
+namespace {
+__global__ void k_lincomb(size_t n, double a, const double* __restrict__ x, double b, const double* __restrict__ y, double* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = y ? a * x[i] + b * y[i] : a * x[i];
+}
+}  // namespace
+
+int tfelcu_array_create(tfelcu_ctx* ctx, size_t n, double** out) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx && out, "null pointer");
+    use_device(ctx);
+    double* p = nullptr;
+    TFELCU_CK(cudaMalloc(&p, (n ? n : 1) * sizeof(double)));
+    TFELCU_CK(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(double), ctx->stream));
+    *out = p;
+  });
+}
+
+int tfelcu_array_destroy(tfelcu_ctx* ctx, double* p) {
+  return guarded([&] {
+    if (!ctx || !p) return;
+    use_device(ctx); ctx->sync();
+    cudaFree(p);
+  });
+}
+
+int tfelcu_array_copy(tfelcu_ctx* ctx, double* dst, const double* src, size_t n) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx && (dst || !n) && (src || !n), "null pointer");
+    use_device(ctx);
+    if (!n) return;
+    TFELCU_CK(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    ctx->sync();
+  });
+}
+
+int tfelcu_array_lincomb(tfelcu_ctx* ctx, size_t n, double a, const double* x, double b, const double* y, double* out) {
+  return guarded([&] {
+    TFELCU_REQUIRE(ctx && x && out, "null pointer");
+    use_device(ctx);
+    if (!n) return;
+    TFELCU_REQUIRE(tfelcu::is_device_pointer(x) && tfelcu::is_device_pointer(out) && (!y || tfelcu::is_device_pointer(y)),
+                   "array arithmetic works on device arrays");
+    size_t g = (n + 255) / 256; if (g > (size_t)ctx->sm_count * 8) g = (size_t)ctx->sm_count * 8;
+    k_lincomb<<<(unsigned)g, 256, 0, ctx->stream>>>(n, a, x, b, y, out);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+  });
+}
+
 // ---- solver --------------------------------------------------------------------------------------
 
 int tfelcu_solver_create(tfelcu_ctx* ctx, const tfelcu_solver_params* params, tfelcu_solver** s) {
