@@ -1,8 +1,9 @@
 // Coefficient functions as __device__ functors (include/tfel/tfel_device.cuh): the general Poisson problem of the parity
 // tests (-lap u + c(x) u = f(x), u = g on the boundary; source of examples/poisson.cpp:4-14 of the reference) assembled
 // three times -- with host callbacks (tabulated on the host, the fallback that reports itself), with device functors
-// tabulated on the device (device_expr) and with device functors called by the assembly kernels themselves (dev(f): the
-// functor is device code of THIS translation unit, nothing is evaluated on the host) -- and compared.
+// tabulated on the device up front (device_expr) and with device functors evaluated when the form is assembled (dev(f):
+// a kernel of THIS translation unit launched by the library on its stream, nothing is evaluated on the host) -- and
+// compared.
 #include <tfel/tfel.hpp>
 #include <tfel/tfel_device.cuh>
 

@@ -1,7 +1,7 @@
 // examples/poisson.cpp of the reference (its source term f is the Gaussian of examples/poisson.cpp:4-14) with the source
-// as DEVICE code: the same program, compiled by nvcc, `f` a __device__ functor instead of a host function pointer. The
-// assembly kernels call it at the quadrature points of every cell (tfel_device.cuh: dev(f)); nothing of the integrand is
-// evaluated on the host, at any mesh size.
+// as DEVICE code: the same program, compiled by nvcc, `f` a __device__ functor instead of a host function pointer. A
+// kernel of this translation unit evaluates it at the quadrature points of every cell when b += ... runs
+// (tfel_device.cuh: dev(f)); nothing of the integrand is evaluated on the host, at any mesh size.
 //   poisson_device [n] [linear_form.bin] [solution.bin]
 #include <tfel/tfel.hpp>
 #include <tfel/tfel_device.cuh>

@@ -580,7 +580,7 @@ struct factor_desc {
   coefficients data;                                 // FIELD coefficients (device resident)
   std::function<double(const double*)> fn;           // host callback (free_function / std_function)
   std::vector<tfelcu_op> prog;                       // PROGRAM
-  const void* device_fn = nullptr;                   // FUNCTION: device code instantiated in the user's nvcc translation unit
+  tfelcu_tabulate_fn device_fn = nullptr;            // FUNCTION: launcher of the kernel instantiated in the user's nvcc TU
   std::shared_ptr<void> device_closure;              // FUNCTION: the functor object in device memory (tfel_device.cuh)
 };
 

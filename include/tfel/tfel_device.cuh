@@ -6,12 +6,15 @@
 //   struct gaussian { double sigma; __device__ double operator()(const double* x) const { ... } };
 //   b += integrate<quad_type>(dev(gaussian{0.1}) * v, m);
 //
-// dev(f) instantiates the functor as DEVICE CODE in the user's translation unit -- a __device__ trampoline
-// double (const void* closure, const double* x) whose address crosses the C ABI (TFELCU_FACTOR_FUNCTION) together with a
-// device copy of the functor object -- and the assembly kernels of libtfel_cuda call it at the quadrature points of every
-// cell, inside the element loop, exactly where the reference evaluates its free_function leaves (expression.hpp:46-48):
-// no table, no host evaluation, no host <-> device copy. TFEL_DEVICE_FUNCTION(name) wraps a plain
+// dev(f) instantiates the functor as DEVICE CODE in the user's translation unit: a kernel k_functor_at_quadrature<F, dim>
+// that evaluates f at the quadrature points of every cell, and a host launcher for it whose address crosses the C ABI
+// (TFELCU_FACTOR_FUNCTION, tfelcu_tabulate_fn) together with a device copy of the functor object. The library calls the
+// launcher on its own stream when the form is assembled, exactly where the reference evaluates its free_function
+// leaves (expression.hpp:46-48): no host evaluation, no host <-> device copy. TFEL_DEVICE_FUNCTION(name) wraps a plain
 // __device__ double name(const double*) the same way.
+// (Why a kernel of the user's module and not a __device__ function pointer called by the library's element kernels:
+// without relocatable device code a function "address" on sm_100a is a module-local handle -- CALL.REL -- and the call
+// faults with "invalid program counter"; with -rdc the element kernels go from 30-64 to 90-200 registers.)
 // device_expr<quad>(f, mesh) is the older variant: it evaluates the functor at every quadrature point into a
 // device-resident table first (TFELCU_FACTOR_TABLE).
 // Include after <tfel/tfel.hpp>; compile with nvcc.
@@ -34,26 +37,38 @@ inline void cuda_ck(cudaError_t e) {
   if (e != cudaSuccess) throw std::string("tfel_device: ") + cudaGetErrorString(e);
 }
 
-// the device code the library calls: one instance per functor type, in the user's translation unit
-template <typename F>
-__device__ double functor_trampoline(const void* closure, const double* x) { return (*static_cast<const F*>(closure))(x); }
+// the device code the library launches: one instance per functor type and dimension, in the user's translation unit
+template <typename F, int DIM>
+__global__ void k_functor_at_quadrature(const F* __restrict__ f, tfelcu_points w, double* __restrict__ out) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= w.n_cells * (size_t)w.nq) return;
+  const size_t k = i / w.nq;
+  const int q = (int)(i - k * w.nq);
+  const uint32_t* c = w.cells + k * (DIM + 1);
+  double v0[DIM], x[DIM];
+#pragma unroll
+  for (int r = 0; r < DIM; ++r) x[r] = v0[r] = w.vertices[(size_t)c[0] * DIM + r];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    const double t = w.xhat[q * DIM + d];
+#pragma unroll
+    for (int r = 0; r < DIM; ++r) x[r] += t * (w.vertices[(size_t)c[d + 1] * DIM + r] - v0[r]);
+  }
+  out[i] = (*f)(x);
+}
 
 template <typename F>
-__global__ void k_trampoline_address(const void** out) { *out = reinterpret_cast<const void*>(&functor_trampoline<F>); }
-
-template <typename F>
-const void* trampoline_address() {
-  static const void* address(nullptr);   // one query per functor type and process
-  if (address) return address;
-  const void** d(nullptr);
-  cuda_ck(cudaMalloc(&d, sizeof(void*)));
-  cudaStream_t stream(static_cast<cudaStream_t>(tfelcu_ctx_stream(context())));
-  k_trampoline_address<F><<<1, 1, 0, stream>>>(d);
-  cuda_ck(cudaGetLastError());
-  cuda_ck(cudaMemcpyAsync(&address, d, sizeof(void*), cudaMemcpyDeviceToHost, stream));
-  cuda_ck(cudaStreamSynchronize(stream));
-  cudaFree(d);
-  return address;
+int launch_functor(const void* closure, const tfelcu_points* w, double* out, void* stream) {
+  const size_t n = w->n_cells * (size_t)w->nq;
+  if (n == 0) return 0;
+  const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const F* f = static_cast<const F*>(closure);
+  if (w->dim == 2) k_functor_at_quadrature<F, 2><<<grid, 256, 0, s>>>(f, *w, out);
+  else if (w->dim == 3) k_functor_at_quadrature<F, 3><<<grid, 256, 0, s>>>(f, *w, out);
+  else if (w->dim == 1) k_functor_at_quadrature<F, 1><<<grid, 256, 0, s>>>(f, *w, out);
+  else return 1;
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 }  // namespace tfel_cuda
@@ -70,7 +85,7 @@ expression<false> dev(const F& f) {
   tfel_cuda::cuda_ck(cudaStreamSynchronize(stream));
   expression<false> e;
   tfel_cuda::factor_desc d;
-  d.kind = TFELCU_FACTOR_FUNCTION; d.device_fn = tfel_cuda::trampoline_address<F>(); d.device_closure = owner;
+  d.kind = TFELCU_FACTOR_FUNCTION; d.device_fn = &tfel_cuda::launch_functor<F>; d.device_closure = owner;
   e.factors.push_back(d);
   tfel_cuda::monomial mono; mono.factors.push_back(0); e.terms.push_back(mono);
   return e;

@@ -48,10 +48,12 @@ enum {
   TFELCU_FACTOR_TABLE = 2,    /* free_function / std_function tabulated at the quadrature points
                                  (expression.hpp:31-87): double[K][nq], host or device */
   TFELCU_FACTOR_PROGRAM = 3,  /* function of x evaluated on device (postfix program) */
-  TFELCU_FACTOR_FUNCTION = 4  /* function of x as DEVICE CODE of the caller: a __device__ function
-                                 double fn(const void* closure, const double* x) compiled by nvcc in the user's translation unit
-                                 (include/tfel/tfel_device.cuh instantiates it from any functor type) and called by the
-                                 assembly kernels at every quadrature point -- no table, no host evaluation */
+  TFELCU_FACTOR_FUNCTION = 4  /* function of x as DEVICE CODE of the caller: a kernel of the caller's own module (nvcc, user's
+                                 translation unit; include/tfel/tfel_device.cuh instantiates it from any functor type), which
+                                 the library launches on its stream when the form is assembled -- see tfelcu_tabulate_fn.
+                                 No host evaluation, no host <-> device copy. (Device function pointers do not cross
+                                 CUDA modules on sm_100a without relocatable device code, and -rdc costs the element kernels
+                                 their register allocation: DESIGN.md section 5.) */
 };
 
 /* postfix opcodes of TFELCU_FACTOR_PROGRAM */
@@ -63,6 +65,22 @@ enum {
 
 typedef struct { int32_t op; int32_t pad; double imm; } tfelcu_op;
 
+/* Where a FUNCTION factor is evaluated: the quadrature points of every cell,
+ * x_q = v_0 + sum_d xhat[q][d] (v_{d+1} - v_0) with v_j = vertices[cells[k][j]] (cell.hpp:456-468). All pointers are
+ * device memory. */
+typedef struct {
+  int32_t dim, nq;
+  size_t n_cells;
+  const double* vertices;      /* [V][dim] */
+  const uint32_t* cells;       /* [K][dim + 1] */
+  const double* xhat;          /* [nq][dim] reference coordinates of the quadrature nodes */
+} tfelcu_points;
+
+/* The caller's launcher of a FUNCTION factor: enqueue on `stream` (a cudaStream_t) device work that writes
+ * out[k * nq + q] = f(x_q of cell k) for every cell; return 0, or nonzero when the launch failed. Called on the host,
+ * once per += that uses the factor; it must not synchronise. */
+typedef int (*tfelcu_tabulate_fn)(const void* closure, const tfelcu_points* where, double* out, void* stream);
+
 typedef struct {
   int32_t kind;               /* TFELCU_FACTOR_* */
   int32_t d;                  /* FIELD: 0 = value, k = derivative along x_k (d<k>(), expression.hpp:369-373) */
@@ -71,7 +89,7 @@ typedef struct {
   const tfelcu_op* ops;       /* PROGRAM: host array */
   int32_t n_ops;
   int32_t pad;
-  const void* fn;             /* FUNCTION: device address of double (*)(const void* closure, const double* x) */
+  tfelcu_tabulate_fn fn;      /* FUNCTION: launcher of the caller's tabulation kernel */
   const void* closure;        /* FUNCTION: device memory handed to fn (the functor object), may be NULL */
 } tfelcu_factor;
 

@@ -182,7 +182,7 @@ def test_device_functor_coefficients():
 
 @pytest.mark.gpu
 def test_poisson_with_a_device_source_makes_no_host_callbacks(tmp_path):
-    """examples/poisson.cpp's Gaussian source as a __device__ functor called by the assembly kernels themselves
+    """examples/poisson.cpp's Gaussian source as a __device__ functor evaluated by a kernel of the user's module at += time
     (TFELCU_FACTOR_FUNCTION): zero host evaluations of integrand leaves, and the linear form equals the oracle's with the
     same source tabulated by numpy (1e-12)."""
     import numpy as np

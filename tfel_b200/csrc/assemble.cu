@@ -344,9 +344,21 @@ void build_form(Ctx* ctx, tfelcu_mesh* mesh, int quad, const tfelcu_factor* fact
       TFELCU_REQUIRE(depth == 1, "malformed coefficient program");
       prog_at += s.n_ops;
     } else if (s.kind == TFELCU_FACTOR_FUNCTION) {
+      // device code of the caller: its module tabulates the function at the quadrature points of every cell, on our
+      // stream, into a table the element kernels read (nothing is evaluated or copied on the host)
       TFELCU_REQUIRE(s.fn != nullptr, "function factor without device code");
       TFELCU_REQUIRE(s.closure == nullptr || is_device_pointer(s.closure), "the closure of a function factor must live in device memory");
-      d.fn = s.fn; d.closure = s.closure;
+      const size_t n = mesh->K * (size_t)Q.nq;
+      out.keep.emplace_back(Q.x.size());
+      double* xhat = out.keep.back().p;
+      ctx->upload(xhat, Q.x.data(), Q.x.size());
+      out.keep.emplace_back(n);
+      tfelcu_points where;
+      where.dim = dim; where.nq = Q.nq; where.n_cells = mesh->K;
+      where.vertices = mesh->vertices.p; where.cells = mesh->cells.p; where.xhat = xhat;
+      const int rc = s.fn(s.closure, &where, out.keep.back().p, (void*)ctx->stream);
+      TFELCU_REQUIRE(rc == 0, "the tabulation kernel of a function factor could not be launched");
+      d.kind = TFELCU_FACTOR_TABLE; d.data = out.keep.back().p;
     } else {
       fail("unknown coefficient factor kind");
     }

@@ -20,8 +20,6 @@ struct DevFactor {
   const uint32_t* dof_map;   // FIELD
   const double* data;        // FIELD: coefficients; TABLE: [K][nq]
   int prog_off, prog_len;    // PROGRAM
-  const void* fn;            // FUNCTION: device code of the caller, double (*)(const void* closure, const double* x)
-  const void* closure;
 };
 
 struct DevTerm {
@@ -99,7 +97,7 @@ __device__ __forceinline__ void eval_factors(const FormDev& F, const double* sm,
         }
         v += c * b;
       }
-    } else if (fa.kind == TFELCU_FACTOR_PROGRAM || fa.kind == TFELCU_FACTOR_FUNCTION) {
+    } else if (fa.kind == TFELCU_FACTOR_PROGRAM) {
       // x_q = v0 + J xhat_q (cell.hpp:456-468)
       const double* xh = sm + F.off_xhat + q * DIM;
       double x[DIM];
@@ -110,8 +108,7 @@ __device__ __forceinline__ void eval_factors(const FormDev& F, const double* sm,
         for (int c = 0; c < DIM; ++c) acc += xh[c] * g.J[r][c];
         x[r] = acc;
       }
-      if (fa.kind == TFELCU_FACTOR_PROGRAM) v = run_program<DIM>(F, fa.prog_off, fa.prog_len, x);
-      else v = reinterpret_cast<double (*)(const void*, const double*)>(const_cast<void*>(fa.fn))(fa.closure, x);
+      v = run_program<DIM>(F, fa.prog_off, fa.prog_len, x);
     }
     fv[f] = v;
   }
