@@ -55,25 +55,30 @@ template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  size_t front = 0;   // elements in front of p (p[-front .. -1]): the lower halo of a distributed vector
   DevBuf() = default;
   explicit DevBuf(size_t count) { alloc(count); }
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), front(o.front) { o.p = nullptr; o.n = 0; o.front = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept {
-    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    if (this != &o) { release(); p = o.p; n = o.n; front = o.front; o.p = nullptr; o.n = 0; o.front = 0; }
     return *this;
   }
   ~DevBuf() { release(); }
-  void alloc(size_t count) {
+  void alloc(size_t count, size_t in_front = 0) {
     release();
-    n = count;
+    n = count; front = in_front;
     // +8 elements of slack: bulk copies in the SpMV kernel read whole 16-byte chunks of 2-, 4- and 8-byte entries
-    if (count) TFELCU_CK(cudaMalloc(&p, (count + 8) * sizeof(T)));
+    if (count + in_front) {
+      T* raw = nullptr;
+      TFELCU_CK(cudaMalloc(&raw, (in_front + count + 8) * sizeof(T)));
+      p = raw + in_front;
+    }
   }
   void release() {
-    if (p) cudaFree(p);
-    p = nullptr; n = 0;
+    if (p) cudaFree(p - front);
+    p = nullptr; n = 0; front = 0;
   }
   size_t bytes() const { return n * sizeof(T); }
 };

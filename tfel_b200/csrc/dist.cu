@@ -37,7 +37,8 @@ __global__ void k_halo_keys(const int32_t* __restrict__ colind, size_t nnz, Rang
 }
 
 __global__ void k_localize_columns(const int32_t* __restrict__ colind, size_t nnz, RowMap R, const uint64_t* __restrict__ keys,
-                                   const uint64_t* __restrict__ halo, size_t n_halo, size_t halo_base, int32_t* __restrict__ out) {
+                                   const uint64_t* __restrict__ halo, size_t n_halo, size_t halo_base, size_t n_front,
+                                   size_t front_pad, int32_t* __restrict__ out) {
   const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (e >= nnz) return;
   const uint64_t key = keys[e];
@@ -47,7 +48,7 @@ __global__ void k_localize_columns(const int32_t* __restrict__ colind, size_t nn
     const size_t mid = lo + (hi - lo) / 2;
     if (halo[mid] < key) lo = mid + 1; else hi = mid;
   }
-  out[e] = (int32_t)(halo_base + lo);
+  out[e] = lo < n_front ? (int32_t)((long long)lo - (long long)front_pad) : (int32_t)(halo_base + (lo - n_front));
 }
 
 __global__ void k_lower_bounds_u64(const uint64_t* __restrict__ sorted, size_t n, int n_targets, unsigned long long* __restrict__ out) {
@@ -100,7 +101,7 @@ __global__ void k_p2p_allreduce(ReduceArgs A, int k, Peers peers, int me, int P,
 // CTA q: my boundary values -> landing zone of rank q; values of rank q -> halo entries of v (words that carry their own
 // sequence number: p2p.cuh)
 __global__ void __launch_bounds__(256)
-k_p2p_halo(double* __restrict__ v, size_t halo_base, const uint32_t* __restrict__ send_idx, HaloArgs H, Peers peers,
+k_p2p_halo(double* __restrict__ v, const uint32_t* __restrict__ send_idx, HaloArgs H, Peers peers,
            int me, unsigned long long* __restrict__ seq_dev, KrylovScalars* __restrict__ S, int do_send, int do_recv,
            int* __restrict__ err) {
   if (S && S->done) return;
@@ -127,7 +128,7 @@ k_p2p_halo(double* __restrict__ v, size_t halo_base, const uint32_t* __restrict_
   if (rc && do_recv) {
     const int par = (int)(seq_r & 1ull);
     const unsigned long long* src = peers.a[me]->halo[par] + 2 * H.recv_off[q];
-    double* dst = v + halo_base + H.recv_off[q];
+    double* dst = v + H.recv_pos[q];
     bool ok = true;
     for (size_t i0 = threadIdx.x; i0 < rc; i0 += (size_t)8 * blockDim.x) {
       const size_t left = (rc - i0 + blockDim.x - 1) / blockDim.x;
@@ -283,20 +284,30 @@ void dist_setup(tfelcu_solver* s) {
   // the halo entries of a vector start on a 128-byte line of their own: the product reads them through the read-only
   // path after another CTA of the same launch has written them, which is only safe for lines no earlier read of the launch
   // (of owned entries) can have brought into an L1
-  D.halo_base = (n_local + 15) & ~(size_t)15;
-  D.n_halo = (D.halo_base - n_local) + n_halo;      // what a vector holds behind its owned entries: padding + halo
-  TFELCU_REQUIRE(D.halo_base + n_halo < 0x7fffffffull, "too many local columns");
-  D.colind_local.alloc(nnz);
-  if (nnz) {
-    k_localize_columns<<<grid_for(nnz, 256), 256, 0, ctx->stream>>>(s->colind, nnz, R, keys.p, halo.p, n_halo, D.halo_base, D.colind_local.p);
-    ctx->count(); TFELCU_LAUNCH_CHECK();
-  }
   DevBuf<unsigned long long> bounds((size_t)P + 1);
   k_lower_bounds_u64<<<1, 32, 0, ctx->stream>>>(halo.p, n_halo, P, bounds.p);
   ctx->count(); TFELCU_LAUNCH_CHECK();
   std::vector<unsigned long long> h_bounds((size_t)P + 1);
   ctx->download(h_bounds.data(), bounds.p, (size_t)P + 1);
   D.recv_off.assign(h_bounds.begin(), h_bounds.end());
+  // what the lower ranks own goes in front of the owned entries, the rest behind them: with the rows of the ranks in
+  // ascending order (the usual block partition) every halo column then lies within a few thousand entries of the rows
+  // that use it, and the product keeps its 16-bit column deltas on every rank
+  D.n_front = (size_t)D.recv_off[me];
+  D.front_pad = (D.n_front + 15) & ~(size_t)15;
+  D.halo_base = (n_local + 15) & ~(size_t)15;
+  D.n_halo = (D.halo_base - n_local) + (n_halo - D.n_front);   // what a vector holds behind its owned entries: padding + halo
+  TFELCU_REQUIRE(D.halo_base + n_halo < 0x7fffffffull, "too many local columns");
+  D.recv_pos.assign((size_t)P, 0);
+  for (int q = 0; q < P; ++q)
+    D.recv_pos[q] = q < me ? (long long)D.recv_off[q] - (long long)D.front_pad
+                           : (long long)D.halo_base + (long long)(D.recv_off[q] - D.n_front);
+  D.colind_local.alloc(nnz);
+  if (nnz) {
+    k_localize_columns<<<grid_for(nnz, 256), 256, 0, ctx->stream>>>(s->colind, nnz, R, keys.p, halo.p, n_halo, D.halo_base, D.n_front,
+                                                                    D.front_pad, D.colind_local.p);
+    ctx->count(); TFELCU_LAUNCH_CHECK();
+  }
   // 3. what every rank receives from every rank
   DevBuf<unsigned long long> cnt_mine(P), cnt_all((size_t)P * P);
   std::vector<unsigned long long> h_cnt(P);
@@ -368,8 +379,9 @@ void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S, cud
   if (D.p2p_halo) {
     HaloArgs H;
     for (int q = 0; q <= P; ++q) { H.send_off[q] = D.send_off[q]; H.recv_off[q] = D.recv_off[q]; }
+    for (int q = 0; q < P; ++q) H.recv_pos[q] = D.recv_pos[q];
     for (int q = 0; q < P; ++q) H.land_off[q] = D.land_off[q];
-    k_p2p_halo<<<P, 256, 0, stream>>>(v, D.halo_base, D.send_idx.p, H, peers_of(ctx), me, ctx->seq_dev,
+    k_p2p_halo<<<P, 256, 0, stream>>>(v, D.send_idx.p, H, peers_of(ctx), me, ctx->seq_dev,
                                      const_cast<KrylovScalars*>(S), mode & 1, (mode >> 1) & 1, ctx->p2p_err);
     ctx->count(); TFELCU_LAUNCH_CHECK();
     return;
@@ -384,7 +396,7 @@ void dist_halo_exchange(tfelcu_solver* s, double* v, const KrylovScalars* S, cud
     if (q == me) continue;
     const size_t rc = D.recv_off[q + 1] - D.recv_off[q], sc = D.send_off[q + 1] - D.send_off[q];
     if (sc) TFELCU_NCCL(ncclSend(D.send_buf.p + D.send_off[q], sc, ncclDouble, q, ctx->comm, stream));
-    if (rc) TFELCU_NCCL(ncclRecv(v + D.halo_base + D.recv_off[q], rc, ncclDouble, q, ctx->comm, stream));
+    if (rc) TFELCU_NCCL(ncclRecv(v + D.recv_pos[q], rc, ncclDouble, q, ctx->comm, stream));
   }
   TFELCU_NCCL(ncclGroupEnd());
 }

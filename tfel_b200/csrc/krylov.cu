@@ -291,7 +291,7 @@ static std::vector<LevelRun> plan_runs(const std::vector<int32_t>& level_ptr) {
 // diagonal block of a row-distributed operator: entries whose (local) column is an owned row
 __global__ void k_owned_flag(const int32_t* __restrict__ colind, size_t nnz, int32_t n, uint32_t* __restrict__ keep) {
   const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (e < nnz) keep[e] = colind[e] < n ? 1u : 0u;
+  if (e < nnz) keep[e] = (colind[e] >= 0 && colind[e] < n) ? 1u : 0u;   // halo columns: negative (lower ranks) or >= n
 }
 
 __global__ void k_block_rowptr(const int32_t* __restrict__ rowptr, const uint32_t* __restrict__ pos, size_t n, size_t nnz,
@@ -642,6 +642,7 @@ void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep) {
   const bool dist = (bool)s->dist;
   const size_t n = s->n;
   const size_t n_halo = dist ? s->dist->n_halo : 0;
+  const size_t front = dist ? s->dist->front_pad : 0;    // every basis vector has its lower halo in front of it
   const int vg = vgrid(s);
   const uint64_t launches0 = ctx->launches;
   uint64_t n_spmv = 0;
@@ -652,7 +653,7 @@ void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep) {
   if (m < 1) m = 1;
   size_t free_b = 0, total_b = 0;
   TFELCU_CK(cudaMemGetInfo(&free_b, &total_b));
-  const size_t ld = (n + n_halo + 3) & ~(size_t)3;
+  const size_t ld = (front + n + n_halo + 15) & ~(size_t)15;
   if (!s->basis.n || s->basis.n < (size_t)(m + 1) * ld) {
     const size_t have = s->basis.bytes();
     long long fit = (long long)((free_b + have) * 0.8 / (8.0 * (double)(ld ? ld : 1))) - 1;
@@ -665,7 +666,7 @@ void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep) {
     if (m > fit) m = fit;
     TFELCU_REQUIRE(m >= 1, "GMRES: not enough device memory for a Krylov basis");
     s->basis.release();
-    s->basis.alloc((size_t)(m + 1) * ld);
+    s->basis.alloc((size_t)(m + 1) * ld, front);
     s->gmres_m = (int)m;
   } else if (s->gmres_m > 0 && m > s->gmres_m) m = s->gmres_m;
   const int M = (int)m;
@@ -699,7 +700,7 @@ void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep) {
     spmv_launch(s, v_in, out, nullptr, nullptr); ++n_spmv;
   };
 
-  ctx->zero(s->x.p, n + n_halo);                             // x0 = 0 (solver.cpp:165-166)
+  ctx->zero(s->x.p - front, front + n + n_halo);             // x0 = 0 (solver.cpp:165-166)
   ctx->zero(s->scal.p, 1);
   precond(s, s->b.p, s->q.p);
   k_dot<<<vg, kVecT, 0, ctx->stream>>>(s->q.p, s->q.p, n, P[0]);

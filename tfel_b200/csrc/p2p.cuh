@@ -81,6 +81,7 @@ struct ReduceArgs { const double* p[4]; int n[4]; };
 
 struct HaloArgs {
   unsigned long long send_off[17], recv_off[17], land_off[16];
+  long long recv_pos[16];   // where the entries received from rank q start in a vector (negative: in front of the owned entries)
 };
 
 // device counters (Ctx::seq_dev, 64 entries): advanced by the kernels themselves so that the loop can live in a CUDA graph

@@ -324,15 +324,16 @@ void solver_setup(tfelcu_solver* s, bool structure) {
   TFELCU_CK(cudaEventCreate(&e0)); TFELCU_CK(cudaEventCreate(&e1)); TFELCU_CK(cudaEventCreate(&e2));
   TFELCU_CK(cudaEventRecord(e0, ctx->stream));
   const size_t n = s->n;
-  size_t n_halo = 0;
+  size_t n_halo = 0, front = 0;
   if (structure) {
     if (s->dist) {
       dist_setup(s);                       // needs the global column indices
       s->colind = s->dist->colind_local.p;
-      n_halo = s->dist->n_halo;
+      n_halo = s->dist->n_halo; front = s->dist->front_pad;
     }
-    s->x.alloc(n + n_halo); s->b.alloc(n); s->r.alloc(n); s->p.alloc(n + n_halo); s->q.alloc(n);
-    ctx->zero(s->x.p, n + n_halo); ctx->zero(s->p.p, n + n_halo);
+    // vectors the product reads carry the halo: [lower ranks' entries | owned (p points here) | pad, upper ranks' entries]
+    s->x.alloc(n + n_halo, front); s->b.alloc(n); s->r.alloc(n); s->p.alloc(n + n_halo, front); s->q.alloc(n);
+    ctx->zero(s->x.p - front, front + n + n_halo); ctx->zero(s->p.p - front, front + n + n_halo);
     s->scal.alloc(1);
     ctx->zero(s->scal.p, 1);
     spmv_plan(s);
@@ -479,10 +480,11 @@ void solve_cg_single_reduction(tfelcu_solver* s, tfelcu_solver_report* rep) {
   const double* dinv = pc == TFELCU_PC_JACOBI ? s->dinv.p : nullptr;
   const bool dist = (bool)s->dist;
   const size_t n_halo = dist ? s->dist->n_halo : 0;
-  if (s->z.n < n + n_halo) s->z.alloc(n + n_halo);
+  const size_t front = dist ? s->dist->front_pad : 0;
+  if (s->z.n < n + n_halo || s->z.front != front) s->z.alloc(n + n_halo, front);
   if (s->sdir.n < n) s->sdir.alloc(n);
   double* u = s->z.p; double* w = s->q.p; double* sd = s->sdir.p;
-  ctx->zero(u, n + n_halo);
+  ctx->zero(u - front, front + n + n_halo);
   double* P_d = s->partial.p;
   double* P_g = s->partial.p + s->n_partial;
   double* P_rr = s->partial.p + 2 * (size_t)s->n_partial;

@@ -90,7 +90,11 @@ struct DistPlan {
   std::vector<RowMap> all_rows;          // rows of every rank
   size_t n_halo = 0;                     // what a vector holds behind its owned entries: padding up to halo_base, then one
                                          // entry per column owned by another rank
-  size_t halo_base = 0;                  // index of the first halo entry (owned entries rounded up to a 128-byte line)
+  size_t halo_base = 0;                  // index of the first halo entry behind the owned ones (rounded up to a 128-byte line)
+  size_t n_front = 0, front_pad = 0;     // halo entries owned by lower ranks sit IN FRONT of the owned entries, at
+                                         // [-front_pad, -front_pad + n_front): their columns stay close to the rows that use
+                                         // them, so every rank keeps 16-bit column deltas (spmv.cu)
+  std::vector<long long> recv_pos;       // [n_ranks] where the entries received from rank q start in a vector
   DevBuf<int32_t> colind_local;          // column indices in [owned | halo] numbering
   DevBuf<uint32_t> send_idx;             // owned entries to send, grouped by destination rank
   DevBuf<double> send_buf;

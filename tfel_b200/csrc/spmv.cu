@@ -180,6 +180,10 @@ void spmv_plan(tfelcu_solver* s) {
 // TMA-streamed kernel
 // ------------------------------------------------------------------------------------------
 
+// "no entry" in the unrolled gather below; local column indices themselves may be negative (halo entries owned by lower
+// ranks sit in front of the owned part of a distributed vector, dist.cu)
+constexpr int kNoColumn = -2147483647 - 1;
+
 // COL_T = int32_t: column indices as stored; int16_t: column - row (solver-internal copy, built when every stored
 // entry of the operator lies within +-32767 of the diagonal -- 2 bytes less per entry to stream)
 template <int TILE_NNZ, int CONSUMERS, int STAGES, typename COL_T>
@@ -267,11 +271,11 @@ k_spmv_stream(const int32_t* __restrict__ rowptr, const COL_T* __restrict__ coli
         for (int u = 0; u < U; ++u) {
           const int eu = e + u * LANES;
           const bool ok = eu < re;
-          c[u] = ok ? (kDelta ? r + (int)cs[eu] : (int)cs[eu]) : -1;
+          c[u] = ok ? (kDelta ? r + (int)cs[eu] : (int)cs[eu]) : kNoColumn;
           v[u] = ok ? vs[eu] : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+        for (int u = 0; u < U; ++u) xv[u] = c[u] != kNoColumn ? __ldg(x + c[u]) : 0.0;
 #pragma unroll
         for (int u = 0; u < U; ++u) sum += v[u] * xv[u];
       }
@@ -436,7 +440,7 @@ __global__ void k_slab_is_boundary(const int4* __restrict__ desc, int n_blocks, 
   if (b >= n_blocks) return;
   const int4 d = desc[b];
   int any = 0;
-  for (int e = d.z + threadIdx.x; e < d.w; e += blockDim.x) any |= (colind[e] >= n_local) ? 1 : 0;
+  for (int e = d.z + threadIdx.x; e < d.w; e += blockDim.x) any |= (colind[e] < 0 || colind[e] >= n_local) ? 1 : 0;
   any = __syncthreads_or(any);
   if (threadIdx.x == 0) flag[b] = any;
 }
