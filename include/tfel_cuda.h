@@ -114,9 +114,10 @@ enum { TFELCU_PC_NONE = 0, TFELCU_PC_JACOBI = 1, TFELCU_PC_BLOCK_JACOBI = 2, TFE
  * PATCH: rows grouped into compact patches of the mesh (quadtree / octree leaves of the dof coordinates); one CTA
  * computes every element matrix of its patch once in shared memory, then each row gathers. AUTO (default): the
  * measured winner; TFELCU_SCATTER=rows|patch|colored|tile in the environment overrides AUTO.
- * TILE: cell-centric with graph colouring inside shared-memory tiles (vertex-based P1 spaces on triangles, constant
- * coefficients): every element matrix once, every value written once; a linear form on the same space that follows the
- * += rides along in the same pass. AUTO picks TILE where it applies, else ROW_GATHER. */
+ * TILE: cell-centric inside shared-memory tiles of the mesh (vertex-based P1 spaces on triangles, constant
+ * coefficients): every element matrix once, every value written once; explicit request only (measured slower than the
+ * rows). For the same class of forms AUTO takes the closed-form P1 row kernel (p1rows.cu); with
+ * either, a constant-coefficient linear form on the same space that follows the += is assembled in the same pass. */
 enum { TFELCU_SCATTER_ROW_GATHER = 0, TFELCU_SCATTER_COLORED = 1, TFELCU_SCATTER_PATCH = 2, TFELCU_SCATTER_AUTO = 3,
        TFELCU_SCATTER_TILE = 4 };
 enum { TFELCU_SPMV_AUTO = 0, TFELCU_SPMV_VECTOR = 1, TFELCU_SPMV_TMA_STREAM = 2 };

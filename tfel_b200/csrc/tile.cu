@@ -18,7 +18,7 @@
 // same space rides along as a fourth value per contribution (one pass over the mesh for A and b).
 // (A first version accumulated colour by colour -- Jones-Plassmann colours inside the tile, one CTA barrier per colour --
 // and was slower than the rows: 1700 instructions per warp and tile, a third of the stall samples on those barriers;
-// profiles/r02_ncu_tile_assembly.md.)
+// profiles/r02_ncu_p1rows_tile.md.)
 #include "p1form.cuh"
 #include "sortutil.cuh"
 
