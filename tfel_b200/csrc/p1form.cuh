@@ -18,6 +18,7 @@ struct P1Form {
   double mhat[3];       // sum_q w_q phi_i
   double Mhat[9];       // sum_q w_q phi_i phi_j
   double b_c[3];        // fused linear form: sum_t c_t mhat_i of ITS quadrature
+  int b_uniform;        // b_c[0] == b_c[1] == b_c[2] bit for bit (any symmetric formula): no select per cell
   // isotropic shape: C = c I (Laplacian-like) and, if there is a value x value term, a reference mass matrix with one
   // diagonal and one off-diagonal value (any symmetric quadrature formula): K_ij = (c W / 4|K|) e_i . e_j + c00 |K| M_ij
   // with e_i the edge opposite to vertex i -- no Jacobian inverse, nothing that depends on the local numbering
@@ -56,6 +57,7 @@ inline P1Form make_p1_form(const FormBuild& fb, const FormBuild* fbv) {
     for (int t = 0; t < G.n_terms; ++t) c += G.terms[t].c;
     for (int i = 0; i < 3; ++i) F.b_c[i] = c * fbv->tables[(size_t)G.off_ref + i];
   }
+  F.b_uniform = (F.b_c[0] == F.b_c[1] && F.b_c[1] == F.b_c[2]) ? 1 : 0;
   return F;
 }
 

@@ -13,6 +13,7 @@
 // Both can fuse the dot product x . (A x) of conjugate gradients (per-CTA partial sums, fixed order).
 //
 // Algorithmic bytes per product: 12 nnz + 4 (n + 1) + 8 n (x once) + 8 n (y).
+#include "tma.cuh"
 #include "solver.cuh"
 #include "sortutil.cuh"
 
@@ -21,42 +22,6 @@
 namespace tfelcu {
 
 constexpr int kTilePad = 16;            // slack for 16-byte aligned bulk copies (8 entries of 2 bytes on either side)
-
-// ------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + 1-D bulk copy global -> shared (SASS: UBLKCP / SYNCS)
-// ------------------------------------------------------------------------------------------
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 
 // ------------------------------------------------------------------------------------------
 // slabs: consecutive rows whose weight sum_r max(len_r, unit) stays below the tile capacity; with

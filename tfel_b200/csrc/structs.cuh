@@ -215,6 +215,11 @@ struct tfelcu_matrix {
   bool has_ell = false, ell_compact = false;   // compact: 8-byte records (vertex offsets from the row's own vertex)
   tfelcu::DevBuf<uint32_t> ell;         // uint4 records [ell_ptr[block] + k][128 rows of the block]
   tfelcu::DevBuf<unsigned int> ell_ptr, ell_deg;
+  bool ell_local = false;               // compact records hold indices into the block's own vertex table (p1rows.cu)
+  tfelcu::DevBuf<unsigned int> vt_ptr;  // [n_blocks + 1] start of a block's table in vt_list
+  tfelcu::DevBuf<uint32_t> vt_list;     // ascending vertex ids every record of the block refers to (padded to 4 entries)
+  tfelcu::DevBuf<int32_t> ell_desc;      // int4 per block for the streamed kernel
+  unsigned int ell_deg_max = 0, vt_max = 0;   // largest degree / table over the blocks (shared-memory sizes of the streamed kernel)
   ~tfelcu_matrix() {
     if (tile_plan) tfelcu::tile_plan_free(tile_plan);
     if (pending) tfelcu::form_build_free(pending);

@@ -19,6 +19,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--configs", nargs="*", default=["rows", "tile", "auto"])
 a = ap.parse_args()
 
+os.environ["TFELCU_NO_POOL"] = "1"   # every configuration builds its own structure
 torch.cuda.set_device(0)
 ctx = capi.Context(0)
 stream = torch.cuda.Stream()
@@ -30,7 +31,13 @@ STIFF = [dict(test=(0, 1), trial=(0, 1)), dict(test=(0, 2), trial=(0, 2))]
 SRC = [dict(test=(0, 0))]
 ref = None
 for cfg in a.configs:
-    parts = cfg.split(":")
+    for k in list(os.environ):
+        if k.startswith("TFELCU_P1_") or k in ("TFELCU_NO_VTAB", "TFELCU_P1STREAM"): os.environ.pop(k)
+    envs = cfg.split("+")[1:]            # auto+TFELCU_P1_MINB=9: environment knobs of one configuration
+    for kv in envs:
+        k, v = kv.split("=")
+        os.environ[k] = v
+    parts = cfg.split("+")[0].split(":")
     scatter = parts[0]
     os.environ.pop("TFELCU_PATCH_ROWS", None); os.environ.pop("TFELCU_PATCH_THREADS", None); os.environ.pop("TFELCU_NO_REC", None)
     if scatter == "rows-norec":   # owner-computes rows without the packed (cell | slots | local dof) records
