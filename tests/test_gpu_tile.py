@@ -28,15 +28,28 @@ def ctx():
     c.close()
 
 
-FAST = ["tile", None]
-FAST_IDS = ["tile", "auto_p1rows"]
+# None = what AUTO picks (p1rows.cu: vertex tables per block + the row kernel); the two environment knobs select its other
+# kernels: the streamed one (TMA producer warp) and the one without vertex tables (meshes whose blocks refer to more than
+# 512 vertices fall back to it)
+FAST = ["tile", None, "auto+TFELCU_P1STREAM", "auto+TFELCU_NO_VTAB"]
+FAST_IDS = ["tile", "auto_p1rows", "p1rows_streamed", "p1rows_offsets"]
+
+
+def _pick(scatter, monkeypatch):
+    """scatter argument of Matrix(...) for one FAST entry; sets the environment knob of the entry for this test"""
+    if scatter is not None and scatter.startswith("auto+"):
+        monkeypatch.setenv(scatter.split("+")[1], "1")
+        monkeypatch.setenv("TFELCU_NO_POOL", "1")     # structures built under another knob must not be re-issued
+        return None
+    return scatter
 
 
 @pytest.mark.parametrize("scatter", FAST, ids=FAST_IDS)
 @pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 57, 130, 257])
-def test_tile_matches_oracle(ctx, n, scatter):
+def test_tile_matches_oracle(ctx, n, scatter, monkeypatch):
     """configs[0] / [1] shape at sizes around the tile edges (16 x 16 vertices per tile): structure bit-exact, values and
     the fused right-hand side to 1e-12"""
+    scatter = _pick(scatter, monkeypatch)
     p = problems.poisson("p1", n)
     ref = oracle_runner.run(p)
     got = cuda_runner.run(ctx, p, scatter=scatter)
@@ -71,9 +84,10 @@ ANISO = [dict(test=(0, 1), trial=(0, 1), c=2.0), dict(test=(0, 2), trial=(0, 2),
 @pytest.mark.parametrize("terms", [STIFF, MASS, STIFF + MASS, ANISO, MIXED],
                          ids=["stiffness", "mass", "stiffness_plus_mass", "anisotropic", "all_tensor_blocks"])
 @pytest.mark.parametrize("dirichlet", [True, False])
-def test_tile_equals_rows_on_a_distorted_mesh(ctx, terms, dirichlet, fast):
+def test_tile_equals_rows_on_a_distorted_mesh(ctx, terms, dirichlet, fast, monkeypatch):
     """general triangles (jittered vertices), every block of the constant-coefficient tensor (value x value, value x
     gradient, gradient x value, gradient x gradient): tile == owner-computes rows up to the order of the additions"""
+    fast = _pick(fast, monkeypatch)
     out = {}
     for key, scatter in (("rows", "rows"), ("fast", fast)):
         m, sp, A, b = _forms(ctx, 75, scatter, jitter=0.6, dirichlet=dirichlet)
@@ -87,7 +101,8 @@ def test_tile_equals_rows_on_a_distorted_mesh(ctx, terms, dirichlet, fast):
 
 
 @pytest.mark.parametrize("scatter", FAST, ids=FAST_IDS)
-def test_fast_paths_are_bitwise_reproducible(ctx, scatter):
+def test_fast_paths_are_bitwise_reproducible(ctx, scatter, monkeypatch):
+    scatter = _pick(scatter, monkeypatch)
     runs = []
     for _ in range(2):
         m, sp, A, b = _forms(ctx, 200, scatter, jitter=0.4)
@@ -99,9 +114,10 @@ def test_fast_paths_are_bitwise_reproducible(ctx, scatter):
 
 
 @pytest.mark.parametrize("scatter", FAST, ids=FAST_IDS)
-def test_fused_linear_form_equals_separate_pass(ctx, scatter):
+def test_fused_linear_form_equals_separate_pass(ctx, scatter, monkeypatch):
     """b += ... right after a += ... rides along in the same pass; looking at the matrix in between launches the += on
     its own and the linear form takes its usual kernel: same vector up to the order of the additions"""
+    scatter = _pick(scatter, monkeypatch)
     m, sp, A, b = _forms(ctx, 90, scatter, jitter=0.5)
     A.assemble("qf5pT", STIFF)
     b.assemble("qf5pT", [dict(test=(0, 0), c=2.5)])
@@ -123,7 +139,8 @@ def test_fused_linear_form_equals_separate_pass(ctx, scatter):
 
 
 @pytest.mark.parametrize("scatter", FAST, ids=FAST_IDS)
-def test_tile_accumulate_twice_and_clear(ctx, scatter):
+def test_tile_accumulate_twice_and_clear(ctx, scatter, monkeypatch):
+    scatter = _pick(scatter, monkeypatch)
     m, sp, A, b = _forms(ctx, 40, scatter)
     A.assemble("qf5pT", STIFF)
     rp, ci, v1 = A.csr()

@@ -169,7 +169,8 @@ k_ell_vertex_table(size_t row_begin, size_t row_end, const unsigned int* __restr
   for (unsigned q = 0; q < nm; ++q) key[at + q] = mine[q];
   __syncthreads();
   uint32_t* out = vt_list + vt_ptr[blockIdx.x];
-  for (unsigned e = threadIdx.x; e < nu_pad; e += kEllRows) out[e] = key[e < nu ? e : (nu ? nu - 1 : 0)];   // padding: a valid id
+  const unsigned allotted = vt_ptr[blockIdx.x + 1] - vt_ptr[blockIdx.x];     // >= nu_pad (uniform tables: the largest one)
+  for (unsigned e = threadIdx.x; e < allotted; e += kEllRows) out[e] = nu ? key[e < nu ? e : nu - 1] : 0u;   // padding: a valid id
   auto find = [&](uint32_t v) {
     unsigned lo = 0, hi = nu;
     while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (key[mid] < v) lo = mid + 1; else hi = mid; }
@@ -192,6 +193,7 @@ struct P1Rows {
   int b_init;           // 1: its clear() is pending: write the entries
   const unsigned int* vt_ptr; const uint32_t* vt_list;   // LOCALV: vertex tables of the blocks
   int stage_doubles;    // LOCALV: the coordinates of the block's table follow the stage at this (even) offset
+  unsigned int uni_deg, uni_vt;   // LOCALV, both > 0: record lines / table entries per block are uniform
   const int4* desc;     // LOCALV: two int4 per block: (first record line, records per row, table offset, table entries),
                         //         (first CSR entry of the block, entries of the block, -, -)
 };
@@ -230,7 +232,7 @@ __device__ __forceinline__ void p1_row_from_corners(const P1Form& F, double2 p0,
 }
 
 // SHAPE: 0 any constant-coefficient form, 1 gradient x gradient terms only, 2 isotropic (P1Form::iso; compact records)
-template <bool FUSE_B, int SHAPE, bool COMPACT, bool LOCALV = false, int MINB = (SHAPE == 2 ? (LOCALV ? 10 : 8) : 1), int AHEAD = 8>
+template <bool FUSE_B, int SHAPE, bool COMPACT, bool LOCALV = false, int MINB = (SHAPE == 2 ? (LOCALV ? 10 : 8) : 1), int AHEAD = ((LOCALV && SHAPE == 2) ? 6 : 8)>
 __global__ void __launch_bounds__(kEllRows, MINB)
 k_assemble_p1_ell(const __grid_constant__ P1Form F, const P1Rows B) {
   static_assert(COMPACT || !LOCALV, "vertex tables go with the compact records");
@@ -247,7 +249,13 @@ k_assemble_p1_ell(const __grid_constant__ P1Form F, const P1Rows B) {
   // and the table ids right behind it, the table's coordinates go global -> shared without a register round trip
   // (cp.async), and the stage is cleared while all of that is in flight.
   int4 d0 = make_int4(0, 0, 0, 0), d1 = d0;
-  if (LOCALV) { d0 = __ldg(B.desc + 2 * (size_t)blockIdx.x); d1 = __ldg(B.desc + 2 * (size_t)blockIdx.x + 1); }
+  if (LOCALV) {
+    d1 = __ldg(B.desc + 2 * (size_t)blockIdx.x + 1);
+    // uniform layout: where the block's records and table are follows from its index -- they are requested without
+    // waiting for the descriptor, which then only carries the extent of the CSR segment
+    if (B.uni_deg) d0 = make_int4((int)(blockIdx.x * B.uni_deg), (int)B.uni_deg, (int)(blockIdx.x * B.uni_vt), (int)B.uni_vt);
+    else d0 = __ldg(B.desc + 2 * (size_t)blockIdx.x);
+  }
   int rs = 0;
   bool dir = false;
   if (r < r1) { rs = B.rowptr[r + to_local]; dir = B.dir_row[(size_t)B.off_te + r] != 0; }
@@ -615,6 +623,20 @@ static bool build_ell(tfelcu_matrix* m) {
   ctx->zero(m->ell_deg.p, n_blocks + 1);
   k_ell_degree<<<(unsigned)n_blocks, kEllRows, 0, ctx->stream>>>(te->adj_ptr.p, rb, re, m->ell_deg.p);
   ctx->count(); TFELCU_LAUNCH_CHECK();
+  // nearly uniform degrees (structured meshes: 6 almost everywhere): pad every block to the largest one, so that a CTA
+  // finds its record lines at block * degree without reading a pointer first
+  m->ell_uni_deg = 0;
+  {
+    std::vector<unsigned int> h_deg(n_blocks + 1, 0u);
+    ctx->download(h_deg.data(), m->ell_deg.p, n_blocks);
+    unsigned long long sum = 0; unsigned int mx = 0;
+    for (size_t b = 0; b < n_blocks; ++b) { sum += h_deg[b]; mx = std::max(mx, h_deg[b]); }
+    if (mx > 0 && (double)mx * (double)n_blocks <= 1.08 * (double)sum && !std::getenv("TFELCU_NO_UNIFORM")) {
+      for (size_t b = 0; b < n_blocks; ++b) h_deg[b] = mx;
+      ctx->upload(m->ell_deg.p, h_deg.data(), n_blocks + 1);
+      m->ell_uni_deg = mx;
+    }
+  }
   exclusive_sum<unsigned int, unsigned int>(ctx, m->ell_deg.p, m->ell_ptr.p, n_blocks + 1);
   unsigned int total = 0; ctx->download(&total, m->ell_ptr.p + n_blocks, 1);
   // compact 8-byte records when the dofs are the vertex ids and the offsets / slots fit their fields
@@ -651,6 +673,18 @@ static bool build_ell(tfelcu_matrix* m) {
     int h_bad = 0; ctx->download(&h_bad, bad.p, 1);
     if (!h_bad) {
       m->vt_ptr.alloc(n_blocks + 1);
+      m->vt_uni = 0;
+      if (m->ell_uni_deg) {   // the same for the tables
+        std::vector<unsigned int> h_cnt(n_blocks + 1, 0u);
+        ctx->download(h_cnt.data(), cnt.p, n_blocks);
+        unsigned long long sum = 0; unsigned int mx = 0;
+        for (size_t b = 0; b < n_blocks; ++b) { sum += h_cnt[b]; mx = std::max(mx, h_cnt[b]); }
+        if (mx > 0 && (double)mx * (double)n_blocks <= 1.08 * (double)sum) {
+          for (size_t b = 0; b < n_blocks; ++b) h_cnt[b] = mx;
+          ctx->upload(cnt.p, h_cnt.data(), n_blocks + 1);
+          m->vt_uni = mx;
+        }
+      }
       exclusive_sum<unsigned int, unsigned int>(ctx, cnt.p, m->vt_ptr.p, n_blocks + 1);
       unsigned int n_list = 0; ctx->download(&n_list, m->vt_ptr.p + n_blocks, 1);
       m->vt_list.alloc((size_t)n_list + 1);
@@ -699,6 +733,7 @@ bool assemble_p1_rows(tfelcu_matrix* m, const FormBuild& fb, tfelcu_vector* v, c
     B.vt_ptr = m->vt_ptr.p; B.vt_list = m->vt_list.p;
     B.stage_doubles = (int)((m->max_block_nnz + 1) & ~(size_t)1);
     B.desc = reinterpret_cast<const int4*>(m->ell_desc.p);
+    B.uni_deg = (m->ell_uni_deg && m->vt_uni) ? m->ell_uni_deg : 0u; B.uni_vt = B.uni_deg ? m->vt_uni : 0u;
     const size_t smem_bytes = local ? (size_t)B.stage_doubles * sizeof(double) + (size_t)kVtCap * sizeof(double2) : stage_bytes;
     if (v) v->zero_pending = false;
     const unsigned grid = grid_for(re - rb, kEllRows);
@@ -746,19 +781,7 @@ bool assemble_p1_rows(tfelcu_matrix* m, const FormBuild& fb, tfelcu_vector* v, c
       case 5: TFELCU_P1C(false, 2); break;
       case 8: TFELCU_P1(true, 0, false, false); break;  case 9: TFELCU_P1C(true, 0); break;
       case 10: TFELCU_P1(true, 1, false, false); break; case 11: TFELCU_P1C(true, 1); break;
-      case 13: {
-        const char* var = std::getenv("TFELCU_P1_VARIANT");   // experiment: occupancy against spills / prefetch depth
-        const int vs = (var && local) ? std::atoi(var) : 0;
-#define TFELCU_P1V(MB, AH)                                                                                          \
-        do {                                                                                                         \
-          ensure_smem(k_assemble_p1_ell<true, 2, true, true, MB, AH>, smem_bytes);                                   \
-          k_assemble_p1_ell<true, 2, true, true, MB, AH><<<grid, kEllRows, smem_bytes, ctx->stream>>>(F, B);         \
-        } while (0)
-        if (vs == 1) TFELCU_P1V(12, 8); else if (vs == 2) TFELCU_P1V(12, 4); else if (vs == 3) TFELCU_P1V(14, 4);
-        else if (vs == 4) TFELCU_P1V(10, 4); else if (vs == 5) TFELCU_P1V(8, 8); else TFELCU_P1C(true, 2);
-#undef TFELCU_P1V
-        break;
-      }
+      case 13: TFELCU_P1C(true, 2); break;
       default: fail("p1 rows: unexpected kernel selection");
     }
 #undef TFELCU_P1C

@@ -165,7 +165,7 @@ void matrix_build_pattern(tfelcu_matrix* m) {
   m->recs.clear();
   m->tile_refused = false;
   m->has_ell = false; m->ell.release(); m->ell_ptr.release(); m->ell_deg.release();
-  m->ell_local = false; m->vt_ptr.release(); m->vt_list.release(); m->ell_desc.release();
+  m->ell_local = false; m->vt_ptr.release(); m->vt_list.release(); m->ell_desc.release(); m->ell_uni_deg = 0; m->vt_uni = 0;
   static uint64_t next_pattern_id = 0;   // one host thread drives a context (API not re-entrant)
   m->pattern_id = ++next_pattern_id;
 }

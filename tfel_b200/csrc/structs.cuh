@@ -219,7 +219,9 @@ struct tfelcu_matrix {
   tfelcu::DevBuf<unsigned int> vt_ptr;  // [n_blocks + 1] start of a block's table in vt_list
   tfelcu::DevBuf<uint32_t> vt_list;     // ascending vertex ids every record of the block refers to (padded to 4 entries)
   tfelcu::DevBuf<int32_t> ell_desc;      // int4 per block for the streamed kernel
-  unsigned int ell_deg_max = 0, vt_max = 0;   // largest degree / table over the blocks (shared-memory sizes of the streamed kernel)
+  unsigned int ell_deg_max = 0, vt_max = 0;
+  unsigned int ell_uni_deg = 0, vt_uni = 0;   // > 0: every block holds this many record lines / table entries (padded): a
+                                              // CTA addresses both from its block index alone   // largest degree / table over the blocks (shared-memory sizes of the streamed kernel)
   ~tfelcu_matrix() {
     if (tile_plan) tfelcu::tile_plan_free(tile_plan);
     if (pending) tfelcu::form_build_free(pending);

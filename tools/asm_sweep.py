@@ -32,7 +32,7 @@ SRC = [dict(test=(0, 0))]
 ref = None
 for cfg in a.configs:
     for k in list(os.environ):
-        if k.startswith("TFELCU_P1_") or k in ("TFELCU_NO_VTAB", "TFELCU_P1STREAM"): os.environ.pop(k)
+        if k.startswith("TFELCU_P1_") or k in ("TFELCU_NO_VTAB", "TFELCU_P1STREAM", "TFELCU_NO_UNIFORM"): os.environ.pop(k)
     envs = cfg.split("+")[1:]            # auto+TFELCU_P1_MINB=9: environment knobs of one configuration
     for kv in envs:
         k, v = kv.split("=")
