@@ -102,21 +102,25 @@ k_ell_fill_compact(const uint32_t* __restrict__ adj_ptr, size_t a_begin, size_t 
 // -- one gather per distinct vertex instead of two per (row, cell) -- and the records then hold 9-bit indices into it.
 // PASS 0: count (and refuse more than kVtCap); PASS 1: write the list and rewrite the records in place.
 constexpr int kVtCap = 512;          // 9-bit indices; 8 KB of coordinates per CTA
-constexpr int kVtSort = 4096;        // 128 rows x up to 16 records x 2 vertices
 
-template <int PASS>
+// k_ell_vertex_sets: one CTA per block sorts the vertex ids of its records (shared-memory bitonic sort over NSORT >= 2 D 128
+// keys), writes the distinct ones to scratch[block * kVtCap ...] and their number to raw_cnt (padded number to vt_cnt).
+// k_ell_vertex_tables: copies a block's list to its place in vt_list (padded with its last id to the allotted length) and
+// rewrites the block's records in place: vertex offsets -> indices into the list.
+template <int NSORT>
 __global__ void __launch_bounds__(kEllRows)
-k_ell_vertex_table(size_t row_begin, size_t row_end, const unsigned int* __restrict__ ptr, const unsigned int* __restrict__ deg,
-                   unsigned long long* __restrict__ ell, unsigned int* __restrict__ vt_cnt, const unsigned int* __restrict__ vt_ptr,
-                   uint32_t* __restrict__ vt_list, int* __restrict__ bad) {
-  __shared__ uint32_t key[kVtSort];
+k_ell_vertex_sets(size_t row_begin, size_t row_end, const unsigned int* __restrict__ ptr, const unsigned int* __restrict__ deg,
+                  const unsigned long long* __restrict__ ell, unsigned int* __restrict__ raw_cnt, unsigned int* __restrict__ vt_cnt,
+                  uint32_t* __restrict__ scratch, int* __restrict__ bad) {
+  constexpr int kChunk = NSORT / kEllRows;
+  __shared__ uint32_t key[NSORT];
+  __shared__ unsigned int chunk[kEllRows];
   __shared__ unsigned int n_unique;
   const size_t r = row_begin + blockIdx.x * (size_t)kEllRows + threadIdx.x;
   const unsigned D = deg[blockIdx.x];
-  unsigned long long* rec = ell + (size_t)ptr[blockIdx.x] * kEllRows + threadIdx.x;
-  if (2u * D * kEllRows > (unsigned)kVtSort) { if (threadIdx.x == 0) { atomicExch(bad, 1); if (PASS == 0) vt_cnt[blockIdx.x] = 0; } return; }
-  for (int e = threadIdx.x; e < kVtSort; e += kEllRows) key[e] = 0xffffffffu;
-  if (threadIdx.x == 0) n_unique = 0;
+  const unsigned long long* rec = ell + (size_t)ptr[blockIdx.x] * kEllRows + threadIdx.x;
+  if (2u * D * kEllRows > (unsigned)NSORT) { if (threadIdx.x == 0) { atomicExch(bad, 1); raw_cnt[blockIdx.x] = 0; vt_cnt[blockIdx.x] = 0; } return; }
+  for (int e = threadIdx.x; e < NSORT; e += kEllRows) key[e] = 0xffffffffu;
   __syncthreads();
   const long long rl = (long long)r;
   for (unsigned k = 0; k < D; ++k) {
@@ -126,9 +130,9 @@ k_ell_vertex_table(size_t row_begin, size_t row_end, const unsigned int* __restr
     key[(2 * k + 1) * kEllRows + threadIdx.x] = (uint32_t)(rl + (((long long)(c << 22)) >> 43));
   }
   __syncthreads();
-  for (int k = 2; k <= kVtSort; k <<= 1)                      // bitonic sort, ascending (padding last)
+  for (int k = 2; k <= NSORT; k <<= 1)                        // bitonic sort, ascending (padding last)
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < kVtSort; t += kEllRows) {
+      for (int t = threadIdx.x; t < NSORT; t += kEllRows) {
         const int u = t ^ j;
         if (u > t) {
           const uint32_t a = key[t], b = key[u];
@@ -138,12 +142,11 @@ k_ell_vertex_table(size_t row_begin, size_t row_end, const unsigned int* __restr
       }
       __syncthreads();
     }
-  // distinct values to the front (stable: one thread per chunk of 32, ranks by a scan over the chunk counts)
-  __shared__ unsigned int chunk[kEllRows + 1];
+  // distinct values: one thread per chunk of consecutive keys, ranks by a scan over the chunk counts
+  auto distinct = [&](int e) { return key[e] != 0xffffffffu && (e == 0 || key[e - 1] != key[e]); };
   {
     unsigned c = 0;
-    for (int e = threadIdx.x * 32; e < threadIdx.x * 32 + 32; ++e)
-      if (key[e] != 0xffffffffu && (e == 0 || key[e - 1] != key[e])) ++c;
+    for (int e = threadIdx.x * kChunk; e < (threadIdx.x + 1) * kChunk; ++e) c += distinct(e) ? 1u : 0u;
     chunk[threadIdx.x] = c;
   }
   __syncthreads();
@@ -154,28 +157,37 @@ k_ell_vertex_table(size_t row_begin, size_t row_end, const unsigned int* __restr
   }
   __syncthreads();
   const unsigned nu = n_unique;
-  const unsigned nu_pad = (nu + 3u) & ~3u;     // 16-byte granules: the streamed kernel fetches a table with one bulk copy
-  if (PASS == 0) {
-    if (threadIdx.x == 0) { vt_cnt[blockIdx.x] = nu_pad; if (nu_pad > (unsigned)kVtCap) atomicExch(bad, 1); }
-    return;
+  if (threadIdx.x == 0) {
+    raw_cnt[blockIdx.x] = nu;
+    vt_cnt[blockIdx.x] = (nu + 3u) & ~3u;                     // 16-byte granules (bulk copies of the streamed kernel)
+    if (((nu + 3u) & ~3u) > (unsigned)kVtCap) atomicExch(bad, 1);
   }
-  // PASS 1: compact into a second array (the tail of key[] is padding once nu <= kVtCap <= kVtSort / 2 ... not in general:
-  // use registers: every thread collects its chunk's distinct values first, then all write after a barrier)
-  uint32_t mine[32]; unsigned nm = 0;
-  for (int e = threadIdx.x * 32; e < threadIdx.x * 32 + 32; ++e)
-    if (key[e] != 0xffffffffu && (e == 0 || key[e - 1] != key[e])) mine[nm++] = key[e];
-  const unsigned at = chunk[threadIdx.x];
-  __syncthreads();
-  for (unsigned q = 0; q < nm; ++q) key[at + q] = mine[q];
+  if (nu > (unsigned)kVtCap) return;
+  uint32_t* out = scratch + (size_t)blockIdx.x * kVtCap;
+  unsigned at = chunk[threadIdx.x];
+  for (int e = threadIdx.x * kChunk; e < (threadIdx.x + 1) * kChunk; ++e) if (distinct(e)) out[at++] = key[e];
+}
+
+__global__ void __launch_bounds__(kEllRows)
+k_ell_vertex_tables(size_t row_begin, size_t row_end, const unsigned int* __restrict__ ptr, const unsigned int* __restrict__ deg,
+                    unsigned long long* __restrict__ ell, const unsigned int* __restrict__ raw_cnt, const unsigned int* __restrict__ vt_ptr,
+                    const uint32_t* __restrict__ scratch, uint32_t* __restrict__ vt_list) {
+  __shared__ uint32_t key[kVtCap];
+  const size_t r = row_begin + blockIdx.x * (size_t)kEllRows + threadIdx.x;
+  const unsigned D = deg[blockIdx.x];
+  const unsigned nu = raw_cnt[blockIdx.x];
+  unsigned long long* rec = ell + (size_t)ptr[blockIdx.x] * kEllRows + threadIdx.x;
+  for (unsigned e = threadIdx.x; e < nu; e += kEllRows) key[e] = scratch[(size_t)blockIdx.x * kVtCap + e];
   __syncthreads();
   uint32_t* out = vt_list + vt_ptr[blockIdx.x];
-  const unsigned allotted = vt_ptr[blockIdx.x + 1] - vt_ptr[blockIdx.x];     // >= nu_pad (uniform tables: the largest one)
+  const unsigned allotted = vt_ptr[blockIdx.x + 1] - vt_ptr[blockIdx.x];     // >= nu rounded up (uniform tables: the largest one)
   for (unsigned e = threadIdx.x; e < allotted; e += kEllRows) out[e] = nu ? key[e < nu ? e : nu - 1] : 0u;   // padding: a valid id
   auto find = [&](uint32_t v) {
     unsigned lo = 0, hi = nu;
     while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (key[mid] < v) lo = mid + 1; else hi = mid; }
     return (unsigned long long)lo;
   };
+  const long long rl = (long long)r;
   for (unsigned k = 0; k < D; ++k) {
     const unsigned long long c = rec[(size_t)k * kEllRows];
     if (!(c >> 63) || r >= row_end) continue;
@@ -664,11 +676,21 @@ static bool build_ell(tfelcu_matrix* m) {
   ctx->count(); TFELCU_LAUNCH_CHECK();
   m->ell_local = false;
   if (m->ell_compact && !std::getenv("TFELCU_NO_VTAB")) {
-    DevBuf<unsigned int> cnt(n_blocks + 1);
+    DevBuf<unsigned int> cnt(n_blocks + 1), raw_cnt(n_blocks + 1);
+    DevBuf<uint32_t> scratch(n_blocks * (size_t)kVtCap);      // the distinct ids of every block, until the tables are laid out
     DevBuf<int> bad(1);
     ctx->zero(cnt.p, n_blocks + 1); ctx->zero(bad.p, 1);
     unsigned long long* ell = reinterpret_cast<unsigned long long*>(m->ell.p);
-    k_ell_vertex_table<0><<<(unsigned)n_blocks, kEllRows, 0, ctx->stream>>>(rb, re, m->ell_ptr.p, m->ell_deg.p, ell, cnt.p, nullptr, nullptr, bad.p);
+    unsigned int deg_max = 0;
+    {
+      std::vector<unsigned int> h_deg(n_blocks);
+      ctx->download(h_deg.data(), m->ell_deg.p, n_blocks);
+      for (size_t b = 0; b < n_blocks; ++b) deg_max = std::max(deg_max, h_deg[b]);
+    }
+    if (2u * deg_max * kEllRows <= 2048u)
+      k_ell_vertex_sets<2048><<<(unsigned)n_blocks, kEllRows, 0, ctx->stream>>>(rb, re, m->ell_ptr.p, m->ell_deg.p, ell, raw_cnt.p, cnt.p, scratch.p, bad.p);
+    else
+      k_ell_vertex_sets<4096><<<(unsigned)n_blocks, kEllRows, 0, ctx->stream>>>(rb, re, m->ell_ptr.p, m->ell_deg.p, ell, raw_cnt.p, cnt.p, scratch.p, bad.p);
     ctx->count(); TFELCU_LAUNCH_CHECK();
     int h_bad = 0; ctx->download(&h_bad, bad.p, 1);
     if (!h_bad) {
@@ -688,8 +710,8 @@ static bool build_ell(tfelcu_matrix* m) {
       exclusive_sum<unsigned int, unsigned int>(ctx, cnt.p, m->vt_ptr.p, n_blocks + 1);
       unsigned int n_list = 0; ctx->download(&n_list, m->vt_ptr.p + n_blocks, 1);
       m->vt_list.alloc((size_t)n_list + 1);
-      k_ell_vertex_table<1><<<(unsigned)n_blocks, kEllRows, 0, ctx->stream>>>(rb, re, m->ell_ptr.p, m->ell_deg.p, ell, cnt.p, m->vt_ptr.p,
-                                                                            m->vt_list.p, bad.p);
+      k_ell_vertex_tables<<<(unsigned)n_blocks, kEllRows, 0, ctx->stream>>>(rb, re, m->ell_ptr.p, m->ell_deg.p, ell, raw_cnt.p, m->vt_ptr.p,
+                                                                           scratch.p, m->vt_list.p);
       ctx->count(); TFELCU_LAUNCH_CHECK();
       m->ell_local = true;
       // extents and block descriptors of the streamed kernel
