@@ -77,7 +77,7 @@ struct Ilu0 {
   DevBuf<int> stuck, rowdone;
   DevBuf<double> ytmp;                   // result of the forward sweep
   int lanes = 8;                         // lanes per row of the triangular sweeps
-  int gate_sleep_ns = 200;               // pause between two reads at the gate of a row (< 0: no gate)
+  int gate_sleep_ns = 0;                 // pause between two reads at the gate of a row (< 0: no gate)
   size_t tri_smem = 0;                   // dynamic shared memory that limits the CTAs per SM of the sweeps (0: no limit)
   int zero_pivot_row = -1;
   int n_levels_l = 0, n_levels_u = 0;    // depth of the dependency graphs of the two sweeps
