@@ -1,15 +1,19 @@
 // Owner-computes rows for constant-coefficient forms on P1 triangles (configs[0] and [1]): the row kernel of assemble.cu
 // (bilinear_form.hpp:64-109 restricted to the cells that touch a row, in ascending cell order) with
 //   * the element matrix row in closed form (p1form.cuh) instead of the contraction of a pre-integrated tensor staged in
-//     shared memory: 178 -> ~90 instructions per (row, cell);
-//   * the packed 16-byte (cell vertices | slots | local dof) records in a blocked ELL layout -- record k of the 128 rows of
-//     a CTA back to back -- so that a warp reads 512 contiguous bytes per step instead of 32 records 96 bytes apart
-//     (ncu on the CSR-ordered records: 17 sectors per load request);
+//     shared memory: 178 -> 88 instructions per (row, cell);
+//   * one 8-byte record per (row, cell) -- two vertex references, three CSR slots, local index, valid bit -- in a blocked
+//     ELL layout (record k of the 128 rows of a CTA is one 1 KB line; 16-byte records where the fields do not fit);
+//   * per-block vertex tables: the coordinates of the ~390 distinct vertices a block refers to are fetched once into
+//     shared memory (cp.async), the records index them with 9 bits;
+//   * a CTA head that is one load level deep (uniform block layout + one descriptor), see k_assemble_p1_ell;
 //   * a constant-coefficient linear form without derivatives on the same space riding along (linear_form.hpp:20-142:
-//     b_i += |K| sum_q w_q f psi_i): the row thread has the cell volumes anyway, the second pass over the mesh (0.52 ms of
-//     1.35 ms on configs[1]) disappears.
+//     b_i += |K| sum_q w_q f psi_i): the row thread has the cell volumes anyway, the second pass over the mesh disappears.
 // Same stage / write-out as k_assemble_rows: every stored value is written once, coalesced; no atomics; the additions to
-// an entry happen in ascending cell order (bitwise reproducible).
+// an entry happen in ascending cell order (bitwise reproducible, bitwise equal to k_assemble_rows).
+// configs[1] (n = 4096), A and b: 1.345 ms (round 1, two generic kernels) -> 0.494 ms; profiles/r02_ncu_p1rows_tile.md.
+// Environment knobs (measurement only): TFELCU_NO_COMPACT, TFELCU_NO_VTAB, TFELCU_NO_UNIFORM, TFELCU_NO_ISO select the
+// fallback layouts / kernels; TFELCU_P1STREAM=1 the streamed kernel (TFELCU_P1_STAGES, TFELCU_P1_CTAS: its ring / residency).
 #include "p1form.cuh"
 #include "tma.cuh"
 #include "sortutil.cuh"
