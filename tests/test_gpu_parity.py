@@ -220,10 +220,12 @@ def test_ilu0_factors_match_oracle(ctx):
     # ILU(0) of the indefinite Navier-Stokes matrix is so ill-conditioned that a 1e-11 preconditioned residual
     # leaves a 1e-7 error (the oracle's ILU(0)-GMRES behaves the same): full GMRES with Jacobi scaling instead
     (problems.navier_stokes(8), dict(method="gmres", precond="jacobi", restart=900)),
+    # the solver every reference program configures (solver.hpp:139-163: GMRES(1000) + ILU(ilufill = 2))
+    (problems.stokes(10), dict(method="gmres", precond="ilu", ilufill=2, restart=1000)),
     (problems.tet("p2", 4), dict(method="cg", precond="block_jacobi", block_size=4)),
     (problems.tet("p1", 6), dict(method="gmres", precond="jacobi", restart=100)),
     (problems.laplace2(12), dict(method="gmres", precond="none", restart=50)),
-], ids=["stokes", "ns", "tet_p2", "tet_p1", "laplace2"])
+], ids=["stokes", "ns", "stokes_gmres_ilu2", "tet_p2", "tet_p1", "laplace2"])
 def test_solution_parity(ctx, problem, kw):
     from tfel_b200 import capi
     ref = oracle_runner.run(problem)
@@ -241,6 +243,33 @@ def test_solution_parity(ctx, problem, kw):
         s.close()
         assert rep["converged"] == 1, rep
         assert np.linalg.norm(x - x_ref) <= 1e-8 * np.linalg.norm(x_ref), rep
+    finally:
+        cuda_runner.close(B)
+
+
+def test_navier_stokes_with_the_configured_solver(ctx):
+    """configs[4] with the solver the reference program configures (test/navier_stokes_2d_p2_p1.cpp:246-254: GMRES(1000) +
+    ILU(2), left preconditioned, rtol 1e-8) on the parity fixture's matrix (synthetic, large previous iterates: strongly
+    indefinite). What is checked is that the device solver BEHAVES like the restated reference solver: same iteration count
+    (+-2; measured 43 = 43) and the same iterate (measured 4e-4 relative; the incomplete factors of this matrix are nearly
+    singular, so the preconditioned residual both solvers stop on says little about the error -- either iterate is O(1)
+    away from the direct solve, which is why `test_solution_parity[ns]` uses Jacobi). The Newton systems of the real
+    program are benign: examples/navier_stokes_2d_p2_p1.cpp converges quadratically with this solver
+    (test_cpp_surface.py, profiles/r02_ns_n128_100steps.log)."""
+    from tfel_b200 import capi
+    problem = problems.navier_stokes(8)
+    ref = oracle_runner.run(problem)
+    a = (ref["csr_rowptr"], ref["csr_colind"], ref["csr_val"])
+    x_orc, its_orc, _ = orc.gmres_ilu(*a, ref["rhs"], restart=1000, levels=2, rtol=1e-8, maxits=2000)
+    B = cuda_runner.build(ctx, problem)
+    try:
+        cuda_runner.assemble(B)
+        s = capi.Solver(ctx, method="gmres", precond="ilu", ilufill=2, restart=1000, maxits=2000, rtol=1e-8)
+        x, rep = B.matrix.solve(B.vector, s)
+        s.close()
+        assert rep["converged"] == 1 and rep["ilu_levels"] == 2, rep
+        assert abs(int(rep["its"]) - its_orc) <= 2, (rep, its_orc)
+        assert np.linalg.norm(x - x_orc) <= 1e-2 * np.linalg.norm(x_orc)
     finally:
         cuda_runner.close(B)
 
