@@ -564,13 +564,17 @@ k_mgs_step(double* __restrict__ w, const double* __restrict__ v_prev, const doub
   if (threadIdx.x == 0) partial_next[blockIdx.x] = t;
 }
 
+// The Hessenberg matrix is stored packed: column k holds its k + 2 entries at k (k + 3) / 2 (restart 1000: 4 MB instead of
+// 8; restart = maxits = 20000: 1.6 GB instead of 3.2)
+__host__ __device__ __forceinline__ size_t hess_col(size_t k) { return k * (k + 3) / 2; }
+
 // Givens rotations of column k of the Hessenberg matrix + residual estimate + stopping test (one thread).
 // H is stored column-major with leading dimension m + 1.
 __global__ void k_gmres_givens(double* __restrict__ H, double* __restrict__ cs, double* __restrict__ sn, double* __restrict__ g,
                                const double* __restrict__ partial_norm, int np, int k, int m, uint32_t maxits,
                                GmresDev* __restrict__ G) {
   if (blockIdx.x || threadIdx.x >= 32 || G->done) return;
-  double* Hk = H + (size_t)k * (m + 1);
+  double* Hk = H + hess_col((size_t)k);
   const double hn = sqrt(warp_sum_fixed(partial_norm, np));
   if (threadIdx.x) return;
   Hk[k + 1] = hn;
@@ -600,14 +604,14 @@ k_gmres_backsolve(const double* __restrict__ H, const double* __restrict__ g, in
   __shared__ double red[256 / 32];
   for (int i = k - 1; i >= 0; --i) {
     double acc = 0.0;
-    for (int j = i + 1 + threadIdx.x; j < k; j += 256) acc += H[(size_t)j * (m + 1) + i] * y[j];
+    for (int j = i + 1 + threadIdx.x; j < k; j += 256) acc += H[hess_col((size_t)j) + i] * y[j];
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
       double t = 0.0;
       for (int w = 0; w < 8; ++w) t += red[w];
-      y[i] = (g[i] - t) / H[(size_t)i * (m + 1) + i];
+      y[i] = (g[i] - t) / H[hess_col((size_t)i) + i];
     }
     __syncthreads();
   }
@@ -675,9 +679,9 @@ void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep) {
   if ((long long)M < wanted && ctx->rank == 0)
     std::fprintf(stderr, "[tfelcu] warning: GMRES restart %lld does not fit in device memory, using restart %d\n", wanted, M);
   TFELCU_REQUIRE((long long)M * 4 >= wanted || M >= 30, "GMRES: the Krylov basis that fits in device memory is far shorter than the requested restart");
-  s->hess.alloc((size_t)(M + 1) * M + 4 * (size_t)(M + 1));
+  s->hess.alloc(hess_col((size_t)M) + 4 * (size_t)(M + 1));
   double* H = s->hess.p;
-  double* cs = H + (size_t)(M + 1) * M;
+  double* cs = H + hess_col((size_t)M);
   double* sn = cs + (M + 1);
   double* g = sn + (M + 1);
   double* y = g + (M + 1);
@@ -738,7 +742,7 @@ void solve_gmres(tfelcu_solver* s, tfelcu_solver_report* rep) {
       double* w = V + (size_t)(k + 1) * ld;
       product(V + (size_t)k * ld, t);
       precond(s, t, w);
-      double* Hk = H + (size_t)k * (M + 1);
+      double* Hk = H + hess_col((size_t)k);
       // MGS: k + 2 fused steps; step j projects out v_{j-1} and starts the product with v_j (the last: with w)
       for (int j = 0; j <= k + 1; ++j) {
         const double* v_prev = j > 0 ? V + (size_t)(j - 1) * ld : nullptr;
