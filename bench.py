@@ -66,6 +66,12 @@ def ncu_traffic(kernel, n, n_gpus):
             return d["dram_read"] + d["dram_write"]
     except Exception:
         pass
+    try:   # N > 1: ncu profiles one process, so the capture is the same kernel at one rank's row count on ONE GPU (a proxy)
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))["per_launch_bytes"]["n_gpus=%d" % n_gpus]
+        if d["n"] == n and d["kernel"] == kernel:
+            return d["dram_read"] + d["dram_write"]
+    except Exception:
+        pass
     return None
 
 
@@ -579,7 +585,9 @@ def run_own(args):
                 "moved_frac": (gbs(moved_bytes) / peak) if spmv_avg_ms else None,
                 "traffic_note": "`achieved` / `frac` divide the ALGORITHMIC bytes of the reference CSR (12 B per stored entry, SURVEY "
                                 "8d) by the kernel time; the kernel streams 16-bit column offsets (10 B per entry: moved_*), so frac "
-                                "can exceed 1 while moved_frac is the bandwidth fraction; ncu DRAM bytes per launch in `traffic`",
+                                "can exceed 1 while moved_frac is the bandwidth fraction; ncu DRAM bytes per launch in `traffic`"
+                                + ("" if world == 1 else " (N > 1: captured on ONE GPU at one rank's row count, profiles/r02_ncu_traffic.json -- ncu "
+                                   "profiles a single process)"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
                 "avg_launch_ms": spmv_avg_ms, "samples_per_solve": int(np.mean(sess.spmv_samples)) if sess.spmv_samples else 0,
                 "frac_of_nominal_8TBs": (gbs(spmv_bytes) / 8000.0) if spmv_avg_ms else None}
